@@ -1,0 +1,1556 @@
+// Device side of the fractional-step time loop: layout conversion, kernels, seam functions.
+// Reference seam being replaced:
+//   explicit  fractionalStep/explicit/Cpp/CUDAcodes.cu            (BCH.cu below)
+//   implicit  fractionalStep/implicit/Cpp/CUDAcodes.cu            (GQ.cu below)
+// and their call sites in blascoCodinaHuerta.cpp (BCH.cpp) / guermondQuartapelle.cpp (GQ.cpp).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace cfdb {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+   char buf[1024];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_err = buf;
+}
+const char* last_error() { return g_err.c_str(); }
+
+// =================================================================================================
+// Sell: host conversion + upload
+// =================================================================================================
+int choose_T(int nrows, long long nnz) {
+   if (nrows <= 0) return 1;
+   const double avg = (double)nnz / nrows;
+   int T = 1;
+   while ((long long)nrows * T < 120000 && T < 8 && avg / (2 * T) >= 8.0) T *= 2;
+   return T;
+}
+
+void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T, SellHost& out) {
+   const int R = 32 / T;
+   const int ns = (nrows + R - 1) / R;
+   Sell& m = out.meta;
+   m.nrows = nrows; m.ncols = ncols; m.T = T; m.R = R; m.nslices = ns; m.nnz = rs[nrows];
+   out.sliceOff.assign((size_t)ns + 1, 0);
+   std::vector<int> width(ns, 0);
+#pragma omp parallel for schedule(static)
+   for (int s = 0; s < ns; s++) {
+      int w = 0;
+      for (int rl = 0; rl < R; rl++) {
+         const int r = s * R + rl;
+         if (r < nrows) w = std::max(w, (rs[r + 1] - rs[r] + T - 1) / T);
+      }
+      width[s] = (w + 1) & ~1;
+   }
+   for (int s = 0; s < ns; s++) out.sliceOff[s + 1] = out.sliceOff[s] + (long long)width[s] * 32;
+   m.padded = out.sliceOff[ns];
+   out.cols.assign((size_t)m.padded, 0);
+   out.perm.assign((size_t)m.nnz, 0);
+#pragma omp parallel for schedule(static)
+   for (int s = 0; s < ns; s++) {
+      const long long off = out.sliceOff[s];
+      const int w = width[s];
+      for (int rl = 0; rl < R; rl++) {
+         const int r = s * R + rl;
+         const int len = (r < nrows) ? rs[r + 1] - rs[r] : 0;
+         const int padcol = len > 0 ? col[rs[r]] : 0;
+         for (int lane = 0; lane < T; lane++) {
+            const int t = rl * T + lane;
+            for (int j = 0; j < w; j++) {
+               const long long pos = off + (long long)(j >> 1) * 64 + 2 * t + (j & 1);
+               const int k = j * T + lane;
+               if (k < len) {
+                  out.cols[pos] = col[rs[r] + k];
+                  out.perm[(size_t)rs[r] + k] = pos;
+               } else {
+                  out.cols[pos] = padcol;
+               }
+            }
+         }
+      }
+   }
+}
+
+int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell& d) {
+   d = h.meta;
+   d.nval = nval;
+   CFD_CK(cudaMalloc(&d.sliceOff, sizeof(long long) * h.sliceOff.size()));
+   CFD_CK(cudaMemcpy(d.sliceOff, h.sliceOff.data(), sizeof(long long) * h.sliceOff.size(), cudaMemcpyHostToDevice));
+   CFD_CK(cudaMalloc(&d.cols, sizeof(int) * std::max<size_t>(h.cols.size(), 2)));
+   CFD_CK(cudaMemcpy(d.cols, h.cols.data(), sizeof(int) * h.cols.size(), cudaMemcpyHostToDevice));
+   std::vector<double> tmp;
+   for (int v = 0; v < nval; v++) {
+      CFD_CK(cudaMalloc(&d.vals[v], sizeof(double) * std::max<size_t>((size_t)d.padded, 2)));
+      if (csrVals && csrVals[v]) {
+         tmp.assign((size_t)d.padded, 0.0);
+         const double* src = csrVals[v];
+#pragma omp parallel for schedule(static)
+         for (long long k = 0; k < d.nnz; k++) tmp[(size_t)h.perm[(size_t)k]] = src[k];
+         CFD_CK(cudaMemcpy(d.vals[v], tmp.data(), sizeof(double) * (size_t)d.padded, cudaMemcpyHostToDevice));
+      } else {
+         CFD_CK(cudaMemset(d.vals[v], 0, sizeof(double) * (size_t)d.padded));
+      }
+   }
+   return CFD_OK;
+}
+
+void sell_free(Sell& s) {
+   cudaFree(s.sliceOff); cudaFree(s.cols);
+   for (int v = 0; v < 3; v++) cudaFree(s.vals[v]);
+   s = Sell();
+}
+
+// =================================================================================================
+// Reference-element tables in constant memory
+// =================================================================================================
+__constant__ double cSv[8][27];       // [k][i]
+__constant__ double cdSv[3][27][8];   // [d][i][k]
+__constant__ double cdSp[3][8][8];    // [d][i][k]
+
+// =================================================================================================
+// Row kernels (one thread per velocity row, T = 1 matrices)
+// =================================================================================================
+
+// y_c = alpha * A x_c + beta * y_c for NV vectors sharing one Sell value array (vectors are
+// component-blocked with stride ldx / ldy).  Multi-RHS: the matrix stream is read once.
+template <int NV>
+__global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const double* __restrict__ x, long long ldx,
+                                                    double* __restrict__ y, long long ldy, double alpha, double beta) {
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = row >> 5, lane = row & 31;
+   if (slice >= A.nslices) return;
+   const double* __restrict__ val = A.vals[vidx];
+   const long long off = A.sliceOff[slice];
+   const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
+   double acc[NV];
+#pragma unroll
+   for (int c = 0; c < NV; c++) acc[c] = 0.0;
+#pragma unroll 2
+   for (int jp = 0; jp < np; jp++) {
+      const long long e = off + ((long long)jp << 6) + 2 * lane;
+      const int2 c2 = ldnc_i2(A.cols + e);
+      const double2 v2 = ldnc_d2(val + e);
+#pragma unroll
+      for (int c = 0; c < NV; c++) acc[c] += v2.x * __ldg(x + c * ldx + c2.x) + v2.y * __ldg(x + c * ldx + c2.y);
+   }
+   if (row < A.nrows) {
+#pragma unroll
+      for (int c = 0; c < NV; c++) {
+         double r = alpha * acc[c];
+         if (beta != 0.0) r += beta * y[c * ldy + row];
+         y[c * ldy + row] = r;
+      }
+   }
+}
+
+// Generic y = alpha*A*x + beta*y for any T (pressure-row matrices), one vector.
+__global__ void __launch_bounds__(256) k_spmv_T(Sell A, int vidx, const double* __restrict__ x, double* __restrict__ y,
+                                                double alpha, double beta) {
+   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = gthread >> 5, lane = gthread & 31;
+   if (slice >= A.nslices) return;
+   const double* __restrict__ val = A.vals[vidx];
+   const long long off = A.sliceOff[slice];
+   const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
+   double acc = 0.0;
+#pragma unroll 2
+   for (int jp = 0; jp < np; jp++) {
+      const long long e = off + ((long long)jp << 6) + 2 * lane;
+      const int2 c2 = ldnc_i2(A.cols + e);
+      const double2 v2 = ldnc_d2(val + e);
+      acc += v2.x * __ldg(x + c2.x) + v2.y * __ldg(x + c2.y);
+   }
+   for (int o = A.T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   const int row = slice * A.R + lane / A.T;
+   if ((lane % A.T) == 0 && row < A.nrows) {
+      double r = alpha * acc;
+      if (beta != 0.0) r += beta * y[row];
+      y[row] = r;
+   }
+}
+
+// step 1 of the explicit scheme, fused (replaces step1GPUpart, BCH.cu:946-973: 6 csrmv + applyVelBC +
+// calculate_UnpHalf):   R1_c = R1_c - K*Uprev_c - G_c*Pn ;  R1[bc] = 0 ;  UnpHalf = Un + dt*R1*MdInv
+__global__ void __launch_bounds__(256) k_step1(Sell K, Sell G, int NN, const double* __restrict__ Uprev,
+                                               const double* __restrict__ Pn, const double* __restrict__ Un,
+                                               const double* __restrict__ MdInv, const int* __restrict__ bcIndex,
+                                               double* __restrict__ R1, double* __restrict__ UnpHalf, double dt) {
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = row >> 5, lane = row & 31;
+   if (slice >= K.nslices) return;
+   double a0 = 0, a1 = 0, a2 = 0;
+   {
+      const double* __restrict__ val = K.vals[0];
+      const long long off = K.sliceOff[slice];
+      const int np = (int)((K.sliceOff[slice + 1] - off) >> 6);
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(K.cols + e);
+         const double2 v2 = ldnc_d2(val + e);
+         a0 += v2.x * __ldg(Uprev + c2.x) + v2.y * __ldg(Uprev + c2.y);
+         a1 += v2.x * __ldg(Uprev + NN + c2.x) + v2.y * __ldg(Uprev + NN + c2.y);
+         a2 += v2.x * __ldg(Uprev + 2 * (long long)NN + c2.x) + v2.y * __ldg(Uprev + 2 * (long long)NN + c2.y);
+      }
+   }
+   {
+      const long long off = G.sliceOff[slice];
+      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(G.cols + e);
+         const double px = __ldg(Pn + c2.x), py = __ldg(Pn + c2.y);
+         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
+         a0 += g1.x * px + g1.y * py;
+         a1 += g2.x * px + g2.y * py;
+         a2 += g3.x * px + g3.y * py;
+      }
+   }
+   if (row < NN) {
+      const bool bc = bcIndex[row] >= 0;
+      const double acc[3] = {a0, a1, a2};
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+         const long long i = (long long)c * NN + row;
+         const double r = bc ? 0.0 : (R1[i] - acc[c]);
+         R1[i] = r;
+         UnpHalf[i] = Un[i] + dt * r * MdInv[i];
+      }
+   }
+}
+
+// step 3 of the explicit scheme, fused (replaces step3GPU, BCH.cu:1029-1060: 3 csrmv + calculate_R3 +
+// applyVelBC + multiplyVectors + calculate_Unp1) plus the velocity half of checkConvergenceGPU's norms:
+//   R3_c = -dt*G_c*Pdot - [iter>1] dt*KAcc_c ; R3[bc]=0 ; Acc = R3*MdInv ; Unp1 = UnpHalf + dt*Acc
+//   sums[0] += |Unp1|^2 ; sums[1] += |Unp1 - Unp1_prev|^2
+__global__ void __launch_bounds__(256) k_step3(Sell G, int NN, const double* __restrict__ Pdot,
+                                               const double* __restrict__ KAcc, int useKAcc,
+                                               const double* __restrict__ MdInv, const int* __restrict__ bcIndex,
+                                               const double* __restrict__ UnpHalf, const double* __restrict__ Unp1_prev,
+                                               double* __restrict__ R3, double* __restrict__ Acc,
+                                               double* __restrict__ Unp1, double dt, double* __restrict__ sums) {
+   __shared__ double sh[64];
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = row >> 5, lane = row & 31;
+   double s[2] = {0.0, 0.0};
+   if (slice < G.nslices) {
+      double a0 = 0, a1 = 0, a2 = 0;
+      const long long off = G.sliceOff[slice];
+      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(G.cols + e);
+         const double px = __ldg(Pdot + c2.x), py = __ldg(Pdot + c2.y);
+         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
+         a0 += g1.x * px + g1.y * py;
+         a1 += g2.x * px + g2.y * py;
+         a2 += g3.x * px + g3.y * py;
+      }
+      if (row < NN) {
+         const bool bc = bcIndex[row] >= 0;
+         const double acc[3] = {a0, a1, a2};
+#pragma unroll
+         for (int c = 0; c < 3; c++) {
+            const long long i = (long long)c * NN + row;
+            double r = -dt * acc[c];
+            if (useKAcc) r = r - dt * KAcc[i];
+            if (bc) r = 0.0;
+            const double a = r * MdInv[i];
+            const double u = UnpHalf[i] + dt * a;
+            R3[i] = r; Acc[i] = a; Unp1[i] = u;
+            const double d = u - Unp1_prev[i];
+            s[0] += u * u; s[1] += d * d;
+         }
+      }
+   }
+   block_sum<2>(s, sh);
+   if (threadIdx.x == 0) { atomicAdd(sums + 0, s[0]); atomicAdd(sums + 1, s[1]); }
+}
+
+// Pnp1 = Pn + dt*Pdot (calculate_Pnp1, BCH.cu:623-634) fused with the pressure half of the
+// convergence norms: sums[2] += |Pnp1|^2 ; sums[3] += |Pnp1 - Pnp1_prev|^2
+__global__ void __launch_bounds__(256) k_pressure_update(int n, const double* __restrict__ Pn, const double* __restrict__ Pdot,
+                                                         const double* __restrict__ Pprev, double* __restrict__ Pnp1, double dt,
+                                                         double* __restrict__ sums) {
+   __shared__ double sh[64];
+   double s[2] = {0.0, 0.0};
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const double p = Pn[i] + dt * Pdot[i];
+      Pnp1[i] = p;
+      const double d = p - Pprev[i];
+      s[0] += p * p; s[1] += d * d;
+   }
+   block_sum<2>(s, sh);
+   if (threadIdx.x == 0) { atomicAdd(sums + 2, s[0]); atomicAdd(sums + 3, s[1]); }
+}
+
+// max |a - b| (checkConvergenceInTimeGPU, BCH.cu:1151-1178 / GQ.cu:975-1002)
+__global__ void __launch_bounds__(256) k_max_abs_diff(long long n, const double* __restrict__ a, const double* __restrict__ b,
+                                                      double* __restrict__ out) {
+   __shared__ double sh[32];
+   double m = 0.0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      m = fmax(m, fabs(a[i] - b[i]));
+   m = warp_max(m);
+   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+   __syncthreads();
+   if (threadIdx.x < 32) {
+      m = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+      m = warp_max(m);
+      if (threadIdx.x == 0) atomic_max_nonneg(out, m);
+   }
+}
+
+// R2 = sum_c G_c^T d_c on the pressure rows, d formed on the fly (replaces calculate_step2dummyV1/V2 +
+// 3 transposed csrmv + applyPresBC of step2GPU, BCH.cu:980-1022; and the implicit variant GQ.cu:897-944):
+//   mode 0 (explicit): d = U/dt^2 - [useKAcc] MdOrigInv*KAcc        mode 1 (implicit): d = -U/dt
+__global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const double* __restrict__ U,
+                                                const double* __restrict__ KAcc, int useKAcc,
+                                                const double* __restrict__ MdOrigInv, double scale, int pinNode,
+                                                double* __restrict__ R2) {
+   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = gthread >> 5, lane = gthread & 31;
+   if (slice >= GT.nslices) return;
+   const long long off = GT.sliceOff[slice];
+   const int np = (int)((GT.sliceOff[slice + 1] - off) >> 6);
+   double acc = 0.0;
+   for (int jp = 0; jp < np; jp++) {
+      const long long e = off + ((long long)jp << 6) + 2 * lane;
+      const int2 c2 = ldnc_i2(GT.cols + e);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+         const double2 g = ldnc_d2(GT.vals[c] + e);
+         const long long ix = (long long)c * NN + c2.x, iy = (long long)c * NN + c2.y;
+         double dx = scale * __ldg(U + ix), dy = scale * __ldg(U + iy);
+         if (mode == 0 && useKAcc) {
+            dx -= __ldg(MdOrigInv + ix) * __ldg(KAcc + ix);
+            dy -= __ldg(MdOrigInv + iy) * __ldg(KAcc + iy);
+         }
+         acc += g.x * dx + g.y * dy;
+      }
+   }
+   for (int o = GT.T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   const int row = slice * GT.R + lane / GT.T;
+   if ((lane % GT.T) == 0 && row < GT.nrows) R2[row] = (pinNode > 0 && row == pinNode) ? 0.0 : acc;
+}
+
+// =================================================================================================
+// Element-by-element convective operator (thread per element, geometry recomputed from the 8 corners)
+//   C(u)_ij = sum_k (u_k . grad N_j) N_i w_k detJ_k              (BCH.cpp:3520-3685, BCH.cu:695-899)
+// Sum-factorised: with b_k = w_k adj(J_k)^T u_k (adj = detJ * J^-1, so no division is needed)
+//   (C(u) x)_i = sum_k N_i(k) * ( b_k . grad_xi x(k) ),   grad_xi x(k) = sum_j dN_j/dxi(k) x_j
+// The 27x27 element matrix is never formed in the apply kernel.
+// =================================================================================================
+template <int NV>
+__device__ __forceinline__ void ebe_gauss_b(const int (&nd)[NV], int NN, const double* __restrict__ coord,
+                                            const double* __restrict__ Uadv, double (&b)[8][3]) {
+   double ug[8][3];
+#pragma unroll
+   for (int k = 0; k < 8; k++) { ug[k][0] = 0; ug[k][1] = 0; ug[k][2] = 0; }
+#pragma unroll
+   for (int c = 0; c < 3; c++) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+         const double v = __ldg(Uadv + (long long)c * NN + nd[i]);
+#pragma unroll
+         for (int k = 0; k < 8; k++) ug[k][c] += cSv[k][i] * v;
+      }
+   }
+   double xc[8][3];
+#pragma unroll
+   for (int m = 0; m < 8; m++) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) xc[m][d] = __ldg(coord + 3 * (long long)nd[m] + d);
+   }
+#pragma unroll
+   for (int k = 0; k < 8; k++) {
+      double J[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+         for (int d = 0; d < 3; d++) {
+            double s = 0;
+#pragma unroll
+            for (int m = 0; m < 8; m++) s += cdSp[a][m][k] * xc[m][d];
+            J[a][d] = s;
+         }
+      // adj(J) (cofactor transpose), same expressions as calcJacob's un-normalised inverse (BCH.cpp:2577-2595)
+      double A[3][3];
+      A[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+      A[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+      A[0][2] = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+      A[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+      A[1][1] = J[2][2] * J[0][0] - J[2][0] * J[0][2];
+      A[1][2] = -(J[1][2] * J[0][0] - J[1][0] * J[0][2]);
+      A[2][0] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+      A[2][1] = -(J[2][1] * J[0][0] - J[2][0] * J[0][1]);
+      A[2][2] = J[1][1] * J[0][0] - J[1][0] * J[0][1];
+      // b_k[m] = sum_i adj[i][m] u_k[i]   (GQ weight = 1, BCH.cpp:2189-2196)
+#pragma unroll
+      for (int m = 0; m < 3; m++) b[k][m] = A[0][m] * ug[k][0] + A[1][m] * ug[k][1] + A[2][m] * ug[k][2];
+   }
+}
+
+// R1 = -C(Uadv) * Ux   (calculateMatrixAGPU, BCH.cu:906-939; R1 must be zeroed first).  Scatter by
+// FP64 atomicAdd (RED.ADD.F64) instead of the reference's 8 coloured launches.
+template <int NV>
+__global__ void __launch_bounds__(128) k_ebe_convect_apply(int NE, int NN, int ldE, const int* __restrict__ LtoGT,
+                                                           const double* __restrict__ coord, const double* __restrict__ Uadv,
+                                                           const double* __restrict__ Ux, double* __restrict__ R1) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= NE) return;
+   int nd[NV];
+#pragma unroll
+   for (int i = 0; i < NV; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
+   double b[8][3];
+   ebe_gauss_b<NV>(nd, NN, coord, Uadv, b);
+#pragma unroll
+   for (int c = 0; c < 3; c++) {
+      double g[8][3];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { g[k][0] = 0; g[k][1] = 0; g[k][2] = 0; }
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+         const double v = __ldg(Ux + (long long)c * NN + nd[j]);
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            g[k][0] += cdSv[0][j][k] * v;
+            g[k][1] += cdSv[1][j][k] * v;
+            g[k][2] += cdSv[2][j][k] * v;
+         }
+      }
+      double t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) t[k] = b[k][0] * g[k][0] + b[k][1] * g[k][1] + b[k][2] * g[k][2];
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+         double r = 0;
+#pragma unroll
+         for (int k = 0; k < 8; k++) r += cSv[k][i] * t[k];
+         atomicAdd(R1 + (long long)c * NN + nd[i], -r);
+      }
+   }
+}
+
+// A += C(Uadv) assembled into the Sell value array through the element map
+// (calculateMatrixAGPU + calcAndAssembleMatrixA, GQ.cu:590-754).
+template <int NV>
+__global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, int ldE, const int* __restrict__ LtoGT,
+                                                              const double* __restrict__ coord, const double* __restrict__ Uadv,
+                                                              const int* __restrict__ mapT, double* __restrict__ Aval) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= NE) return;
+   double b[8][3];
+   {
+      int nd[NV];
+#pragma unroll
+      for (int i = 0; i < NV; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
+      ebe_gauss_b<NV>(nd, NN, coord, Uadv, b);
+   }
+   for (int j = 0; j < NV; j++) {
+      double cj[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) cj[k] = b[k][0] * cdSv[0][j][k] + b[k][1] * cdSv[1][j][k] + b[k][2] * cdSv[2][j][k];
+      for (int i = 0; i < NV; i++) {
+         double a = 0;
+#pragma unroll
+         for (int k = 0; k < 8; k++) a += cSv[k][i] * cj[k];
+         const int pos = __ldg(mapT + (long long)(i * NV + j) * ldE + e);
+         atomicAdd(Aval + pos, a);
+      }
+   }
+}
+
+// Dirichlet rows of A -> identity rows (applyVelBC_LHS, GQ.cu:478-498), on the Sell layout (T = 1).
+__global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restrict__ bcNodes) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nbc) return;
+   const int row = bcNodes[i];
+   const int slice = row >> 5, lane = row & 31;
+   const long long off = A.sliceOff[slice];
+   const int w = (int)((A.sliceOff[slice + 1] - off) >> 5);
+   double* val = A.vals[vidx];
+   bool diagDone = false;
+   for (int j = 0; j < w; j++) {
+      const long long pos = off + (long long)(j >> 1) * 64 + 2 * lane + (j & 1);
+      const bool isDiag = (!diagDone && A.cols[pos] == row);
+      val[pos] = isDiag ? 1.0 : 0.0;
+      diagDone = diagDone || isDiag;
+   }
+}
+
+__global__ void k_extract_dinv(int n, const double* __restrict__ val, const int* __restrict__ diagPos, double* __restrict__ dinv) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) dinv[i] = 1.0 / val[diagPos[i]];
+}
+
+// Right-hand sides of the three implicit momentum systems in one pass (replaces calculate_dummyPdiff +
+// per-direction 2 csrmv + applyVelBC_RHS, GQ.cu:809-855):
+//   R1_d = M*Uk_prev_d - G_d*(2 Pk_prev - Pk_prevprev) ;  R1_d[bc] = BCstr[whichBC][d]
+__global__ void __launch_bounds__(256) k_gq_rhs(Sell MK, int mIdx, Sell G, int NN, const double* __restrict__ Uprev,
+                                                const double* __restrict__ Pk_prev, const double* __restrict__ Pk_prevprev,
+                                                const int* __restrict__ bcIndex, const double* __restrict__ BCstr,
+                                                double* __restrict__ R1) {
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   const int slice = row >> 5, lane = row & 31;
+   if (slice >= MK.nslices) return;
+   double a0 = 0, a1 = 0, a2 = 0;
+   {
+      const double* __restrict__ val = MK.vals[mIdx];
+      const long long off = MK.sliceOff[slice];
+      const int np = (int)((MK.sliceOff[slice + 1] - off) >> 6);
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(MK.cols + e);
+         const double2 v2 = ldnc_d2(val + e);
+         a0 += v2.x * __ldg(Uprev + c2.x) + v2.y * __ldg(Uprev + c2.y);
+         a1 += v2.x * __ldg(Uprev + NN + c2.x) + v2.y * __ldg(Uprev + NN + c2.y);
+         a2 += v2.x * __ldg(Uprev + 2 * (long long)NN + c2.x) + v2.y * __ldg(Uprev + 2 * (long long)NN + c2.y);
+      }
+   }
+   {
+      const long long off = G.sliceOff[slice];
+      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(G.cols + e);
+         const double px = 2 * __ldg(Pk_prev + c2.x) - __ldg(Pk_prevprev + c2.x);
+         const double py = 2 * __ldg(Pk_prev + c2.y) - __ldg(Pk_prevprev + c2.y);
+         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
+         a0 -= g1.x * px + g1.y * py;
+         a1 -= g2.x * px + g2.y * py;
+         a2 -= g3.x * px + g3.y * py;
+      }
+   }
+   if (row < NN) {
+      const int w = bcIndex[row];
+      R1[row] = (w >= 0) ? BCstr[3 * w + 0] : a0;
+      R1[(long long)NN + row] = (w >= 0) ? BCstr[3 * w + 1] : a1;
+      R1[2 * (long long)NN + row] = (w >= 0) ? BCstr[3 * w + 2] : a2;
+   }
+}
+
+__global__ void k_axpy_out(long long n, const double* __restrict__ a, const double* __restrict__ b, double s, double* __restrict__ out) {
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      out[i] = a[i] + s * b[i];
+}
+__global__ void k_add(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      out[i] = a[i] + b[i];
+}
+
+// =================================================================================================
+// Persistent cooperative Krylov kernels
+// =================================================================================================
+struct PcgArgs {
+   Sell Z;
+   int n;
+   const double* b;
+   double* x;
+   double *r, *p, *q;
+   const double* dinv;
+   double* scratch;   // 2 buffers x 3 x gridDim doubles
+   double* info;      // [0]=iterations [1]=|r|^2 [2]=|b|^2
+   double tol;
+   int maxit;
+   int x0zero;
+};
+
+// q = Z*p for the slices owned by this warp; returns the partial sum of p_i q_i over its rows.
+// p is written by this same kernel in other phases: plain (coherent) loads, not __ldg.
+__device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const double* p, double* q, int gwarp, int nwarps, int lane) {
+   double pq = 0.0;
+   const double* __restrict__ val = Z.vals[0];
+   const int T = Z.T, sub = lane % T;
+   for (int s = gwarp; s < Z.nslices; s += nwarps) {
+      const long long off = Z.sliceOff[s];
+      const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
+      double acc = 0.0;
+#pragma unroll 4
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(Z.cols + e);
+         const double2 v2 = ldnc_d2(val + e);
+         acc += v2.x * p[c2.x] + v2.y * p[c2.y];
+      }
+      for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const int row = s * Z.R + lane / T;
+      if (sub == 0 && row < Z.nrows) {
+         q[row] = acc;
+         pq += p[row] * acc;
+      }
+   }
+   return pq;
+}
+
+// Jacobi-preconditioned CG, whole solve in one launch (replaces CUSP_CG_solver, BCH.cu:418-451 /
+// GQ.cu:302-362: cusp::krylov::cg + diagonal preconditioner + default_monitor(b, maxit, tol)).
+// 3 grid syncs per iteration; all reductions on the device; no host round trip.
+__global__ void __launch_bounds__(512) k_pcg(PcgArgs a) {
+   cg::grid_group grid = cg::this_grid();
+   __shared__ double sh[3 * 32];
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
+   double* buf0 = a.scratch;
+   double* buf1 = a.scratch + 3 * (size_t)gridDim.x;
+   const int n = a.n;
+
+   if (!a.x0zero) {
+      // r = b - Z x  (warm start, BCH.cu:418-451 keeps the previous Pdot)
+      pcg_spmv_phase(a.Z, a.x, a.q, gwarp, nwarps, lane);
+      grid.sync();
+   }
+   double v3[3] = {0, 0, 0};
+   for (int i = tid; i < n; i += nthreads) {
+      const double bi = a.b[i];
+      double ri = bi;
+      if (a.x0zero) a.x[i] = 0.0; else ri = bi - a.q[i];
+      const double zi = a.dinv[i] * ri;
+      a.r[i] = ri;
+      a.p[i] = zi;
+      v3[0] += ri * zi; v3[1] += bi * bi; v3[2] += ri * ri;
+   }
+   grid_sum<3>(grid, v3, buf0, sh);
+   double rz = v3[0];
+   const double bb = v3[1];
+   double rr = v3[2];
+   const double thresh = a.tol * sqrt(bb);
+   int it = 0;
+   while (true) {
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;
+      double v1[1];
+      v1[0] = pcg_spmv_phase(a.Z, a.p, a.q, gwarp, nwarps, lane);
+      grid_sum<1>(grid, v1, buf1, sh);
+      const double alpha = rz / v1[0];
+      double v2[2] = {0, 0};
+      for (int i = tid; i < n; i += nthreads) {
+         a.x[i] += alpha * a.p[i];
+         const double ri = a.r[i] - alpha * a.q[i];
+         a.r[i] = ri;
+         v2[0] += ri * (a.dinv[i] * ri);
+         v2[1] += ri * ri;
+      }
+      grid_sum<2>(grid, v2, buf0, sh);
+      const double beta = v2[0] / rz;
+      rz = v2[0];
+      rr = v2[1];
+      for (int i = tid; i < n; i += nthreads) a.p[i] = a.dinv[i] * a.r[i] + beta * a.p[i];
+      it++;
+      grid.sync();
+   }
+   if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
+}
+
+struct BicgArgs {
+   Sell A;
+   int vidx;
+   int n;
+   const double* b;   // [3][n]
+   double* x;         // [3][n]
+   double* w;         // work: r, rs, p, ph, AMp, sh, AMs  -> 7 x [3][n]
+   const double* dinv;
+   double* scratch;   // 2 buffers x 6 x gridDim
+   double* info;      // [3 + s] iterations of system s
+   double tol;
+   int maxit;
+};
+
+// out_s = A * in_s for the active systems (multi-RHS: one pass over A); returns nothing, the caller
+// computes its dots in the following elementwise sweep... except that fusing the dot here saves a pass:
+// dots[s][0] += l1_s[row]*out, dots[s][1] += out*out
+__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, int vidx, int n, const double* in, double* out, const bool (&act)[3],
+                                                const double* l1, double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
+   const double* __restrict__ val = A.vals[vidx];
+   for (int s = gwarp; s < A.nslices; s += nwarps) {
+      const long long off = A.sliceOff[s];
+      const int np = (int)((A.sliceOff[s + 1] - off) >> 6);
+      double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+      for (int jp = 0; jp < np; jp++) {
+         const long long e = off + ((long long)jp << 6) + 2 * lane;
+         const int2 c2 = ldnc_i2(A.cols + e);
+         const double2 v2 = ldnc_d2(val + e);
+         if (act[0]) a0 += v2.x * in[c2.x] + v2.y * in[c2.y];
+         if (act[1]) a1 += v2.x * in[(size_t)n + c2.x] + v2.y * in[(size_t)n + c2.y];
+         if (act[2]) a2 += v2.x * in[2 * (size_t)n + c2.x] + v2.y * in[2 * (size_t)n + c2.y];
+      }
+      const int row = s * 32 + lane;   // T = 1
+      if (row < n) {
+         const double acc[3] = {a0, a1, a2};
+#pragma unroll
+         for (int c = 0; c < 3; c++)
+            if (act[c]) {
+               const size_t i = (size_t)c * n + row;
+               out[i] = acc[c];
+               d0[c] += l1[i] * acc[c];
+               d1[c] += acc[c] * acc[c];
+            }
+      }
+   }
+}
+
+// Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
+// CUSP_GMRES_solver -> cusp::krylov::bicgstab, GQ.cu:369-433, x0 = 0).  The three systems share A,
+// so each of the two SpMV phases per iteration streams A once for all still-active right-hand sides.
+__global__ void __launch_bounds__(512) k_bicgstab3(BicgArgs a) {
+   cg::grid_group grid = cg::this_grid();
+   __shared__ double sh[6 * 32];
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
+   double* buf0 = a.scratch;
+   double* buf1 = a.scratch + 6 * (size_t)gridDim.x;
+   const int n = a.n;
+   const size_t N3 = 3 * (size_t)n;
+   double* r = a.w;
+   double* rs = a.w + N3;
+   double* p = a.w + 2 * N3;
+   double* ph = a.w + 3 * N3;    // M p
+   double* AMp = a.w + 4 * N3;
+   double* shv = a.w + 5 * N3;   // M s
+   double* AMs = a.w + 6 * N3;
+
+   double v6[6] = {0, 0, 0, 0, 0, 0};
+   for (int c = 0; c < 3; c++)
+      for (int i = tid; i < n; i += nthreads) {
+         const size_t k = (size_t)c * n + i;
+         const double bi = a.b[k];
+         a.x[k] = 0.0;
+         r[k] = bi; rs[k] = bi; p[k] = bi;
+         ph[k] = a.dinv[i] * bi;
+         v6[c] += bi * bi;
+      }
+   grid_sum<6>(grid, v6, buf0, sh);
+   double bb[3], rr[3], rrs[3], thresh[3];
+   int its[3] = {0, 0, 0};
+   bool act[3];
+   for (int c = 0; c < 3; c++) { bb[c] = v6[c]; rr[c] = v6[c]; rrs[c] = v6[c]; thresh[c] = a.tol * sqrt(bb[c]); act[c] = true; }
+   while (true) {
+      for (int c = 0; c < 3; c++)
+         if (act[c] && (sqrt(rr[c]) <= thresh[c] || its[c] >= a.maxit)) act[c] = false;
+      if (!act[0] && !act[1] && !act[2]) break;
+      // ---- AMp = A (M p), d0 = rs . AMp
+      double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+      bicg_spmv_phase(a.A, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
+      for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = 0; }
+      grid_sum<6>(grid, v6, buf1, sh);
+      double alpha[3];
+      for (int c = 0; c < 3; c++) alpha[c] = act[c] ? rrs[c] / v6[c] : 0.0;
+      // ---- s = r - alpha AMp (stored in r), sh = M s, |s|^2
+      for (int c = 0; c < 3; c++) { v6[c] = 0; v6[3 + c] = 0; }
+      for (int c = 0; c < 3; c++)
+         if (act[c])
+            for (int i = tid; i < n; i += nthreads) {
+               const size_t k = (size_t)c * n + i;
+               const double si = r[k] - alpha[c] * AMp[k];
+               r[k] = si;
+               shv[k] = a.dinv[i] * si;
+               v6[c] += si * si;
+            }
+      grid_sum<6>(grid, v6, buf0, sh);
+      bool half[3];   // converged at the half step: x += alpha M p and stop
+      bool act2[3];
+      for (int c = 0; c < 3; c++) {
+         half[c] = act[c] && (sqrt(v6[c]) <= thresh[c]);
+         act2[c] = act[c] && !half[c];
+      }
+      // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
+      for (int c = 0; c < 3; c++) { d0[c] = 0; d1[c] = 0; }
+      bicg_spmv_phase(a.A, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
+      for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = d1[c]; }
+      grid_sum<6>(grid, v6, buf1, sh);
+      double omega[3];
+      for (int c = 0; c < 3; c++) omega[c] = act2[c] ? v6[c] / v6[3 + c] : 0.0;
+      // ---- x += alpha M p + omega M s ; r = s - omega AMs ; rs.r , r.r
+      for (int c = 0; c < 3; c++) { v6[c] = 0; v6[3 + c] = 0; }
+      for (int c = 0; c < 3; c++) {
+         if (half[c]) {
+            for (int i = tid; i < n; i += nthreads) {
+               const size_t k = (size_t)c * n + i;
+               a.x[k] += alpha[c] * ph[k];
+            }
+         } else if (act2[c]) {
+            for (int i = tid; i < n; i += nthreads) {
+               const size_t k = (size_t)c * n + i;
+               a.x[k] += alpha[c] * ph[k] + omega[c] * shv[k];
+               const double ri = r[k] - omega[c] * AMs[k];
+               r[k] = ri;
+               v6[c] += rs[k] * ri;
+               v6[3 + c] += ri * ri;
+            }
+         }
+      }
+      grid_sum<6>(grid, v6, buf0, sh);
+      // ---- p = r + beta (p - omega AMp) ; ph = M p
+      for (int c = 0; c < 3; c++) {
+         if (half[c]) { its[c]++; act[c] = false; continue; }
+         if (!act2[c]) continue;
+         const double beta = (v6[c] / rrs[c]) * (alpha[c] / omega[c]);
+         rrs[c] = v6[c];
+         rr[c] = v6[3 + c];
+         for (int i = tid; i < n; i += nthreads) {
+            const size_t k = (size_t)c * n + i;
+            const double pi = r[k] + beta * (p[k] - omega[c] * AMp[k]);
+            p[k] = pi;
+            ph[k] = a.dinv[i] * pi;
+         }
+         its[c]++;
+      }
+      grid.sync();
+   }
+   if (tid == 0)
+      for (int c = 0; c < 3; c++) { a.info[3 + c] = (double)its[c]; a.info[6 + c] = rr[c]; }
+}
+
+}   // namespace cfdb
+
+// =================================================================================================
+// Host side of the context
+// =================================================================================================
+using namespace cfdb;
+
+namespace {
+
+struct ProfScope {
+   cfd_ctx* c;
+   const char* name;
+   double bytes;
+   ProfScope(cfd_ctx* c_, const char* n, double b) : c(c_), name(n), bytes(b) {
+      if (c->profile) cudaEventRecord(c->ev0, c->stream);
+   }
+   ~ProfScope() {
+      if (c->profile) {
+         cudaEventRecord(c->ev1, c->stream);
+         cudaEventSynchronize(c->ev1);
+         float ms = 0;
+         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+         ProfEntry& p = c->prof[name];
+         p.ms += ms; p.launches += 1; p.bytes += bytes;
+      }
+   }
+};
+
+inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }
+
+template <typename T>
+int dalloc(cfd_ctx* c, T** p, size_t count) {
+   CFD_CK(cudaMalloc((void**)p, sizeof(T) * std::max<size_t>(count, 1)));
+   CFD_CK(cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(count, 1)));
+   c->allocs.push_back((void*)*p);
+   return CFD_OK;
+}
+template <typename T>
+int dupload(cfd_ctx* c, T** p, const T* host, size_t count) {
+   int rc = dalloc(c, p, count);
+   if (rc) return rc;
+   if (count) CFD_CK(cudaMemcpy(*p, host, sizeof(T) * count, cudaMemcpyHostToDevice));
+   return CFD_OK;
+}
+
+int regvec(cfd_ctx* c, const char* name, double** p, long long n) {
+   int rc = dalloc(c, p, (size_t)n);
+   if (rc) return rc;
+   c->vecs[name] = std::make_pair(p, n);
+   return CFD_OK;
+}
+
+// algorithmic bytes of a CSR SpMV with nvec right-hand sides
+double spmv_bytes(const Sell& A, int nval, int nvec, bool accumulate) {
+   return (8.0 * nval + 4.0) * (double)A.nnz + 4.0 * (A.nrows + 1.0) + 8.0 * nvec * ((double)A.ncols + (double)A.nrows * (accumulate ? 2 : 1));
+}
+
+int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   PcgArgs a;
+   a.Z = c->Z; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
+   a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
+   void* args[] = {&a};
+   ProfScope ps(c, "pcg", 0.0);
+   CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
+   c->launches++;
+   return CFD_OK;
+}
+
+int fetch_kinfo(cfd_ctx* c) {
+   CFD_CK(cudaMemcpyAsync(c->h_pinned + 16, c->kinfo, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   c->last_cg = (int)c->h_pinned[16];
+   for (int d = 0; d < 3; d++) c->last_bicg[d] = (int)c->h_pinned[16 + 3 + d];
+   return CFD_OK;
+}
+
+template <int NV>
+int launch_ebe_apply(cfd_ctx* c, const double* Uadv, const double* Ux, double* R1) {
+   const int NE = c->P.NE;
+   k_ebe_convect_apply<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, Ux, R1);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+template <int NV>
+int launch_ebe_assemble(cfd_ctx* c, const double* Uadv, double* Aval) {
+   const int NE = c->P.NE;
+   k_ebe_convect_assemble<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, c->mapT, Aval);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
+double ebe_bytes(const cfd_ctx* c, bool assemble) {
+   // per element: node ids + 8 corner coordinates + gather of the advecting field (+ second field and
+   // scatter RMW for the apply form; + map and RMW of NENv^2 matrix entries for the assembly form)
+   const double nv = c->P.NENv;
+   double per = 4.0 * nv + 8.0 * 8 * 3 + 8.0 * 3 * nv;
+   per += assemble ? (4.0 + 16.0) * nv * nv : (8.0 * 3 * nv + 16.0 * 3 * nv);
+   return per * c->P.NE;
+}
+
+}   // namespace
+
+extern "C" {
+
+const char* cfd_last_error(void) { return cfdb::last_error(); }
+const char* cfd_version(void) { return "cfdb200 0.1 (sm_100a)"; }
+
+void cfd_default_options(cfd_options* o) {
+   memset(o, 0, sizeof *o);
+   o->cg_tol = 1e-6; o->cg_maxit = 1000; o->cg_warm_start = 0;
+   o->bicg_tol = 1e-6; o->bicg_maxit = 1000; o->maxacc_rule = 0; o->device = -1;
+}
+
+int cfd_selectCUDAdevice(int device) {
+   int n = 0;
+   CFD_CK(cudaGetDeviceCount(&n));
+   if (n == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
+   if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return CFD_ERR_ARG; }
+   CFD_CK(cudaSetDevice(device));
+   return CFD_OK;
+}
+
+void cfd_destroy(cfd_ctx* c) {
+   if (!c) return;
+   cudaSetDevice(c->device);
+   if (c->stream) cudaStreamSynchronize(c->stream);
+   for (void* p : c->allocs) cudaFree(p);
+   sell_free(c->K); sell_free(c->G); sell_free(c->GT); sell_free(c->Z);
+   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+   if (c->ev0) cudaEventDestroy(c->ev0);
+   if (c->ev1) cudaEventDestroy(c->ev1);
+   if (c->stream) cudaStreamDestroy(c->stream);
+   delete c;
+}
+
+int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, cfd_ctx** out) {
+   if (!P || !out) { set_error("null argument"); return CFD_ERR_ARG; }
+   if ((P->NENv != 27 && P->NENv != 8) || P->NENp != 8 || P->NGP != 8) {
+      set_error("unsupported element: NENv=%d NENp=%d NGP=%d (supported: 27/8/8 and 8/8/8)", P->NENv, P->NENp, P->NGP);
+      return CFD_ERR_ARG;
+   }
+   if (!P->coord || !P->LtoGnode || !P->sparseMrowStarts || !P->sparseMcol || !P->sparseKvalue || !P->sparseGrowStarts ||
+       !P->sparseGcol || !P->sparseG1value || !P->sparseG2value || !P->sparseG3value || !P->sparseZrowStarts || !P->sparseZcol ||
+       !P->sparseZvalue || (P->BCnVelNodes > 0 && (!P->BCvelNodes || !P->BCstr))) {
+      set_error("cfd_problem: a required array is NULL");
+      return CFD_ERR_ARG;
+   }
+   if (P->scheme == CFD_EXPLICIT && (!P->MdInv || !P->MdOrigInv)) { set_error("explicit scheme needs MdInv and MdOrigInv"); return CFD_ERR_ARG; }
+   if (P->scheme == CFD_IMPLICIT && (!P->sparseMvalue || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
+   cfd_options o;
+   if (opt) o = *opt; else cfd_default_options(&o);
+   int ndev = 0;
+   CFD_CK(cudaGetDeviceCount(&ndev));
+   if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
+   if (o.device >= 0) CFD_CK(cudaSetDevice(o.device));
+   cfd_ctx* c = new cfd_ctx();
+   *out = nullptr;
+   c->P = *P;
+   c->opt = o;
+   CFD_CK(cudaGetDevice(&c->device));
+   cudaDeviceProp prop;
+   CFD_CK(cudaGetDeviceProperties(&prop, c->device));
+   c->numSMs = prop.multiProcessorCount;
+   if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); delete c; return CFD_ERR_CUDA; }
+   CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   CFD_CK(cudaEventCreate(&c->ev0));
+   CFD_CK(cudaEventCreate(&c->ev1));
+   CFD_CK(cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double)));
+
+   const int NN = P->NN, NNp = P->NNp, NE = P->NE, nv = P->NENv;
+   int rc;
+#define TRY(x) do { rc = (x); if (rc) { cfd_destroy(c); return rc; } } while (0)
+
+   // reference-element tables -> constant memory
+   {
+      FeTables T;
+      build_fe_tables(nv, T);
+      CFD_CK(cudaMemcpyToSymbol(cSv, T.Sv, sizeof(T.Sv)));
+      CFD_CK(cudaMemcpyToSymbol(cdSv, T.dSv, sizeof(T.dSv)));
+      CFD_CK(cudaMemcpyToSymbol(cdSp, T.dSp, sizeof(T.dSp)));
+   }
+   // ---- matrices -> Sell
+   {
+      SellHost h;
+      sell_build_host(NN, NN, P->sparseMrowStarts, P->sparseMcol, 1, h);
+      if (P->scheme == CFD_EXPLICIT) {
+         const double* v[1] = {P->sparseKvalue};
+         TRY(sell_upload(h, 1, v, c->K));
+      } else {
+         std::vector<double> mk((size_t)P->sparseM_nnz);
+#pragma omp parallel for schedule(static)
+         for (long long k = 0; k < P->sparseM_nnz; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
+         const double* v[3] = {mk.data(), P->sparseMvalue, nullptr};
+         TRY(sell_upload(h, 3, v, c->K));
+         // element -> Sell position map, transposed to [q][e]
+         c->ldE = (NE + 31) & ~31;
+         std::vector<int> mt((size_t)nv * nv * c->ldE, 0);
+#pragma omp parallel for schedule(static)
+         for (int e = 0; e < NE; e++)
+            for (int q = 0; q < nv * nv; q++) mt[(size_t)q * c->ldE + e] = (int)h.perm[(size_t)P->sparseMapM_1d[(size_t)e * nv * nv + q]];
+         TRY(dupload(c, &c->mapT, mt.data(), mt.size()));
+         std::vector<int> dp(NN, 0);
+#pragma omp parallel for schedule(static)
+         for (int r = 0; r < NN; r++)
+            for (int k = P->sparseMrowStarts[r]; k < P->sparseMrowStarts[r + 1]; k++)
+               if (P->sparseMcol[k] == r) { dp[r] = (int)h.perm[k]; break; }
+         TRY(dupload(c, &c->diagPosA, dp.data(), dp.size()));
+      }
+   }
+   {
+      SellHost h;
+      sell_build_host(NN, NNp, P->sparseGrowStarts, P->sparseGcol, 1, h);
+      const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
+      TRY(sell_upload(h, 3, v, c->G));
+   }
+   {
+      // explicit transpose of the G pattern: rows = pressure nodes (instead of the reference's
+      // OPERATION_TRANSPOSE csrmv scatter, BCH.cu:1006-1009)
+      const int nnzG = P->sparseG_nnz;
+      std::vector<int> ts(NNp + 1, 0), tcol(nnzG);
+      std::vector<double> t1(nnzG), t2(nnzG), t3(nnzG);
+      for (int k = 0; k < nnzG; k++) ts[P->sparseGcol[k] + 1]++;
+      for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
+      std::vector<int> fill(ts.begin(), ts.end() - 1);
+      for (int r = 0; r < NN; r++)
+         for (int k = P->sparseGrowStarts[r]; k < P->sparseGrowStarts[r + 1]; k++) {
+            const int p = fill[P->sparseGcol[k]]++;
+            tcol[p] = r; t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k];
+         }
+      SellHost h;
+      sell_build_host(NNp, NN, ts.data(), tcol.data(), choose_T(NNp, nnzG), h);
+      const double* v[3] = {t1.data(), t2.data(), t3.data()};
+      TRY(sell_upload(h, 3, v, c->GT));
+   }
+   {
+      SellHost h;
+      sell_build_host(NNp, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NNp, P->sparseZ_nnz), h);
+      const double* v[1] = {P->sparseZvalue};
+      TRY(sell_upload(h, 1, v, c->Z));
+      std::vector<double> dinv(NNp, 1.0);
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < NNp; r++)
+         for (int k = P->sparseZrowStarts[r]; k < P->sparseZrowStarts[r + 1]; k++)
+            if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
+      TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
+   }
+   // ---- mesh tables
+   {
+      if (!c->ldE) c->ldE = (NE + 31) & ~31;
+      std::vector<int> lt((size_t)nv * c->ldE, 0);
+#pragma omp parallel for schedule(static)
+      for (int e = 0; e < NE; e++)
+         for (int i = 0; i < nv; i++) lt[(size_t)i * c->ldE + e] = P->LtoGnode[(size_t)e * nv + i];
+      TRY(dupload(c, &c->LtoGT, lt.data(), lt.size()));
+      TRY(dupload(c, &c->coord, P->coord, (size_t)NN * 3));
+      std::vector<int> bi(NN, -1), bn(P->BCnVelNodes);
+      for (int i = 0; i < P->BCnVelNodes; i++) { bn[i] = P->BCvelNodes[2 * i]; bi[bn[i]] = P->BCvelNodes[2 * i + 1]; }
+      TRY(dupload(c, &c->bcIndex, bi.data(), bi.size()));
+      TRY(dupload(c, &c->bcNodes, bn.data(), bn.size()));
+      TRY(dupload(c, &c->BCstr, P->BCstr, (size_t)3 * P->nBC));
+   }
+   // ---- vectors
+   const long long N3 = 3LL * NN;
+   if (P->scheme == CFD_EXPLICIT) {
+      TRY(dupload(c, &c->MdInv, P->MdInv, (size_t)N3));
+      TRY(dupload(c, &c->MdOrigInv, P->MdOrigInv, (size_t)N3));
+      TRY(regvec(c, "Un", &c->Un, N3)); TRY(regvec(c, "Unp1", &c->Unp1, N3)); TRY(regvec(c, "Unp1_prev", &c->Unp1_prev, N3));
+      TRY(regvec(c, "UnpHalf", &c->UnpHalf, N3)); TRY(regvec(c, "UnpHalf_prev", &c->UnpHalf_prev, N3));
+      TRY(regvec(c, "Acc", &c->Acc, N3)); TRY(regvec(c, "Acc_prev", &c->Acc_prev, N3));
+      TRY(regvec(c, "KtimesAcc_prev", &c->KtimesAcc_prev, N3)); TRY(regvec(c, "R1", &c->R1, N3)); TRY(regvec(c, "R3", &c->R3, N3));
+      TRY(regvec(c, "Pn", &c->Pn, NNp)); TRY(regvec(c, "Pnp1", &c->Pnp1, NNp)); TRY(regvec(c, "Pnp1_prev", &c->Pnp1_prev, NNp));
+      TRY(regvec(c, "Pdot", &c->Pdot, NNp)); TRY(regvec(c, "R2", &c->R2, NNp));
+   } else {
+      TRY(regvec(c, "Uk", &c->Uk, N3)); TRY(regvec(c, "Uk_prev", &c->Uk_prev, N3));
+      TRY(regvec(c, "Pk", &c->Pk, NNp)); TRY(regvec(c, "Pk_prev", &c->Pk_prev, NNp)); TRY(regvec(c, "Pk_prevprev", &c->Pk_prevprev, NNp));
+      TRY(regvec(c, "Pdiff", &c->Pdiff, NNp)); TRY(regvec(c, "R2", &c->R2, NNp)); TRY(regvec(c, "R1", &c->R1i, N3));
+      TRY(dalloc(c, &c->Adinv, (size_t)NN));
+      TRY(dalloc(c, &c->bw, (size_t)(7 * N3)));
+   }
+   TRY(dalloc(c, &c->cg_r, (size_t)NNp)); TRY(dalloc(c, &c->cg_p, (size_t)NNp)); TRY(dalloc(c, &c->cg_q, (size_t)NNp));
+   TRY(dalloc(c, &c->kinfo, 16)); TRY(dalloc(c, &c->scal, 16));
+   // initial state (applyBC_initial, BCH.cpp:4062-4110 / GQ.cpp:4559-4607)
+   {
+      std::vector<double> u0((size_t)N3, 0.0);
+      if (P->U0) std::copy(P->U0, P->U0 + N3, u0.begin());
+      else
+         for (int i = 0; i < P->BCnVelNodes; i++) {
+            const int node = P->BCvelNodes[2 * i], w = P->BCvelNodes[2 * i + 1];
+            for (int d = 0; d < 3; d++) u0[(size_t)d * NN + node] = P->BCstr[3 * w + d];
+         }
+      double* Ud = P->scheme == CFD_EXPLICIT ? c->Un : c->Uk_prev;
+      double* Pd = P->scheme == CFD_EXPLICIT ? c->Pn : c->Pk_prev;
+      CFD_CK(cudaMemcpy(Ud, u0.data(), sizeof(double) * N3, cudaMemcpyHostToDevice));
+      if (P->P0) CFD_CK(cudaMemcpy(Pd, P->P0, sizeof(double) * NNp, cudaMemcpyHostToDevice));
+   }
+   // ---- cooperative launch geometry: persistent kernels, a whole number of CTAs per SM
+   {
+      int occ = 0;
+      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, c->pcg_threads, 0));
+      if (occ < 1) { set_error("k_pcg does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
+      const long long wantWarps = std::max<long long>(c->Z.nslices, ((long long)NNp + 31) / 32);
+      int blocks = c->numSMs * occ;
+      const int needed = (int)std::max<long long>(1, (wantWarps * 32 + c->pcg_threads - 1) / c->pcg_threads);
+      if (needed < blocks) blocks = std::max(c->numSMs, ((needed + c->numSMs - 1) / c->numSMs) * c->numSMs);
+      c->pcg_blocks = std::min(blocks, c->numSMs * occ);
+      int occ2 = 0;
+      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_bicgstab3, c->bicg_threads, 0));
+      if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
+      const int needed2 = std::max(1, (NN + c->bicg_threads - 1) / c->bicg_threads);
+      int blocks2 = c->numSMs * occ2;
+      if (needed2 < blocks2) blocks2 = std::max(c->numSMs, ((needed2 + c->numSMs - 1) / c->numSMs) * c->numSMs);
+      c->bicg_blocks = std::min(blocks2, c->numSMs * occ2);
+      TRY(dalloc(c, &c->partials, (size_t)2 * 6 * std::max(c->pcg_blocks, c->bicg_blocks)));
+   }
+#undef TRY
+   // scalar fields stay; host pointers are not ours to keep
+   c->P.coord = nullptr; c->P.LtoGnode = nullptr; c->P.sparseMrowStarts = nullptr; c->P.sparseMcol = nullptr;
+   c->P.sparseKvalue = nullptr; c->P.sparseMvalue = nullptr; c->P.sparseGrowStarts = nullptr; c->P.sparseGcol = nullptr;
+   c->P.sparseG1value = c->P.sparseG2value = c->P.sparseG3value = nullptr;
+   c->P.sparseZrowStarts = nullptr; c->P.sparseZcol = nullptr; c->P.sparseZvalue = nullptr; c->P.sparseMapM_1d = nullptr;
+   c->P.MdInv = c->P.MdOrigInv = nullptr; c->P.BCvelNodes = nullptr; c->P.BCstr = nullptr; c->P.U0 = c->P.P0 = nullptr;
+   CFD_CK(cudaDeviceSynchronize());
+   *out = c;
+   return CFD_OK;
+}
+
+int cfd_download(cfd_ctx* c, const char* name, double* host, long long count) {
+   if (!c) return CFD_ERR_ARG;
+   if (std::string(name) == "sparseAvalue" || std::string(name) == "Adinv") {
+      // diagnostic: A in CSR order is not kept on the device; only the Jacobi diagonal is exposed
+      if (std::string(name) == "Adinv" && count == c->P.NN) {
+         CFD_CK(cudaStreamSynchronize(c->stream));
+         CFD_CK(cudaMemcpy(host, c->Adinv, sizeof(double) * count, cudaMemcpyDeviceToHost));
+         return CFD_OK;
+      }
+      set_error("vector %s not downloadable", name);
+      return CFD_ERR_ARG;
+   }
+   auto it = c->vecs.find(name);
+   if (it == c->vecs.end() || count != it->second.second) { set_error("unknown vector %s or wrong length %lld", name, count); return CFD_ERR_ARG; }
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   CFD_CK(cudaMemcpy(host, *it->second.first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+   return CFD_OK;
+}
+int cfd_upload(cfd_ctx* c, const char* name, const double* host, long long count) {
+   if (!c) return CFD_ERR_ARG;
+   auto it = c->vecs.find(name);
+   if (it == c->vecs.end() || count != it->second.second) { set_error("unknown vector %s or wrong length %lld", name, count); return CFD_ERR_ARG; }
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   CFD_CK(cudaMemcpy(*it->second.first, host, sizeof(double) * count, cudaMemcpyHostToDevice));
+   return CFD_OK;
+}
+int cfd_get_fields(cfd_ctx* c, double* U, double* P) {
+   if (!c) return CFD_ERR_ARG;
+   const bool ex = c->P.scheme == CFD_EXPLICIT;
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   if (U) CFD_CK(cudaMemcpy(U, ex ? c->Un : c->Uk_prev, sizeof(double) * 3 * (size_t)c->P.NN, cudaMemcpyDeviceToHost));
+   if (P) CFD_CK(cudaMemcpy(P, ex ? c->Pn : c->Pk_prev, sizeof(double) * (size_t)c->P.NNp, cudaMemcpyDeviceToHost));
+   return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// explicit seam
+// ------------------------------------------------------------------------------------------------
+int bch_beginTimeStep(cfd_ctx* c) {
+   const size_t N3 = 3 * (size_t)c->P.NN;
+   CFD_CK(cudaMemcpyAsync(c->UnpHalf_prev, c->Un, N3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->Pnp1_prev, c->Pn, c->P.NNp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemsetAsync(c->Acc_prev, 0, N3 * sizeof(double), c->stream));
+   return CFD_OK;
+}
+
+int bch_calculateMatrixAGPU(cfd_ctx* c) {
+   const size_t N3 = 3 * (size_t)c->P.NN;
+   ProfScope ps(c, "ebe", ebe_bytes(c, false));
+   CFD_CK(cudaMemsetAsync(c->R1, 0, N3 * sizeof(double), c->stream));
+   if (c->P.NENv == 27) return launch_ebe_apply<27>(c, c->Un, c->UnpHalf_prev, c->R1);
+   return launch_ebe_apply<8>(c, c->Un, c->UnpHalf_prev, c->R1);
+}
+
+int bch_step1GPUpart(cfd_ctx* c, int /*iter*/) {
+   const int NN = c->P.NN;
+   ProfScope ps(c, "step1", spmv_bytes(c->K, 1, 3, true) + spmv_bytes(c->G, 3, 1, false) + 8.0 * 3 * NN * 3);
+   k_step1<<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, c->G, NN, c->UnpHalf_prev, c->Pn, c->Un, c->MdInv,
+                                                                                c->bcIndex, c->R1, c->UnpHalf, c->P.dt);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
+int bch_step2GPU(cfd_ctx* c, int iter) {
+   const int NN = c->P.NN, NNp = c->P.NNp;
+   const double dt = c->P.dt;
+   {
+      ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
+      k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 0, c->UnpHalf, c->KtimesAcc_prev, iter != 1,
+                                                                                    c->MdOrigInv, 1.0 / (dt * dt), c->P.zeroPressureNode, c->R2);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   int rc = run_pcg(c, c->R2, c->Pdot, !c->opt.cg_warm_start);
+   if (rc) return rc;
+   {
+      ProfScope ps(c, "update", 40.0 * NNp);
+      CFD_CK(cudaMemsetAsync(c->scal, 0, 4 * sizeof(double), c->stream));
+      k_pressure_update<<<std::min(gridFor(NNp, 256), 4 * c->numSMs), 256, 0, c->stream>>>(NNp, c->Pn, c->Pdot, c->Pnp1_prev, c->Pnp1, dt, c->scal);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   return CFD_OK;
+}
+
+int bch_step3GPU(cfd_ctx* c, int iter) {
+   const int NN = c->P.NN;
+   ProfScope ps(c, "step3", spmv_bytes(c->G, 3, 1, false) + 8.0 * 3 * NN * 7);
+   k_step3<<<gridFor((long long)c->G.nslices * 32, 256), 256, 0, c->stream>>>(c->G, NN, c->Pdot, c->KtimesAcc_prev, iter != 1, c->MdInv, c->bcIndex,
+                                                                                c->UnpHalf, c->Unp1_prev, c->R3, c->Acc, c->Unp1, c->P.dt, c->scal);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
+int bch_checkConvergenceGPU(cfd_ctx* c, int* converged) {
+   CFD_CK(cudaMemcpyAsync(c->h_pinned, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   int rc = fetch_kinfo(c);
+   if (rc) return rc;
+   const double* s = c->h_pinned;
+   const double n1 = sqrt(s[1]) / sqrt(s[0]);   // NaN when the field is still zero -> not converged, like BCH.cpp:2946-2959
+   const double n2 = sqrt(s[3]) / sqrt(s[2]);
+   if (converged) *converged = (n1 < c->P.tolerance && n2 < c->P.tolerance) ? 1 : 0;
+   return CFD_OK;
+}
+
+int bch_rotateIterates(cfd_ctx* c) {
+   const size_t N3 = 3 * (size_t)c->P.NN * sizeof(double);
+   CFD_CK(cudaMemcpyAsync(c->UnpHalf_prev, c->UnpHalf, N3, cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->Unp1_prev, c->Unp1, N3, cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->Acc_prev, c->Acc, N3, cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->Pnp1_prev, c->Pnp1, c->P.NNp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   return CFD_OK;
+}
+
+int bch_calculate_KtimesAcc_prevGPU(cfd_ctx* c) {
+   const int NN = c->P.NN;
+   ProfScope ps(c, "spmv_k", spmv_bytes(c->K, 1, 3, false));
+   k_spmv_multi<3><<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, 0, c->Acc_prev, NN, c->KtimesAcc_prev, NN, 1.0, 0.0);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
+static int max_acc(cfd_ctx* c, const double* a, const double* b, int* steady, double* maxAcc) {
+   const long long N3 = 3LL * c->P.NN;
+   {
+      ProfScope ps(c, "update", 16.0 * N3);
+      CFD_CK(cudaMemsetAsync(c->scal + 4, 0, sizeof(double), c->stream));
+      k_max_abs_diff<<<std::min(gridFor(N3, 256), 8 * c->numSMs), 256, 0, c->stream>>>(N3, a, b, c->scal + 4);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   CFD_CK(cudaMemcpyAsync(c->h_pinned + 8, c->scal + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   double m = c->h_pinned[8];
+   if (c->opt.maxacc_rule == 0) m = m * (1.0 / c->P.dt);
+   if (maxAcc) *maxAcc = m;
+   if (steady) *steady = (m > c->P.convergenceCriteria) ? 0 : 1;
+   return CFD_OK;
+}
+
+int bch_checkConvergenceInTimeGPU(cfd_ctx* c, int* steady, double* maxAcc) { return max_acc(c, c->Unp1, c->Un, steady, maxAcc); }
+
+int bch_endTimeStep(cfd_ctx* c) {
+   CFD_CK(cudaMemcpyAsync(c->Un, c->Unp1, 3 * (size_t)c->P.NN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->Pn, c->Pnp1, c->P.NNp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   c->timeN++;
+   return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit seam
+// ------------------------------------------------------------------------------------------------
+int gq_calculateMatrixAGPU(cfd_ctx* c) {
+   ProfScope ps(c, "assemble", ebe_bytes(c, true));
+   if (c->P.NENv == 27) return launch_ebe_assemble<27>(c, c->Uk_prev, c->K.vals[2]);
+   return launch_ebe_assemble<8>(c, c->Uk_prev, c->K.vals[2]);
+}
+
+int gq_step1GPU(cfd_ctx* c) {
+   const int NN = c->P.NN;
+   // A <- M + K (kept pre-summed), then A += C(Uk_prev), Dirichlet rows -> identity
+   {
+      ProfScope ps(c, "assemble", 16.0 * c->K.padded);
+      CFD_CK(cudaMemcpyAsync(c->K.vals[2], c->K.vals[0], sizeof(double) * (size_t)c->K.padded, cudaMemcpyDeviceToDevice, c->stream));
+   }
+   int rc = gq_calculateMatrixAGPU(c);
+   if (rc) return rc;
+   {
+      ProfScope ps(c, "assemble", 0.0);
+      if (c->P.BCnVelNodes > 0) {
+         k_bc_rows_identity<<<gridFor(c->P.BCnVelNodes, 128), 128, 0, c->stream>>>(c->K, 2, c->P.BCnVelNodes, c->bcNodes);
+         c->launches++;
+      }
+      k_extract_dinv<<<gridFor(NN, 256), 256, 0, c->stream>>>(NN, c->K.vals[2], c->diagPosA, c->Adinv);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   {
+      ProfScope ps(c, "gq_rhs", spmv_bytes(c->K, 1, 3, false) + spmv_bytes(c->G, 3, 1, false));
+      k_gq_rhs<<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, 1, c->G, NN, c->Uk_prev, c->Pk_prev, c->Pk_prevprev,
+                                                                                   c->bcIndex, c->BCstr, c->R1i);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   {
+      BicgArgs a;
+      a.A = c->K; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
+      a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
+      void* args[] = {&a};
+      ProfScope ps(c, "bicgstab", 0.0);
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_bicgstab3, dim3(c->bicg_blocks), dim3(c->bicg_threads), args, 0, c->stream));
+      c->launches++;
+   }
+   return CFD_OK;
+}
+
+int gq_step2GPU(cfd_ctx* c) {
+   const int NN = c->P.NN, NNp = c->P.NNp;
+   {
+      ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
+      k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 1, c->Uk, nullptr, 0, nullptr, -1.0 / c->P.dt,
+                                                                                    c->P.zeroPressureNode, c->R2);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   int rc = run_pcg(c, c->R2, c->Pdiff, true);   // cudaMemset(Pdiff_d, 0) each call, GQ.cu:307
+   if (rc) return rc;
+   {
+      ProfScope ps(c, "update", 24.0 * NNp);
+      k_add<<<std::min(gridFor(NNp, 256), 4 * c->numSMs), 256, 0, c->stream>>>(NNp, c->Pk_prev, c->Pdiff, c->Pk);   // calculate_Pk, GQ.cu:554-565
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   return CFD_OK;
+}
+
+int gq_checkConvergenceInTimeGPU(cfd_ctx* c, int* steady, double* maxAcc) { return max_acc(c, c->Uk, c->Uk_prev, steady, maxAcc); }
+
+int gq_endTimeStep(cfd_ctx* c) {
+   std::swap(c->Uk, c->Uk_prev);   // Uk_prev <- Uk; the old Uk_prev buffer is fully rewritten by the next BiCGStab solve
+   double* t = c->Pk_prevprev;     // Pk_prevprev <- Pk_prev <- Pk; the freed buffer becomes the next Pk
+   c->Pk_prevprev = c->Pk_prev; c->Pk_prev = c->Pk; c->Pk = t;
+   c->timeN++;
+   return CFD_OK;
+}
+
+int cfd_printMonitorDataGPU(cfd_ctx* c, double out[4]) {
+   const bool ex = c->P.scheme == CFD_EXPLICIT;
+   const double* U = ex ? c->Un : c->Uk_prev;
+   const double* Pp = ex ? c->Pn : c->Pk_prev;
+   const int m = c->P.monPoint, NN = c->P.NN;
+   for (int d = 0; d < 3; d++) CFD_CK(cudaMemcpyAsync(c->h_pinned + 32 + d, U + (size_t)d * NN + m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaMemcpyAsync(c->h_pinned + 35, Pp + m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   for (int d = 0; d < 4; d++) out[d] = c->h_pinned[32 + d];
+   return CFD_OK;
+}
+
+int cfd_last_cg_iterations(cfd_ctx* c) {
+   if (fetch_kinfo(c)) return -1;
+   return c->last_cg;
+}
+int cfd_last_bicgstab_iterations(cfd_ctx* c, int its[3]) {
+   int rc = fetch_kinfo(c);
+   if (rc) return rc;
+   for (int d = 0; d < 3; d++) its[d] = c->last_bicg[d];
+   return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole time steps
+// ------------------------------------------------------------------------------------------------
+int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* reports, int* done) {
+   if (!c) return CFD_ERR_ARG;
+   int rc = 0;
+   int s = 0;
+   for (; s < nsteps; s++) {
+      cfd_step_report rep;
+      memset(&rep, 0, sizeof rep);
+      if (c->P.scheme == CFD_EXPLICIT) {
+         if ((rc = bch_beginTimeStep(c))) return rc;
+         int iter;
+         for (iter = 1; iter <= c->P.maxIter; iter++) {
+            if ((rc = bch_calculateMatrixAGPU(c))) return rc;
+            if ((rc = bch_step1GPUpart(c, iter))) return rc;
+            if ((rc = bch_step2GPU(c, iter))) return rc;
+            if ((rc = bch_step3GPU(c, iter))) return rc;
+            int conv = 0;
+            if ((rc = bch_checkConvergenceGPU(c, &conv))) return rc;
+            rep.cg_iterations += c->last_cg;
+            rep.cg_solves++;
+            if (conv) break;
+            if ((rc = bch_rotateIterates(c))) return rc;
+            if ((rc = bch_calculate_KtimesAcc_prevGPU(c))) return rc;
+         }
+         rep.iter = iter;
+         if ((rc = bch_checkConvergenceInTimeGPU(c, &rep.steady, &rep.maxAcc))) return rc;
+         if ((rc = bch_endTimeStep(c))) return rc;
+      } else {
+         if ((rc = gq_step1GPU(c))) return rc;
+         if ((rc = gq_step2GPU(c))) return rc;
+         if ((rc = gq_checkConvergenceInTimeGPU(c, &rep.steady, &rep.maxAcc))) return rc;
+         if ((rc = fetch_kinfo(c))) return rc;
+         rep.iter = 1;
+         rep.cg_iterations = c->last_cg;
+         rep.cg_solves = 1;
+         for (int d = 0; d < 3; d++) rep.bicg_iterations[d] = c->last_bicg[d];
+         if ((rc = gq_endTimeStep(c))) return rc;
+      }
+      rep.timeN = c->timeN;
+      if ((rc = cfd_printMonitorDataGPU(c, rep.monitor))) return rc;
+      if (reports) reports[s] = rep;
+      if (stop_on_steady && rep.steady) { s++; break; }
+   }
+   if (done) *done = s;
+   return CFD_OK;
+}
+
+int cfd_profile(cfd_ctx* c, int enable) {
+   c->profile = enable != 0;
+   if (enable) c->prof.clear();
+   return CFD_OK;
+}
+int cfd_profile_get(cfd_ctx* c, const char* name, double* ms, long long* launches, double* bytes) {
+   auto it = c->prof.find(name);
+   if (it == c->prof.end()) { if (ms) *ms = 0; if (launches) *launches = 0; if (bytes) *bytes = 0; return CFD_ERR_ARG; }
+   if (ms) *ms = it->second.ms;
+   if (launches) *launches = it->second.launches;
+   if (bytes) *bytes = it->second.bytes;
+   return CFD_OK;
+}
+long long cfd_kernel_launches(cfd_ctx* c) { return c->launches; }
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone kernels on caller data
+// ------------------------------------------------------------------------------------------------
+int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, const double* val, int nvec, const double* x, double* y,
+                 double alpha, double beta, int repeat, double* ms_per_call) {
+   if (nvec != 1 && nvec != 3 && nvec != 6) { set_error("nvec must be 1, 3 or 6"); return CFD_ERR_ARG; }
+   int ndev = 0;
+   CFD_CK(cudaGetDeviceCount(&ndev));
+   if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
+   SellHost h;
+   sell_build_host(nrows, ncols, rowStarts, col, 1, h);
+   Sell A;
+   const double* v[1] = {val};
+   int rc = sell_upload(h, 1, v, A);
+   if (rc) return rc;
+   double *dx = nullptr, *dy = nullptr;
+   CFD_CK(cudaMalloc(&dx, sizeof(double) * (size_t)nvec * ncols));
+   CFD_CK(cudaMalloc(&dy, sizeof(double) * (size_t)nvec * nrows));
+   CFD_CK(cudaMemcpy(dx, x, sizeof(double) * (size_t)nvec * ncols, cudaMemcpyHostToDevice));
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   float best = 1e30f;
+   for (int it = 0; it < std::max(1, repeat); it++) {
+      CFD_CK(cudaMemcpy(dy, y, sizeof(double) * (size_t)nvec * nrows, cudaMemcpyHostToDevice));
+      cudaEventRecord(e0);
+      const int grid = gridFor((long long)A.nslices * 32, 256);
+      if (nvec == 1) k_spmv_multi<1><<<grid, 256>>>(A, 0, dx, ncols, dy, nrows, alpha, beta);
+      else if (nvec == 3) k_spmv_multi<3><<<grid, 256>>>(A, 0, dx, ncols, dy, nrows, alpha, beta);
+      else k_spmv_multi<6><<<grid, 256>>>(A, 0, dx, ncols, dy, nrows, alpha, beta);
+      cudaEventRecord(e1);
+      CFD_CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = std::min(best, ms);
+   }
+   CFD_CK(cudaGetLastError());
+   CFD_CK(cudaMemcpy(y, dy, sizeof(double) * (size_t)nvec * nrows, cudaMemcpyDeviceToHost));
+   if (ms_per_call) *ms_per_call = best;
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(dx); cudaFree(dy);
+   sell_free(A);
+   return CFD_OK;
+}
+
+int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x, double tol, int maxit,
+                int* its, double* ms) {
+   int ndev = 0;
+   CFD_CK(cudaGetDeviceCount(&ndev));
+   if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
+   SellHost h;
+   sell_build_host(n, n, rowStarts, col, choose_T(n, rowStarts[n]), h);
+   Sell Z;
+   const double* v[1] = {val};
+   int rc = sell_upload(h, 1, v, Z);
+   if (rc) return rc;
+   std::vector<double> dinv(n, 1.0);
+   for (int r = 0; r < n; r++)
+      for (int k = rowStarts[r]; k < rowStarts[r + 1]; k++)
+         if (col[k] == r) { dinv[r] = 1.0 / val[k]; break; }
+   double *db, *dx, *dr, *dp, *dq, *dd, *scr, *info;
+   CFD_CK(cudaMalloc(&db, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dx, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dr, 8 * (size_t)n));
+   CFD_CK(cudaMalloc(&dp, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dq, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dd, 8 * (size_t)n));
+   CFD_CK(cudaMalloc(&info, 8 * 16));
+   CFD_CK(cudaMemcpy(db, b, 8 * (size_t)n, cudaMemcpyHostToDevice));
+   CFD_CK(cudaMemcpy(dx, x, 8 * (size_t)n, cudaMemcpyHostToDevice));
+   CFD_CK(cudaMemcpy(dd, dinv.data(), 8 * (size_t)n, cudaMemcpyHostToDevice));
+   int dev = 0, sms = 0, occ = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, 512, 0));
+   const int blocks = sms * std::max(1, occ);
+   CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
+   PcgArgs a;
+   a.Z = Z; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
+   a.tol = tol; a.maxit = maxit; a.x0zero = 0;
+   void* args[] = {&a};
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   cudaEventRecord(e0);
+   CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(blocks), dim3(512), args, 0, 0));
+   cudaEventRecord(e1);
+   CFD_CK(cudaEventSynchronize(e1));
+   float t = 0;
+   cudaEventElapsedTime(&t, e0, e1);
+   double hinfo[16];
+   CFD_CK(cudaMemcpy(hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
+   CFD_CK(cudaMemcpy(x, dx, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+   if (its) *its = (int)hinfo[0];
+   if (ms) *ms = t;
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(db); cudaFree(dx); cudaFree(dr); cudaFree(dp); cudaFree(dq); cudaFree(dd); cudaFree(scr); cudaFree(info);
+   sell_free(Z);
+   return CFD_OK;
+}
+
+}   // extern "C"

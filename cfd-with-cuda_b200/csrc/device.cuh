@@ -1,0 +1,115 @@
+// Device-side data model of the fractional-step time loop (product code, sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace cfdb {
+
+#define CFD_CK(call)                                                                          \
+   do {                                                                                       \
+      cudaError_t e_ = (call);                                                                \
+      if (e_ != cudaSuccess) {                                                                \
+         cfdb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+         return CFD_ERR_CUDA;                                                                 \
+      }                                                                                       \
+   } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Sliced CSR ("SELL-32"): the device layout every CSR matrix of the reference is converted to.
+//   * rows are grouped in slices of R = 32/T rows; one warp owns one slice, T lanes share a row
+//   * every lane of a slice holds the same even number W of (col,val) entries, stored as PAIRS
+//     interleaved across the 32 lanes: entry j of lane t lives at  off + (j/2)*64 + 2*t + (j&1)
+//     -> one warp-wide load fetches 32 double2 (512 B) / 32 int2 (256 B), fully coalesced, 16-byte
+//        aligned: the 128-bit path the byte model in DESIGN.md assumes
+//   * padding entries carry val = 0 and a valid column of the same row
+//   * several value arrays (K/M/A, G1/G2/G3) share one pattern, like the reference's CSR triplets
+// ---------------------------------------------------------------------------------------------
+struct Sell {
+   int nrows = 0, ncols = 0;
+   int T = 1;              // lanes per row (1,2,4,8)
+   int R = 32;             // rows per slice
+   int nslices = 0;
+   int nval = 0;
+   long long nnz = 0;      // true non-zeros (algorithmic bytes use this)
+   long long padded = 0;   // stored entries
+   long long* sliceOff = nullptr;   // [nslices+1] entry offsets (multiples of 64)
+   int* cols = nullptr;             // [padded]
+   double* vals[3] = {nullptr, nullptr, nullptr};
+};
+
+struct SellHost {   // result of the host-side conversion
+   Sell meta;       // device pointers unset
+   std::vector<long long> sliceOff;
+   std::vector<int> cols;
+   std::vector<long long> perm;   // CSR position -> SELL position
+};
+
+int choose_T(int nrows, long long nnz);
+void sell_build_host(int nrows, int ncols, const int* rowStarts, const int* col, int T, SellHost& out);
+int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell& dev);
+void sell_free(Sell& s);
+
+// per kernel-class profile (CUDA events on the context stream)
+struct ProfEntry {
+   double ms = 0;
+   long long launches = 0;
+   double bytes = 0;
+};
+
+}   // namespace cfdb
+
+// The opaque context of include/cfdb200.h
+struct cfd_ctx {
+   cfd_problem P;   // scalar fields only are valid after init (pointers nulled)
+   cfd_options opt;
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   int numSMs = 148;
+   // matrices
+   cfdb::Sell K;    // vals[0] = K (explicit) | vals[0]=K+M ("MK"), vals[1]=M, vals[2]=A (implicit)
+   cfdb::Sell G;    // vals[0..2] = G1,G2,G3           rows = velocity nodes
+   cfdb::Sell GT;   // vals[0..2] = G1^T,G2^T,G3^T     rows = pressure nodes
+   cfdb::Sell Z;    // vals[0]
+   double* Zdinv = nullptr;     // 1/diag(Z)
+   // mesh / EBE data
+   int ldE = 0;                 // padded NE (leading dimension of the transposed element tables)
+   int* LtoGT = nullptr;        // [NENv][ldE] node ids, transposed for coalesced per-element access
+   double* coord = nullptr;     // [NN][3]
+   int* mapT = nullptr;         // implicit: [NENv*NENv][ldE] SELL positions of A entries
+   int* diagPosA = nullptr;     // implicit: [NN] SELL position of the diagonal
+   int* bcIndex = nullptr;      // [NN] whichBC or -1
+   int* bcNodes = nullptr;      // [BCnVelNodes]
+   double* BCstr = nullptr;     // [nBC][3]
+   double *MdInv = nullptr, *MdOrigInv = nullptr;
+   // named work vectors
+   std::map<std::string, std::pair<double**, long long> > vecs;
+   // explicit
+   double *Un = nullptr, *Unp1 = nullptr, *Unp1_prev = nullptr, *UnpHalf = nullptr, *UnpHalf_prev = nullptr;
+   double *Acc = nullptr, *Acc_prev = nullptr, *KtimesAcc_prev = nullptr, *R1 = nullptr, *R3 = nullptr;
+   double *Pn = nullptr, *Pnp1 = nullptr, *Pnp1_prev = nullptr, *Pdot = nullptr, *R2 = nullptr;
+   // implicit
+   double *Uk = nullptr, *Uk_prev = nullptr, *Pk = nullptr, *Pk_prev = nullptr, *Pk_prevprev = nullptr, *Pdiff = nullptr;
+   double* R1i = nullptr;       // [3][NN] the three momentum right-hand sides
+   double* Adinv = nullptr;     // [NN]
+   double* bw = nullptr;        // BiCGStab work: 7 x [3][NN]
+   // Krylov work
+   double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;
+   double* partials = nullptr;  // grid-reduction scratch
+   double* kinfo = nullptr;     // device: Krylov results (iterations, residuals)
+   double* scal = nullptr;      // device: [0..3] convergence sums, [4] maxAcc bits
+   double* h_pinned = nullptr;  // pinned host mirror for read-backs (64 doubles)
+   int pcg_blocks = 0, pcg_threads = 512, bicg_blocks = 0, bicg_threads = 512;
+   // bookkeeping
+   int timeN = 0;
+   int last_cg = 0, last_bicg[3] = {0, 0, 0};
+   long long launches = 0;
+   bool profile = false;
+   std::map<std::string, cfdb::ProfEntry> prof;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   std::vector<void*> allocs;
+};

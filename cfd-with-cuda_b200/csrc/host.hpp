@@ -1,0 +1,61 @@
+// Host side of the solver (product code): mesh input, node generation, sparsity, step0 assembly,
+// output.  Re-designed from the reference's serial O(NE*26*12) / O(NN*216) preprocessing
+// (blascoCodinaHuerta.cpp:732-2159) as hashed / sort-based O(NE) passes with OpenMP, producing the
+// same numbering and the same CSR arrays.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace cfdb {
+
+struct Mesh {
+   // .inp header (blascoCodinaHuerta.cpp:545-562)
+   int eType = 1, NE = 0, NCN = 0, NENv = 27, NENp = 8, NGP = 8;
+   double alpha = 1, dt = 0, t_ini = 0, t_final = 0;
+   int maxIter = 1;
+   double tolerance = 0, converge = 0;
+   int isRestart = 0;
+   double density = 1, viscosity = 0, fx = 0, fy = 0;
+   std::vector<double> coord;   // [node][3]; NCN rows after reading, NN rows after generate_midnodes
+   std::vector<int> LtoGnode;   // [e][NENv]
+   int nBC = 0;
+   std::vector<double> BCtype, BCstr;   // BCstr [nBC][3]
+   std::vector<int> velFaces, outFaces; // [i][3] = elem, face, bc (0-based)
+   int zeroPressureNode = -1;
+   double monCoord[3] = {0, 0, 0};
+   // derived
+   int NN = 0, NNp = 0;
+   std::vector<int> BCvelNodes;   // [i][2]
+   int BCnVelNodes = 0;
+   int monPoint = 0;
+   std::vector<int> meshColors, NmeshColors, elementsOfColor;   // setupMeshColoring (kept for API parity; kernels use atomics)
+   int nActiveColors = 0;
+};
+
+struct CsrPattern {
+   int nrows = 0, ncols = 0;
+   std::vector<int> rowStarts, col;
+   long long nnz() const { return (long long)col.size(); }
+};
+
+struct Assembled {
+   CsrPattern Mp, Gp, Zp;
+   std::vector<int> mapM, mapG, mapZ;   // [e][i][j] CSR positions
+   std::vector<double> Mval, Kval, G1, G2, G3, Zval;
+   std::vector<double> MdInv, MdOrigInv;
+};
+
+bool read_inp(const std::string& path, Mesh& m);
+void make_cavity(int nx, int ny, int nz, double cluster, int NENv, Mesh& m);
+void generate_midnodes(Mesh& m);
+void find_bc_nodes(Mesh& m);
+void find_monitor(Mesh& m);
+void color_mesh(Mesh& m);
+void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map);
+void assemble_step0(const Mesh& m, int scheme, Assembled& A);
+bool write_tecplot(const Mesh& m, const double* U, const double* P, const std::string& path, const std::string& title);
+bool read_restart(const Mesh& m, const std::string& path, double* U, double* P);
+
+}   // namespace cfdb

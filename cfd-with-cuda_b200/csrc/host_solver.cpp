@@ -1,0 +1,487 @@
+// step0 assembly, Tecplot/restart I/O and the solver-level C API (product host code).
+//
+// Replaces step0 / calculateZ / calculateZ_CUSP / calculateZGPU / createTecplot / readRestartFile /
+// main of blascoCodinaHuerta.cpp (BCH.cpp) and guermondQuartapelle.cpp (GQ.cpp).
+#include <sys/time.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "host.hpp"
+
+namespace cfdb {
+
+namespace {
+
+const int kEdgeCorner[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {0, 4}, {1, 5}, {2, 6}, {3, 7}, {4, 5}, {5, 6}, {6, 7}, {7, 4}};
+const int kFaceCorner[6][4] = {{0, 1, 2, 3}, {0, 1, 4, 5}, {1, 2, 5, 6}, {2, 3, 6, 7}, {0, 3, 4, 7}, {4, 5, 6, 7}};
+
+// Physical gradients and quadrature factors of one element at its 8 Gauss points
+// (calcJacob, BCH.cpp:2495-2711; sub-parametric: Jacobian from the 8 corners through dSp).
+struct ElemGeom {
+   double fac[8];          // detJ * weight
+   double gv[8][27][3];    // grad N_i (velocity basis)
+   double gp[8][8][3];     // grad Sp_i (pressure basis)
+};
+
+void element_geometry(const Mesh& m, const FeTables& T, int e, ElemGeom& g) {
+   const int nv = m.NENv;
+   const int* L = &m.LtoGnode[(size_t)e * nv];
+   double xc[8][3];
+   for (int i = 0; i < 8; i++)
+      for (int d = 0; d < 3; d++) xc[i][d] = m.coord[3 * (size_t)L[i] + d];
+   for (int k = 0; k < 8; k++) {
+      double J[3][3], I[3][3];
+      for (int a = 0; a < 3; a++)
+         for (int d = 0; d < 3; d++) {
+            double s = 0;
+            for (int q = 0; q < 8; q++) s += T.dSp[a][q][k] * xc[q][d];
+            J[a][d] = s;
+         }
+      const double c00 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+      const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      const double id = 1.0 / det;
+      I[0][0] = c00 * id;
+      I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+      I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+      I[1][0] = c01 * id;
+      I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+      I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+      I[2][0] = c02 * id;
+      I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+      I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+      g.fac[k] = det;   // unit Gauss weights
+      for (int i = 0; i < nv; i++)
+         for (int a = 0; a < 3; a++)
+            g.gv[k][i][a] = I[a][0] * T.dSv[0][i][k] + I[a][1] * T.dSv[1][i][k] + I[a][2] * T.dSv[2][i][k];
+      for (int i = 0; i < 8; i++)
+         for (int a = 0; a < 3; a++)
+            g.gp[k][i][a] = I[a][0] * T.dSp[0][i][k] + I[a][1] * T.dSp[1][i][k] + I[a][2] * T.dSp[2][i][k];
+   }
+}
+
+inline void atomic_add(double& t, double v) {
+#pragma omp atomic
+   t += v;
+}
+
+}   // namespace
+
+// step0 (BCH.cpp:3127-3315, GQ.cpp:3425-3572): M, K, G1..3; lumped mass and Z = sum_c G_c^T Md^-1 G_c
+// (explicit, BCH.cpp:3322-3479 / BCH.cu:281-411) or the FE Laplacian Z (implicit, GQ.cpp:3677-3772).
+// Element loop in parallel with atomic adds instead of the reference's serial loop.
+void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
+   const int NE = m.NE, nv = m.NENv, NN = m.NN, NNp = m.NNp;
+   FeTables T;
+   build_fe_tables(nv, T);
+   build_pattern(m, nv, nv, NN, NN, A.Mp, scheme == CFD_IMPLICIT ? &A.mapM : &A.mapM);
+   build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG);
+   const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp.nnz();
+   A.Mval.assign(nnzM, 0.0); A.Kval.assign(nnzM, 0.0);
+   A.G1.assign(nnzG, 0.0); A.G2.assign(nnzG, 0.0); A.G3.assign(nnzG, 0.0);
+   const double invDens = 1.0 / m.density;
+   const double mscale = scheme == CFD_IMPLICIT ? 1.0 / m.dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
+   if (scheme == CFD_IMPLICIT) {
+      build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ);
+      A.Zval.assign((size_t)A.Zp.nnz(), 0.0);
+   }
+#pragma omp parallel
+   {
+      ElemGeom* g = new ElemGeom;
+#pragma omp for schedule(static)
+      for (int e = 0; e < NE; e++) {
+         element_geometry(m, T, e, *g);
+         const int* mm = &A.mapM[(size_t)e * nv * nv];
+         for (int i = 0; i < nv; i++)
+            for (int j = 0; j < nv; j++) {
+               double me = 0, ke = 0;
+               for (int k = 0; k < 8; k++) {
+                  me += T.Sv[k][i] * T.Sv[k][j] * g->fac[k];
+                  ke += (g->gv[k][i][0] * g->gv[k][j][0] + g->gv[k][i][1] * g->gv[k][j][1] + g->gv[k][i][2] * g->gv[k][j][2]) * g->fac[k];
+               }
+               atomic_add(A.Mval[mm[i * nv + j]], mscale * me);
+               atomic_add(A.Kval[mm[i * nv + j]], m.viscosity * ke);
+            }
+         const int* mg = &A.mapG[(size_t)e * nv * 8];
+         for (int i = 0; i < nv; i++)
+            for (int j = 0; j < 8; j++) {
+               double g1 = 0, g2 = 0, g3 = 0;
+               for (int k = 0; k < 8; k++) {
+                  const double w = T.Sp[k][j] * g->fac[k];
+                  g1 += w * g->gv[k][i][0]; g2 += w * g->gv[k][i][1]; g3 += w * g->gv[k][i][2];
+               }
+               atomic_add(A.G1[mg[i * 8 + j]], -invDens * g1);
+               atomic_add(A.G2[mg[i * 8 + j]], -invDens * g2);
+               atomic_add(A.G3[mg[i * 8 + j]], -invDens * g3);
+            }
+         if (scheme == CFD_IMPLICIT) {
+            const int* mz = &A.mapZ[(size_t)e * 64];
+            for (int i = 0; i < 8; i++)
+               for (int j = 0; j < 8; j++) {
+                  double z = 0;
+                  for (int k = 0; k < 8; k++)
+                     z += (g->gp[k][i][0] * g->gp[k][j][0] + g->gp[k][i][1] * g->gp[k][j][1] + g->gp[k][i][2] * g->gp[k][j][2]) * g->fac[k];
+                  atomic_add(A.Zval[mz[i * 8 + j]], -z);
+               }
+         }
+      }
+      delete g;
+   }
+   if (scheme == CFD_EXPLICIT) {
+      // lumped mass, BC rows -> 1 (BCH.cpp:3254-3292)
+      std::vector<double> md((size_t)NN, 0.0);
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < NN; r++) {
+         double s = 0;
+         for (int k = A.Mp.rowStarts[r]; k < A.Mp.rowStarts[r + 1]; k++) s += A.Mval[k];
+         md[r] = s;
+      }
+      A.MdOrigInv.resize((size_t)3 * NN); A.MdInv.resize((size_t)3 * NN);
+      for (int c = 0; c < 3; c++)
+         for (int r = 0; r < NN; r++) { A.MdOrigInv[(size_t)c * NN + r] = 1.0 / md[r]; A.MdInv[(size_t)c * NN + r] = 1.0 / md[r]; }
+      for (int i = 0; i < m.BCnVelNodes; i++)
+         for (int c = 0; c < 3; c++) A.MdInv[(size_t)c * NN + m.BCvelNodes[2 * i]] = 1.0;
+      // Z = sum_c G_c^T diag(MdOrigInv) G_c : row-wise sparse product through the transposed pattern
+      std::vector<int> ts((size_t)NNp + 1, 0), trow(nnzG), tpos(nnzG);
+      for (size_t k = 0; k < nnzG; k++) ts[A.Gp.col[k] + 1]++;
+      for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
+      {
+         std::vector<int> fill(ts.begin(), ts.end() - 1);
+         for (int r = 0; r < NN; r++)
+            for (int k = A.Gp.rowStarts[r]; k < A.Gp.rowStarts[r + 1]; k++) {
+               const int p = fill[A.Gp.col[k]]++;
+               trow[p] = r; tpos[p] = k;
+            }
+      }
+      A.Zp.nrows = A.Zp.ncols = NNp;
+      A.Zp.rowStarts.assign((size_t)NNp + 1, 0);
+      std::vector<std::vector<int> > zc(NNp);
+      std::vector<std::vector<double> > zv(NNp);
+#pragma omp parallel
+      {
+         std::vector<double> acc((size_t)NNp, 0.0);
+         std::vector<int> mark((size_t)NNp, -1), list;
+#pragma omp for schedule(dynamic, 256)
+         for (int i = 0; i < NNp; i++) {
+            list.clear();
+            for (int t = ts[i]; t < ts[i + 1]; t++) {
+               const int r = trow[t];
+               const double d = md[r];
+               const double w1 = A.G1[tpos[t]] / d, w2 = A.G2[tpos[t]] / d, w3 = A.G3[tpos[t]] / d;
+               for (int k = A.Gp.rowStarts[r]; k < A.Gp.rowStarts[r + 1]; k++) {
+                  const int j = A.Gp.col[k];
+                  if (mark[j] != i) { mark[j] = i; acc[j] = 0.0; list.push_back(j); }
+                  acc[j] += w1 * A.G1[k] + w2 * A.G2[k] + w3 * A.G3[k];
+               }
+            }
+            std::sort(list.begin(), list.end());
+            zc[i] = list;
+            zv[i].resize(list.size());
+            for (size_t q = 0; q < list.size(); q++) zv[i][q] = acc[list[q]];
+         }
+      }
+      for (int i = 0; i < NNp; i++) A.Zp.rowStarts[i + 1] = A.Zp.rowStarts[i] + (int)zc[i].size();
+      A.Zp.col.resize((size_t)A.Zp.rowStarts[NNp]);
+      A.Zval.resize((size_t)A.Zp.rowStarts[NNp]);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < NNp; i++) {
+         std::copy(zc[i].begin(), zc[i].end(), A.Zp.col.begin() + A.Zp.rowStarts[i]);
+         std::copy(zv[i].begin(), zv[i].end(), A.Zval.begin() + A.Zp.rowStarts[i]);
+      }
+   }
+   // pressure pin: diagonal * 1000, only for node > 0 (applyBC_Step2(1), BCH.cpp:4167-4180)
+   const int pin = m.zeroPressureNode;
+   if (pin > 0)
+      for (int k = A.Zp.rowStarts[pin]; k < A.Zp.rowStarts[pin + 1]; k++)
+         if (A.Zp.col[k] == pin) { A.Zval[k] *= 1000.0; break; }
+}
+
+// createTecplot (BCH.cpp:4249-4482): same bytes (TITLE / VARIABLES / ZONE lines, `scientific`
+// precision 11 rows, 8 sub-bricks per Q2 element), written through one large buffer.
+bool write_tecplot(const Mesh& m, const double* U, const double* P, const std::string& path, const std::string& title) {
+   FILE* f = fopen(path.c_str(), "w");
+   if (!f) { set_error("cannot write %s", path.c_str()); return false; }
+   const int NN = m.NN, nv = m.NENv, NE = m.NE;
+   std::vector<char> iobuf(1 << 22);
+   setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+   fprintf(f, "TITLE = %s\n", title.c_str());
+   fprintf(f, "VARIABLES = x,  y,  z,  u, v, w, p\n");
+   fprintf(f, "ZONE N=%d, E=%d, F=FEPOINT, ET=BRICK\n", NN, nv == 27 ? 8 * NE : NE);
+   std::vector<double> pn((size_t)NN, 0.0);
+   std::copy(P, P + m.NNp, pn.begin());
+   if (nv == 27)
+      for (int e = 0; e < NE; e++) {   // element order matters: later elements overwrite shared nodes (BCH.cpp:4299-4436)
+         const int* L = &m.LtoGnode[(size_t)e * nv];
+         for (int ed = 0; ed < 12; ed++) pn[L[8 + ed]] = 0.5 * (pn[L[kEdgeCorner[ed][0]]] + pn[L[kEdgeCorner[ed][1]]]);
+         for (int fc = 0; fc < 6; fc++)
+            pn[L[20 + fc]] = 0.25 * (pn[L[kFaceCorner[fc][0]]] + pn[L[kFaceCorner[fc][1]]] + pn[L[kFaceCorner[fc][2]]] + pn[L[kFaceCorner[fc][3]]]);
+         pn[L[26]] = 0.125 * (pn[L[0]] + pn[L[1]] + pn[L[2]] + pn[L[3]] + pn[L[4]] + pn[L[5]] + pn[L[6]] + pn[L[7]]);
+      }
+   for (int i = 0; i < NN; i++)
+      fprintf(f, "%.11e %.11e %.11e %.11e %.11e %.11e %.11e\n", m.coord[3 * (size_t)i], m.coord[3 * (size_t)i + 1], m.coord[3 * (size_t)i + 2],
+              U[i], U[(size_t)NN + i], U[2 * (size_t)NN + i], pn[i]);
+   static const int sub[8][8] = {{0, 8, 20, 11, 12, 21, 26, 24},  {8, 1, 9, 20, 21, 13, 22, 26},  {11, 20, 10, 3, 24, 26, 23, 15},
+                                 {20, 9, 2, 10, 26, 22, 14, 23},  {12, 21, 26, 24, 4, 16, 25, 19}, {21, 13, 22, 26, 16, 5, 17, 25},
+                                 {24, 26, 23, 15, 19, 25, 18, 7}, {26, 22, 14, 23, 25, 17, 6, 18}};
+   for (int e = 0; e < NE; e++) {
+      const int* L = &m.LtoGnode[(size_t)e * nv];
+      if (nv == 27) {
+         for (int s = 0; s < 8; s++)
+            fprintf(f, "%d %d %d %d %d %d %d %d\n", L[sub[s][0]] + 1, L[sub[s][1]] + 1, L[sub[s][2]] + 1, L[sub[s][3]] + 1, L[sub[s][4]] + 1,
+                    L[sub[s][5]] + 1, L[sub[s][6]] + 1, L[sub[s][7]] + 1);
+      } else {
+         // Q1/Q1: the reference writer reads local nodes 8..26 and cannot run; one brick per element
+         fprintf(f, "%d %d %d %d %d %d %d %d\n", L[0] + 1, L[1] + 1, L[2] + 1, L[3] + 1, L[4] + 1, L[5] + 1, L[6] + 1, L[7] + 1);
+      }
+   }
+   const bool ok = !ferror(f);
+   fclose(f);
+   if (!ok) set_error("write error on %s", path.c_str());
+   return ok;
+}
+
+// readRestartFile (BCH.cpp:4214-4242): 3 header lines, then NN rows x y z u v w p (p kept for the
+// first NCN rows only).
+bool read_restart(const Mesh& m, const std::string& path, double* U, double* P) {
+   FILE* f = fopen(path.c_str(), "r");
+   if (!f) { set_error("cannot open %s", path.c_str()); return false; }
+   char line[512];
+   for (int i = 0; i < 3; i++)
+      if (!fgets(line, sizeof line, f)) { fclose(f); set_error("%s: truncated header", path.c_str()); return false; }
+   for (int i = 0; i < m.NN; i++) {
+      double x, y, z, u, v, w, p;
+      if (!fgets(line, sizeof line, f) || sscanf(line, "%lf %lf %lf %lf %lf %lf %lf", &x, &y, &z, &u, &v, &w, &p) != 7) {
+         fclose(f);
+         set_error("%s: malformed row %d", path.c_str(), i);
+         return false;
+      }
+      U[i] = u; U[(size_t)m.NN + i] = v; U[2 * (size_t)m.NN + i] = w;
+      if (i < m.NCN) P[i] = p;
+   }
+   fclose(f);
+   return true;
+}
+
+}   // namespace cfdb
+
+// =================================================================================================
+// Solver-level C API
+// =================================================================================================
+using namespace cfdb;
+
+struct cfd_solver {
+   Mesh mesh;
+   Assembled A;
+   cfd_problem prob;
+   cfd_options opt;
+   cfd_ctx* ctx = nullptr;
+   int scheme = 0;
+   std::vector<double> U0, P0;
+   double timeT = 0;
+};
+
+namespace {
+
+double now_s() {
+   timeval tv;
+   gettimeofday(&tv, nullptr);
+   return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::string& restartPath, int init_gpu) {
+   Mesh& m = s->mesh;
+   s->scheme = scheme;
+   if (opt) s->opt = *opt; else cfd_default_options(&s->opt);
+   generate_midnodes(m);
+   find_bc_nodes(m);
+   find_monitor(m);
+   assemble_step0(m, scheme, s->A);
+   cfd_problem& P = s->prob;
+   memset(&P, 0, sizeof P);
+   P.scheme = scheme; P.NE = m.NE; P.NN = m.NN; P.NNp = m.NNp; P.NENv = m.NENv; P.NENp = m.NENp; P.NGP = m.NGP;
+   P.dt = m.dt; P.density = m.density; P.viscosity = m.viscosity; P.maxIter = m.maxIter; P.tolerance = m.tolerance;
+   P.convergenceCriteria = m.converge;
+   P.coord = m.coord.data(); P.LtoGnode = m.LtoGnode.data();
+   P.sparseM_nnz = (int)s->A.Mp.nnz(); P.sparseMrowStarts = s->A.Mp.rowStarts.data(); P.sparseMcol = s->A.Mp.col.data();
+   P.sparseKvalue = s->A.Kval.data(); P.sparseMvalue = s->A.Mval.data();
+   P.sparseG_nnz = (int)s->A.Gp.nnz(); P.sparseGrowStarts = s->A.Gp.rowStarts.data(); P.sparseGcol = s->A.Gp.col.data();
+   P.sparseG1value = s->A.G1.data(); P.sparseG2value = s->A.G2.data(); P.sparseG3value = s->A.G3.data();
+   P.sparseZ_nnz = (int)s->A.Zp.nnz(); P.sparseZrowStarts = s->A.Zp.rowStarts.data(); P.sparseZcol = s->A.Zp.col.data();
+   P.sparseZvalue = s->A.Zval.data();
+   P.sparseMapM_1d = s->A.mapM.data();
+   P.MdInv = s->A.MdInv.empty() ? nullptr : s->A.MdInv.data();
+   P.MdOrigInv = s->A.MdOrigInv.empty() ? nullptr : s->A.MdOrigInv.data();
+   P.BCnVelNodes = m.BCnVelNodes; P.BCvelNodes = m.BCvelNodes.data(); P.nBC = m.nBC; P.BCstr = m.BCstr.data();
+   P.zeroPressureNode = m.zeroPressureNode; P.monPoint = m.monPoint;
+   if (m.isRestart == 1 && !restartPath.empty()) {
+      s->U0.assign((size_t)3 * m.NN, 0.0); s->P0.assign((size_t)m.NNp, 0.0);
+      if (!read_restart(m, restartPath, s->U0.data(), s->P0.data())) return CFD_ERR_IO;
+      P.U0 = s->U0.data(); P.P0 = s->P0.data();
+   }
+   s->timeT = m.t_ini;
+   if (!init_gpu) return CFD_OK;
+   return cfd_initializeAndAllocateGPU(&P, &s->opt, &s->ctx);
+}
+
+}   // namespace
+
+extern "C" {
+
+int cfd_solver_create_from_inp(const char* inp_path, int scheme, const cfd_options* opt, int init_gpu, cfd_solver** out) {
+   if (!inp_path || !out) { set_error("null argument"); return CFD_ERR_ARG; }
+   *out = nullptr;
+   cfd_solver* s = new cfd_solver();
+   if (!read_inp(inp_path, s->mesh)) { delete s; return CFD_ERR_IO; }
+   std::string base(inp_path);
+   const size_t dot = base.rfind(".inp");
+   if (dot != std::string::npos) base = base.substr(0, dot);
+   int rc = finish_create(s, scheme, opt, base + "_restart.dat", init_gpu);
+   if (rc) { delete s; return rc; }
+   *out = s;
+   return CFD_OK;
+}
+
+int cfd_solver_create_cavity(int nx, int ny, int nz, double cluster, int NENv, int scheme, double dt, double viscosity, int maxIter,
+                             double tolerance, const cfd_options* opt, int init_gpu, cfd_solver** out) {
+   if (!out || nx < 1 || ny < 1 || nz < 1 || (NENv != 8 && NENv != 27)) { set_error("bad cavity arguments"); return CFD_ERR_ARG; }
+   if (cluster != 0.0 && ((nx | ny | nz) & 1)) { set_error("clustering needs even element counts"); return CFD_ERR_ARG; }
+   *out = nullptr;
+   cfd_solver* s = new cfd_solver();
+   make_cavity(nx, ny, nz, cluster, NENv, s->mesh);
+   s->mesh.dt = dt; s->mesh.viscosity = viscosity; s->mesh.maxIter = maxIter; s->mesh.tolerance = tolerance;
+   s->mesh.converge = 1e-6; s->mesh.t_final = 1e30; s->mesh.density = 1.0;
+   int rc = finish_create(s, scheme, opt, "", init_gpu);
+   if (rc) { delete s; return rc; }
+   *out = s;
+   return CFD_OK;
+}
+
+int cfd_solver_init_gpu(cfd_solver* s) {
+   if (!s) return CFD_ERR_ARG;
+   if (s->ctx) return CFD_OK;
+   return cfd_initializeAndAllocateGPU(&s->prob, &s->opt, &s->ctx);
+}
+
+void cfd_solver_destroy(cfd_solver* s) {
+   if (!s) return;
+   cfd_destroy(s->ctx);
+   delete s;
+}
+cfd_ctx* cfd_solver_ctx(cfd_solver* s) { return s ? s->ctx : nullptr; }
+const cfd_problem* cfd_solver_problem(cfd_solver* s) { return s ? &s->prob : nullptr; }
+
+long long cfd_solver_int(cfd_solver* s, const char* name) {
+   const std::string n(name);
+   const Mesh& m = s->mesh;
+   if (n == "NE") return m.NE; if (n == "NCN") return m.NCN; if (n == "NN") return m.NN; if (n == "NNp") return m.NNp;
+   if (n == "NENv") return m.NENv; if (n == "nnzM") return s->A.Mp.nnz(); if (n == "nnzG") return s->A.Gp.nnz();
+   if (n == "nnzZ") return s->A.Zp.nnz(); if (n == "BCnVelNodes") return m.BCnVelNodes; if (n == "monPoint") return m.monPoint;
+   if (n == "zeroPressureNode") return m.zeroPressureNode; if (n == "maxIter") return m.maxIter; if (n == "isRestart") return m.isRestart;
+   if (n == "nActiveColors") { if (m.meshColors.empty()) color_mesh(s->mesh); return s->mesh.nActiveColors; }
+   return -999999;
+}
+
+const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, int* is_int) {
+   const std::string n(name);
+   Mesh& m = s->mesh;
+   Assembled& A = s->A;
+#define DV(nm, v) if (n == nm) { *count = (long long)(v).size(); *is_int = 0; return (v).data(); }
+#define IV(nm, v) if (n == nm) { *count = (long long)(v).size(); *is_int = 1; return (v).data(); }
+   DV("coord", m.coord) IV("LtoGnode", m.LtoGnode) IV("BCvelNodes", m.BCvelNodes) DV("BCstr", m.BCstr)
+   IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp.rowStarts) IV("sparseGcol", A.Gp.col)
+   IV("sparseZrowStarts", A.Zp.rowStarts) IV("sparseZcol", A.Zp.col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG)
+   DV("sparseMvalue", A.Mval) DV("sparseKvalue", A.Kval) DV("sparseG1value", A.G1) DV("sparseG2value", A.G2) DV("sparseG3value", A.G3)
+   DV("sparseZvalue", A.Zval) DV("MdInv", A.MdInv) DV("MdOrigInv", A.MdOrigInv)
+   if (n == "meshColors" || n == "NmeshColors" || n == "elementsOfColor") {
+      if (m.meshColors.empty()) color_mesh(m);
+      IV("meshColors", m.meshColors) IV("NmeshColors", m.NmeshColors) IV("elementsOfColor", m.elementsOfColor)
+   }
+#undef DV
+#undef IV
+   *count = -1; *is_int = 0;
+   return nullptr;
+}
+
+int cfd_solver_write_tecplot(cfd_solver* s, const char* dat_path, const char* title) {
+   std::vector<double> U((size_t)3 * s->mesh.NN), P((size_t)s->mesh.NNp);
+   int rc = cfd_get_fields(s->ctx, U.data(), P.data());
+   if (rc) return rc;
+   return write_tecplot(s->mesh, U.data(), P.data(), dat_path, title) ? CFD_OK : CFD_ERR_IO;
+}
+
+int cfd_solver_read_restart(cfd_solver* s, const char* dat_path) {
+   std::vector<double> U((size_t)3 * s->mesh.NN, 0.0), P((size_t)s->mesh.NNp, 0.0);
+   if (!read_restart(s->mesh, dat_path, U.data(), P.data())) return CFD_ERR_IO;
+   const bool ex = s->scheme == CFD_EXPLICIT;
+   int rc = cfd_upload(s->ctx, ex ? "Un" : "Uk_prev", U.data(), (long long)U.size());
+   if (rc) return rc;
+   return cfd_upload(s->ctx, ex ? "Pn" : "Pk_prev", P.data(), (long long)P.size());
+}
+
+// The reference's main() + timeLoop() (BCH.cpp:383-520, 2815-3120 / GQ.cpp:367-500, 3266-3418):
+// ./ProblemName.txt -> <name>.inp -> monitor table on stdout -> <name>.dat.
+int cfd_solver_main(const char* workdir, int scheme, int max_steps) {
+   const std::string dir = (workdir && *workdir) ? std::string(workdir) + "/" : std::string();
+   std::ifstream pn((dir + "ProblemName.txt").c_str());
+   std::string name;
+   if (!(pn >> name)) { set_error("cannot read %sProblemName.txt", dir.c_str()); return CFD_ERR_IO; }
+   printf("\n\n*********************************************************");
+   printf("\n*    3D Unsteady Incompressible Navier-Stokes Solver    *");
+   printf("\n*  %s  *", scheme == CFD_EXPLICIT ? "     Formulation of Blasco, Codina & Huerta        " : "     Formulation of Guermond & Quartapelle         ");
+   printf("\n*        B200-native fractional-step time loop          *");
+   printf("\n*********************************************************\n\n");
+   double t0 = now_s();
+   cfd_solver* s = nullptr;
+   int rc = cfd_solver_create_from_inp((dir + name + ".inp").c_str(), scheme, nullptr, 1, &s);
+   if (rc) return rc;
+   const Mesh& m = s->mesh;
+   printf("readInputFile() .. step0() took  %8.3f seconds.\n", now_s() - t0);
+   printf("\n NN = %d\n NNp = %d\n sparseM_NNZ = %lld\n sparseG_NNZ = %lld\n", m.NN, m.NNp, 3 * s->A.Mp.nnz(), 3 * s->A.Gp.nnz());
+   printf("\n\nMonitoring node is %d, with coordinates [%f, %f, %f]\n\n\n", m.monPoint, m.coord[3 * (size_t)m.monPoint],
+          m.coord[3 * (size_t)m.monPoint + 1], m.coord[3 * (size_t)m.monPoint + 2]);
+   const std::string dat = dir + name + ".dat";
+   if ((rc = cfd_solver_write_tecplot(s, dat.c_str(), name.c_str()))) { cfd_solver_destroy(s); return rc; }   // initial state (BCH.cpp:2801)
+   if (scheme == CFD_EXPLICIT) {
+      printf("Time step  Iter     Time       u_monitor     v_monitor     w_monitor     p_monitor     TimeSpend      maxAcc \n");
+      printf("-------------------------------------------------------------------------------------------------------------\n");
+   } else {
+      printf("Time step  Time       u_monitor     v_monitor     w_monitor     p_monitor     TimeSpend      maxAcc \n");
+      printf("----------------------------------------------------------------------------------------------------\n");
+   }
+   double timeT = m.t_ini;
+   int timeN = 0;
+   const double tStart = now_s();
+   while (timeT < m.t_final) {
+      if (max_steps > 0 && timeN >= max_steps) break;
+      const double ts = now_s();
+      timeN++;
+      timeT += m.dt;
+      cfd_step_report rep;
+      int done = 0;
+      if ((rc = cfd_timeLoop(s->ctx, 1, 0, &rep, &done))) { cfd_solver_destroy(s); return rc; }
+      const double spent = now_s() - ts;
+      if (scheme == CFD_EXPLICIT)
+         printf("%6d  %6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, rep.iter, timeT, rep.monitor[0], rep.monitor[1],
+                rep.monitor[2], rep.monitor[3], spent, rep.maxAcc);
+      else
+         printf("%6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, timeT, rep.monitor[0], rep.monitor[1], rep.monitor[2],
+                rep.monitor[3], spent, rep.maxAcc);
+      if (rep.steady) {
+         cfd_solver_write_tecplot(s, dat.c_str(), name.c_str());
+         break;
+      }
+      if (timeN % 1000 == 0 || std::fabs(timeT - m.t_final) < 1e-10) cfd_solver_write_tecplot(s, dat.c_str(), name.c_str());
+   }
+   printf("\nTotal run took %10.3f seconds.\n", now_s() - tStart);
+   printf("\nThe program is terminated successfully.\n\n\n");
+   rc = cfd_solver_write_tecplot(s, dat.c_str(), name.c_str());   // BCH.cpp:517
+   cfd_solver_destroy(s);
+   return rc;
+}
+
+}   // extern "C"

@@ -1,0 +1,206 @@
+/* =============================================================================
+ * cfdb200.h -- C ABI of the B200-native fractional-step FE Navier-Stokes time loop.
+ *
+ * Drop-in boundary for the GPU seam of mmgocmen/cfd-with-cuda: the set of
+ * `...GPU()` functions that the reference's host code calls under `#ifdef USECUDA`
+ *   explicit (Blasco-Codina-Huerta):  fractionalStep/explicit/Cpp/blascoCodinaHuerta.cpp:365-377
+ *   implicit (Guermond-Quartapelle):  fractionalStep/implicit/Cpp/guermondQuartapelle.cpp:350-361
+ * The reference shares ~60 `extern` globals with its CUDAcodes.cu; here the same
+ * arrays travel in one POD struct (`cfd_problem`, caller-owned, copied at init) and
+ * all device state lives in an opaque `cfd_ctx`.  Names keep the reference's
+ * (`step1GPUpart`, `step2GPU`, ...) with a `bch_` / `gq_` prefix for the two solvers.
+ *
+ * All functions return 0 on success, a negative code on failure
+ * (`cfd_last_error()` gives the message).  Nothing here blocks on stdin and no
+ * function allocates device memory after `cfd_initializeAndAllocateGPU`.
+ * Plain pointers and sizes only: no C++ or torch types cross this boundary.
+ * ============================================================================= */
+#ifndef CFDB200_H
+#define CFDB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFD_EXPLICIT 0 /* blascoCodinaHuerta */
+#define CFD_IMPLICIT 1 /* guermondQuartapelle */
+
+#define CFD_OK 0
+#define CFD_ERR_ARG (-1)
+#define CFD_ERR_CUDA (-2)
+#define CFD_ERR_IO (-3)
+#define CFD_ERR_NCCL (-4)
+#define CFD_ERR_STATE (-5)
+
+typedef struct cfd_ctx cfd_ctx;
+
+/* The data model a replacement consumes.  Field names are the
+ * reference's globals; every array is host memory, read-only, copied during init. */
+typedef struct cfd_problem {
+   int scheme;                /* CFD_EXPLICIT | CFD_IMPLICIT */
+   int NE, NN, NNp;           /* elements, velocity nodes, pressure nodes (BCH.cpp:150-160) */
+   int NENv, NENp, NGP;       /* 27|8, 8, 8 */
+   double dt, density, viscosity;
+   int maxIter;               /* explicit inner iterations per step (inp `maxIter`) */
+   double tolerance;          /* explicit inner-iteration tolerance (inp `tolerance`) */
+   double convergenceCriteria;/* steady-state tolerance (inp `converge`) */
+   const double* coord;       /* [NN][3]   (BCH.cpp coord) */
+   const int* LtoGnode;       /* [NE][NENv] (BCH.cpp LtoGnode; LtoGvel_1d = c*NN + LtoGnode) */
+   /* one NN x NN pattern shared by K, M, A (BCH.cpp:212-219) */
+   int sparseM_nnz;           /* nnz of ONE block (= reference sparseM_NNZ / 3) */
+   const int* sparseMrowStarts;
+   const int* sparseMcol;
+   const double* sparseKvalue;
+   const double* sparseMvalue;  /* implicit only: int N_i N_j / dt (GQ.cpp:3495) */
+   /* one NN x NNp pattern shared by G1, G2, G3 (BCH.cpp:221-229) */
+   int sparseG_nnz;           /* nnz of ONE block (= reference sparseG_NNZ / 3) */
+   const int* sparseGrowStarts;
+   const int* sparseGcol;
+   const double* sparseG1value;
+   const double* sparseG2value;
+   const double* sparseG3value;
+   /* pressure matrix Z, full (both triangles), 0-based, pin already applied (BCH.cu:281-411, GQ.cpp:3677-3772) */
+   int sparseZ_nnz;
+   const int* sparseZrowStarts;
+   const int* sparseZcol;
+   const double* sparseZvalue;
+   const int* sparseMapM_1d;  /* implicit only: [NE][NENv][NENv] CSR positions (BCH.cpp:1887-1898) */
+   const double* MdInv;       /* explicit only: [3NN], BC rows = 1 (BCH.cpp:3283-3292) */
+   const double* MdOrigInv;   /* explicit only: [3NN] */
+   int BCnVelNodes;
+   const int* BCvelNodes;     /* [BCnVelNodes][2] = node, whichBC (BCH.cpp:199) */
+   int nBC;
+   const double* BCstr;       /* [nBC][3] */
+   int zeroPressureNode;      /* 0-based; applied only when > 0 (BCH.cpp:4172) */
+   int monPoint;              /* monitor node (BCH.cpp:1646-1668) */
+   const double* U0;          /* [3NN] initial Un (explicit) / Uk_prev (implicit), BCs applied; NULL = zeros + BCs */
+   const double* P0;          /* [NNp] initial pressure; NULL = zeros */
+} cfd_problem;
+
+/* Solver settings the reference hard-codes (BCH.cu:433, GQ.cu:344,404) plus the
+ * switches that select between its four mutually inconsistent builds. */
+typedef struct cfd_options {
+   double cg_tol;     /* default 1e-6: stop when ||r||_2 <= cg_tol * ||b||_2 */
+   int cg_maxit;      /* default 1000 */
+   int cg_warm_start; /* explicit only. 0 (default) = x0 = 0 (BCH.cpp:3997); 1 = previous Pdot (BCH.cu:418-451) */
+   double bicg_tol;   /* default 1e-6 */
+   int bicg_maxit;    /* default 1000 */
+   int maxacc_rule;   /* 0 (default) = max|dU|/dt (BCH.cpp:3053); 1 = max|dU| (BCH.cu:107-117) */
+   int device;        /* CUDA device ordinal; -1 = current device */
+   int reserved[8];
+} cfd_options;
+
+void cfd_default_options(cfd_options* opt);
+const char* cfd_last_error(void);
+const char* cfd_version(void);
+
+/* replaces selectCUDAdevice()            BCH.cu:126-154 (no "last device" heuristic: explicit ordinal) */
+int cfd_selectCUDAdevice(int device);
+/* replaces initializeAndAllocateGPU()    BCH.cu:161-273 / GQ.cu:166-295: uploads the problem, converts
+ * the CSR matrices to the device layout, allocates every work vector. */
+int cfd_initializeAndAllocateGPU(const cfd_problem* prob, const cfd_options* opt, cfd_ctx** out);
+void cfd_destroy(cfd_ctx* ctx);
+
+/* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
+ * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);
+ * "Uk","Uk_prev","Pk","Pk_prev","Pk_prevprev","Pdiff","R1","R2","sparseAvalue" (implicit). */
+int cfd_download(cfd_ctx* ctx, const char* name, double* host, long long count);
+int cfd_upload(cfd_ctx* ctx, const char* name, const double* host, long long count);
+/* current velocity [3NN] and pressure [NNp] (Un/Pn or Uk_prev/Pk_prev after a completed step) */
+int cfd_get_fields(cfd_ctx* ctx, double* U, double* P);
+
+/* ---- explicit seam (call order = timeLoop, BCH.cpp:2859-3118) ------------------------------- */
+int bch_beginTimeStep(cfd_ctx* ctx);               /* D2D copies + memset at BCH.cpp:2866-2869 */
+int bch_calculateMatrixAGPU(cfd_ctx* ctx);         /* BCH.cu:906-939  R1 = -C(Un) UnpHalf_prev */
+int bch_step1GPUpart(cfd_ctx* ctx, int iter);      /* BCH.cu:946-973 */
+int bch_step2GPU(cfd_ctx* ctx, int iter);          /* BCH.cu:980-1022 (+ CUSP_CG_solver :418-451) */
+int bch_step3GPU(cfd_ctx* ctx, int iter);          /* BCH.cu:1029-1060 */
+int bch_checkConvergenceGPU(cfd_ctx* ctx, int* converged); /* BCH.cu:1084-1121 */
+int bch_rotateIterates(cfd_ctx* ctx);              /* the four D2D copies at BCH.cpp:2929-2932 */
+int bch_calculate_KtimesAcc_prevGPU(cfd_ctx* ctx); /* BCH.cu:1067-1077 */
+int bch_checkConvergenceInTimeGPU(cfd_ctx* ctx, int* steady, double* maxAcc); /* BCH.cu:1151-1178 */
+int bch_endTimeStep(cfd_ctx* ctx);                 /* Un<-Unp1, Pn<-Pnp1, BCH.cpp:3070-3071 */
+
+/* ---- implicit seam (GQ.cpp:3308-3416) ------------------------------------------------------- */
+int gq_calculateMatrixAGPU(cfd_ctx* ctx);          /* GQ.cu:726-754 (A += C(Uk_prev); A must hold M+K) */
+int gq_step1GPU(cfd_ctx* ctx);                     /* GQ.cu:761-890 */
+int gq_step2GPU(cfd_ctx* ctx);                     /* GQ.cu:897-944 */
+int gq_checkConvergenceInTimeGPU(cfd_ctx* ctx, int* steady, double* maxAcc); /* GQ.cu:975-1002 */
+int gq_endTimeStep(cfd_ctx* ctx);                  /* rotations at GQ.cpp:3366-3368 */
+
+/* replaces printMonitorDataGPU()  BCH.cu:1128-1144 / GQ.cu:951-967: out[4] = u,v,w,p at monPoint
+ * (a 4-double read-back instead of the reference's full-field D2H). */
+int cfd_printMonitorDataGPU(cfd_ctx* ctx, double out[4]);
+
+/* Krylov statistics of the most recent step2 / step1 call */
+int cfd_last_cg_iterations(cfd_ctx* ctx);
+int cfd_last_bicgstab_iterations(cfd_ctx* ctx, int its[3]);
+
+/* ---- whole time steps (the fused fast path; same arithmetic as the seam sequence) ------------ */
+typedef struct cfd_step_report {
+   int timeN;            /* step counter after this step */
+   int iter;             /* explicit: value the reference prints (maxIter+1 if not converged); implicit: 1 */
+   int cg_iterations;    /* summed over the step's pressure solves */
+   int cg_solves;
+   int bicg_iterations[3];
+   double maxAcc;
+   int steady;           /* maxAcc <= convergenceCriteria */
+   double monitor[4];    /* u,v,w,p at monPoint */
+} cfd_step_report;
+/* runs `nsteps` passes of the time-loop body; `reports` may be NULL or hold nsteps entries.
+ * Stops early (returning the number of steps done in *done) when a step reports steady state
+ * and stop_on_steady != 0. */
+int cfd_timeLoop(cfd_ctx* ctx, int nsteps, int stop_on_steady, cfd_step_report* reports, int* done);
+
+/* ---- timing / roofline instrumentation --------------------------------------------------------
+ * Per-kernel-class accumulated CUDA-event time on the context's stream (enabled by cfd_profile(ctx,1)).
+ * names: "ebe","spmv_k","spmv_g","spmv_gt","pcg","bicgstab","update","assemble". */
+int cfd_profile(cfd_ctx* ctx, int enable);
+int cfd_profile_get(cfd_ctx* ctx, const char* name, double* ms, long long* launches, double* bytes);
+long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context so far */
+
+/* ---- stand-alone kernels on caller data (micro-benchmarks and parity tests) ------------------- */
+/* y = alpha*A*x + beta*y for `nvec` vectors sharing one CSR matrix; x is [nvec][ncols], y [nvec][nrows] host arrays */
+int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, const double* val, int nvec,
+                 const double* x, double* y, double alpha, double beta, int repeat, double* ms_per_call);
+/* Jacobi-PCG on a CSR matrix: returns iterations in *its */
+int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x,
+                double tol, int maxit, int* its, double* ms);
+
+/* =============================================================================
+ * Solver-level API: the whole `solverGPU` program of the reference as a library
+ * (readInputFile -> preprocessing -> step0 -> timeLoop -> createTecplot), host side
+ * written from scratch in C++ (csrc/host_*.cpp).
+ * ============================================================================= */
+typedef struct cfd_solver cfd_solver;
+
+/* Reads `<path>` (the reference's .inp grammar, BCH.cpp:528-725), generates mid-edge/face/centre
+ * nodes with the reference's numbering, builds CSR patterns, assembles M,K,G,Z (step0). */
+int cfd_solver_create_from_inp(const char* inp_path, int scheme, const cfd_options* opt, int init_gpu, cfd_solver** out);
+/* Same, for an in-memory structured nx*ny*nz cavity (cube generator numbering)
+ * without the text round trip: used for the 128^3 / 256^3 synthetic configs.  NENv = 8 or 27. */
+int cfd_solver_create_cavity(int nx, int ny, int nz, double cluster, int NENv, int scheme, double dt,
+                             double viscosity, int maxIter, double tolerance, const cfd_options* opt,
+                             int init_gpu, cfd_solver** out);
+/* init_gpu = 0 above stops after step0 (host arrays only, no CUDA call: what the CPU-side tests
+ * use); this uploads the problem afterwards. */
+int cfd_solver_init_gpu(cfd_solver* s);
+void cfd_solver_destroy(cfd_solver* s);
+cfd_ctx* cfd_solver_ctx(cfd_solver* s);
+const cfd_problem* cfd_solver_problem(cfd_solver* s);
+/* integer facts by name: "NE","NCN","NN","NNp","nnzM","nnzG","nnzZ","BCnVelNodes","monPoint",
+ * "zeroPressureNode","nActiveColors" */
+long long cfd_solver_int(cfd_solver* s, const char* name);
+/* host arrays by name (reference global names, see cfd_problem) -> pointer + count */
+const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, int* is_int);
+/* createTecplot() BCH.cpp:4249-4482 and readRestartFile() BCH.cpp:4214-4242 */
+int cfd_solver_write_tecplot(cfd_solver* s, const char* dat_path, const char* title);
+int cfd_solver_read_restart(cfd_solver* s, const char* dat_path);
+/* the reference's main(): reads ./ProblemName.txt, runs to t_final, prints the monitor table,
+ * writes <name>.dat.  max_steps > 0 bounds the run. */
+int cfd_solver_main(const char* workdir, int scheme, int max_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFDB200_H */
