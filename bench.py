@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the fractional-step time loop (contract: see the task statement / DESIGN.md section 7).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one JSON line on rank 0
+  python bench.py --impl reference --steps K --warmup W    # the CPU oracle (reference restatement), host cores
+
+A "step" is one pass of the time-loop body (BCH.cpp:2859-3118 / GQ.cpp:3308-3416) over the whole mesh.
+metric = time steps/s.  `value`: state resident in HBM, CUDA-event time on the launch stream.
+`e2e`: same steps driven through cfd_timeStep_host with pinned HOST buffers (H2D + step + D2H per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cfd-with-cuda_b200"))
+
+WORKLOADS = {
+    # BASELINE.json configs[4] (the config the metric is quoted on), single-GPU form
+    "cavity256_q1_implicit": dict(n=256, NENv=8, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    # configs[3]
+    "cavity128_q1_implicit": dict(n=128, NENv=8, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity128_q1_explicit": dict(n=128, NENv=8, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity64_q2_explicit": dict(n=64, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity64_q2_implicit": dict(n=64, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    # configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (30^3 Q2/Q1, sinh clustering 2.0)
+    "ne27000_explicit": dict(n=30, NENv=27, scheme="explicit", cluster=2.0, viscosity=0.01, dt=1e-3, inp=True),
+    "ne27000_implicit": dict(n=30, NENv=27, scheme="implicit", cluster=2.0, viscosity=0.001, dt=1e-3, inp=True),
+}
+DEFAULT_WORKLOAD = "cavity128_q1_implicit"
+CPU_SAMPLE_N = 64   # mesh edge of the bounded CPU sample for workloads larger than this
+
+
+def sizes(w):
+    n, q2 = w["n"], w["NENv"] == 27
+    NN = (2 * n + 1) ** 3 if q2 else (n + 1) ** 3
+    NNp = (n + 1) ** 3
+    return dict(NE=n ** 3, NN=NN, NNp=NNp, DOF=3 * NN + NNp)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, kernel_class):
+    """dram bytes per launch of the dominant kernel from a committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload, {}).get(kernel_class)
+        except Exception:
+            return None
+    return None
+
+
+def make_inp(w, path, n=None):
+    import meshgen
+    meshgen.cube(path, n or w["n"], cluster=w["cluster"], NENv=w["NENv"], viscosity=w["viscosity"], dt=w["dt"],
+                 full_precision=not w.get("inp", False))
+
+
+def run_oracle(w, steps, warmup, n, threads=0):
+    """The CPU oracle (line-faithful restatement of the reference's CPU path; the reference itself does not
+    compile: MKL/CSparse/Paralution absent) on an n^3 mesh of the workload's kind.  Returns seconds per step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "sample.inp")
+        make_inp(w, path, n)
+        t0 = time.time()
+        o = orc.Oracle(path, w["scheme"], threads)
+        setup = time.time() - t0
+        if warmup:
+            o.run(warmup)
+        t0 = time.time()
+        o.run(steps)
+        dt = (time.time() - t0) / steps
+        cg = o.arr("cgIters")
+        info = dict(setup_s=round(setup, 2), cg_iterations_per_solve=float(cg.mean()) if len(cg) else 0.0,
+                    cg_gdof_iter_per_s=(o.i("NNp") * float(cg.sum()) / o.d("cgSeconds") / 1e9) if o.d("cgSeconds") > 0 else None,
+                    threads=orc.threads())
+        o.close()
+    return dt, info
+
+
+def cpu_sample(w, steps, warmup):
+    n_s = min(w["n"], CPU_SAMPLE_N)
+    sec, info = run_oracle(w, steps, warmup, n_s)
+    scale = (n_s ** 3) / float(w["n"] ** 3)   # per-step work ~ elements (Krylov iteration growth with n ignored: favours the CPU)
+    sample = ("oracle (C++/OpenMP restatement of the reference CPU path), %d^3 %s %s mesh, %d timed steps after %d warm-up"
+              % (n_s, "Q2/Q1" if w["NENv"] == 27 else "Q1/Q1", w["scheme"], steps, warmup))
+    if n_s != w["n"]:
+        sample += "; steps/s scaled by element count %d^3/%d^3 to the workload mesh" % (n_s, w["n"])
+    return dict(value=scale / sec, unit="steps/s", cores=info["threads"], kind="port", sample=sample,
+                sample_steps_per_s=1.0 / sec, cg_gdof_iter_per_s=info["cg_gdof_iter_per_s"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CFD_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    sz = sizes(w)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = dict(workload=a.workload, scheme=w["scheme"], element="Q2/Q1" if w["NENv"] == 27 else "Q1/Q1", mesh="%d^3 hex cavity" % w["n"],
+                  NE=sz["NE"], DOF=sz["DOF"], dt=w["dt"], viscosity=w["viscosity"],
+                  krylov="Jacobi-PCG 1e-6/1000 (pressure)" + (", Jacobi-BiCGStab 1e-6/1000 x3 (momentum)" if w["scheme"] == "implicit" else ""))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_sample(w, max(1, a.steps), a.warmup)
+        line = dict(metric="time steps/s", value=cb["value"], unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", impl="reference", config=config, cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import fracstep
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fracstep.build()
+    opts = fracstep.options(device=local_rank)
+    t0 = time.time()
+    tmp = None
+    if w.get("inp"):
+        tmp = tempfile.TemporaryDirectory()
+        path = os.path.join(tmp.name, a.workload + ".inp")
+        make_inp(w, path)
+        s = fracstep.Solver(path, w["scheme"], opts=opts)
+    else:
+        s = fracstep.Solver(scheme=w["scheme"], opts=opts,
+                            cavity=dict(nx=w["n"], cluster=w["cluster"], NENv=w["NENv"], dt=w["dt"], viscosity=w["viscosity"]))
+    setup_s = time.time() - t0
+    c = s.ctx
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed region (state resident in HBM)
+    if a.warmup:
+        c.time_loop(a.warmup)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    c.profile(True)
+    l0 = c.kernel_launches()
+    reps, ms = c.time_loop_timed(a.steps)
+    launches = c.kernel_launches() - l0
+    barrier()
+    clk = clocks.stop()
+    classes = ["ebe", "step1", "gt_rhs", "pcg", "update", "step3", "spmv_k", "assemble", "gq_rhs", "bicgstab"]
+    prof = {k: c.profile_get(k) for k in classes}
+    c.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end: host buffers in, host buffers out, every step
+    U, P = c.fields()
+    Uh = torch.from_numpy(U).pin_memory().numpy()
+    Ph = torch.from_numpy(P).pin_memory().numpy()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(a.steps):
+        _, m1 = c.time_step_host(Uh, Ph)
+        e2e_ms += m1
+    barrier()
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank != 0:
+        return 0
+    n_rep = world   # independent replicas until the partitioned path is built
+    peak, peak_src = measured_peak()
+    total_ms = sum(p["ms"] for p in prof.values())
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    traffic = ncu_traffic(a.workload, dom)
+    cg_its = sum(r["cg_iterations"] for r in reps)
+    cg_ms = prof["pcg"]["ms"]
+    kernels = {k: dict(ms=round(v["ms"], 3), launches=v["launches"], gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
+                       share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
+    config.update(parallelism="1 GPU" if world == 1 else "%d independent replicas" % world,
+                  l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["bytes"] for v in prof.values()) / a.steps / 1e9),
+                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps),
+                  bicgstab_iterations_last_step=reps[-1]["bicg_iterations"])
+    line = dict(metric="time steps/s", value=n_rep * a.steps / (ms_max * 1e-3), unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=ms_max / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=config, clocks=clk,
+                e2e=dict(value=n_rep * a.steps / (e2e_ms * 1e-3), unit="steps/s", h2d_bytes_per_step=int(8 * (U.size + P.size)),
+                         d2h_bytes_per_step=int(8 * (U.size + P.size))),
+                gpu_launches=int(launches),
+                roofline=dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
+                              traffic=traffic, peak_source=peak_src, share_of_step=round(d["ms"] / total_ms, 4) if total_ms else None),
+                cg_gdof_iter_per_s=(sz["NNp"] * cg_its / (cg_ms * 1e-3) / 1e9) if cg_ms > 0 else None,
+                kernels=kernels)
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sample(w, 2, 1)
+    print(json.dumps(line))
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

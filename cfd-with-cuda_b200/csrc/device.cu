@@ -823,24 +823,40 @@ using namespace cfdb;
 
 namespace {
 
+// Event pair around one launch (no synchronisation here; resolved by profile_collect).
 struct ProfScope {
    cfd_ctx* c;
-   const char* name;
-   double bytes;
-   ProfScope(cfd_ctx* c_, const char* n, double b) : c(c_), name(n), bytes(b) {
-      if (c->profile) cudaEventRecord(c->ev0, c->stream);
+   int idx = -1;
+   ProfScope(cfd_ctx* c_, const char* n, double b) : c(c_) {
+      if (!c->profile || c->recsUsed >= (1u << 16)) return;
+      if (c->recsUsed == c->recs.size()) {
+         cfd_ctx::ProfRec r;
+         r.cls = n; r.bytes = 0;
+         if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+         c->recs.push_back(r);
+      }
+      idx = (int)c->recsUsed++;
+      c->recs[idx].cls = n;
+      c->recs[idx].bytes = b;
+      cudaEventRecord(c->recs[idx].a, c->stream);
    }
    ~ProfScope() {
-      if (c->profile) {
-         cudaEventRecord(c->ev1, c->stream);
-         cudaEventSynchronize(c->ev1);
-         float ms = 0;
-         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-         ProfEntry& p = c->prof[name];
-         p.ms += ms; p.launches += 1; p.bytes += bytes;
-      }
+      if (idx >= 0) cudaEventRecord(c->recs[idx].b, c->stream);
    }
 };
+
+void profile_collect(cfd_ctx* c) {
+   if (!c->recsUsed) return;
+   cudaStreamSynchronize(c->stream);
+   for (size_t i = 0; i < c->recsUsed; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->recs[i].a, c->recs[i].b) != cudaSuccess) continue;
+      ProfEntry& p = c->prof[c->recs[i].cls];
+      p.ms += ms; p.launches += 1; p.bytes += c->recs[i].bytes;
+   }
+   c->recsUsed = 0;
+   c->lastPcgRec = c->lastBicgRec = -1;
+}
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }
 
@@ -876,7 +892,8 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    a.Z = c->Z; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
    void* args[] = {&a};
-   ProfScope ps(c, "pcg", 0.0);
+   ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
+   c->lastPcgRec = ps.idx;
    CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
    c->launches++;
    return CFD_OK;
@@ -887,6 +904,21 @@ int fetch_kinfo(cfd_ctx* c) {
    CFD_CK(cudaStreamSynchronize(c->stream));
    c->last_cg = (int)c->h_pinned[16];
    for (int d = 0; d < 3; d++) c->last_bicg[d] = (int)c->h_pinned[16 + 3 + d];
+   // algorithmic bytes of the Krylov launches are known only now (iteration counts): DESIGN.md byte model
+   if (c->lastPcgRec >= 0) {
+      const double N = c->P.NNp;
+      c->recs[c->lastPcgRec].bytes += 48.0 * N + c->last_cg * (12.0 * (double)c->Z.nnz + 4.0 * (N + 1) + 104.0 * N);
+      c->lastPcgRec = -1;
+   }
+   if (c->lastBicgRec >= 0) {
+      const double N = c->P.NN;
+      double b = 0;
+      const int mx = std::max(c->last_bicg[0], std::max(c->last_bicg[1], c->last_bicg[2]));
+      b += mx * 2.0 * (12.0 * (double)c->K.nnz + 4.0 * (N + 1));       // A streamed twice per lock-step iteration
+      for (int d = 0; d < 3; d++) b += c->last_bicg[d] * 192.0 * N;    // 24 vector reads/writes per system-iteration
+      c->recs[c->lastBicgRec].bytes += b;
+      c->lastBicgRec = -1;
+   }
    return CFD_OK;
 }
 
@@ -947,7 +979,8 @@ void cfd_destroy(cfd_ctx* c) {
    if (c->h_pinned) cudaFreeHost(c->h_pinned);
    if (c->ev0) cudaEventDestroy(c->ev0);
    if (c->ev1) cudaEventDestroy(c->ev1);
-   if (c->stream) cudaStreamDestroy(c->stream);
+   for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+   if (c->stream && c->ownStream) cudaStreamDestroy(c->stream);
    delete c;
 }
 
@@ -980,7 +1013,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    CFD_CK(cudaGetDeviceProperties(&prop, c->device));
    c->numSMs = prop.multiProcessorCount;
    if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); delete c; return CFD_ERR_CUDA; }
-   CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   if (o.cuda_stream) { c->stream = (cudaStream_t)o.cuda_stream; c->ownStream = false; }
+   else CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
    CFD_CK(cudaEventCreate(&c->ev0));
    CFD_CK(cudaEventCreate(&c->ev1));
    CFD_CK(cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double)));
@@ -1335,6 +1369,7 @@ int gq_step1GPU(cfd_ctx* c) {
       a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
       void* args[] = {&a};
       ProfScope ps(c, "bicgstab", 0.0);
+      c->lastBicgRec = ps.idx;
       CFD_CK(cudaLaunchCooperativeKernel((void*)k_bicgstab3, dim3(c->bicg_blocks), dim3(c->bicg_threads), args, 0, c->stream));
       c->launches++;
    }
@@ -1443,12 +1478,48 @@ int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* re
    return CFD_OK;
 }
 
+int cfd_timeLoop_timed(cfd_ctx* c, int nsteps, cfd_step_report* reports, double* device_ms) {
+   if (!c) return CFD_ERR_ARG;
+   CFD_CK(cudaEventRecord(c->ev0, c->stream));
+   int done = 0;
+   int rc = cfd_timeLoop(c, nsteps, 0, reports, &done);
+   if (rc) return rc;
+   CFD_CK(cudaEventRecord(c->ev1, c->stream));
+   CFD_CK(cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   CFD_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+   if (device_ms) *device_ms = ms;
+   return CFD_OK;
+}
+
+int cfd_timeStep_host(cfd_ctx* c, double* U, double* P, cfd_step_report* report, double* device_ms) {
+   if (!c || !U || !P) return CFD_ERR_ARG;
+   const bool ex = c->P.scheme == CFD_EXPLICIT;
+   const size_t nU = 3 * (size_t)c->P.NN * sizeof(double), nP = (size_t)c->P.NNp * sizeof(double);
+   CFD_CK(cudaEventRecord(c->ev0, c->stream));
+   CFD_CK(cudaMemcpyAsync(ex ? c->Un : c->Uk_prev, U, nU, cudaMemcpyHostToDevice, c->stream));
+   CFD_CK(cudaMemcpyAsync(ex ? c->Pn : c->Pk_prev, P, nP, cudaMemcpyHostToDevice, c->stream));
+   int done = 0;
+   int rc = cfd_timeLoop(c, 1, 0, report, &done);
+   if (rc) return rc;
+   CFD_CK(cudaMemcpyAsync(U, ex ? c->Un : c->Uk_prev, nU, cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaMemcpyAsync(P, ex ? c->Pn : c->Pk_prev, nP, cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaEventRecord(c->ev1, c->stream));
+   CFD_CK(cudaEventSynchronize(c->ev1));
+   float ms = 0;
+   CFD_CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+   if (device_ms) *device_ms = ms;
+   return CFD_OK;
+}
+
 int cfd_profile(cfd_ctx* c, int enable) {
+   profile_collect(c);
    c->profile = enable != 0;
    if (enable) c->prof.clear();
    return CFD_OK;
 }
 int cfd_profile_get(cfd_ctx* c, const char* name, double* ms, long long* launches, double* bytes) {
+   profile_collect(c);
    auto it = c->prof.find(name);
    if (it == c->prof.end()) { if (ms) *ms = 0; if (launches) *launches = 0; if (bytes) *bytes = 0; return CFD_ERR_ARG; }
    if (ms) *ms = it->second.ms;

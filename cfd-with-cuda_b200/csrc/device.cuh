@@ -110,6 +110,11 @@ struct cfd_ctx {
    long long launches = 0;
    bool profile = false;
    std::map<std::string, cfdb::ProfEntry> prof;
+   struct ProfRec { const char* cls; cudaEvent_t a, b; double bytes; };
+   std::vector<ProfRec> recs;   // event-pair pool (grown on demand, reused)
+   size_t recsUsed = 0;
+   int lastPcgRec = -1, lastBicgRec = -1;
+   bool ownStream = true;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    std::vector<void*> allocs;
 };

@@ -49,7 +49,7 @@ class cfd_options(C.Structure):
     _fields_ = [
         ("cg_tol", C.c_double), ("cg_maxit", C.c_int), ("cg_warm_start", C.c_int),
         ("bicg_tol", C.c_double), ("bicg_maxit", C.c_int), ("maxacc_rule", C.c_int),
-        ("device", C.c_int), ("reserved", C.c_int * 8),
+        ("device", C.c_int), ("reserved", C.c_int * 8), ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -101,6 +101,8 @@ def lib():
     L.cfd_last_cg_iterations.argtypes = [vp]
     L.cfd_last_bicgstab_iterations.argtypes = [vp, _ip]
     L.cfd_timeLoop.argtypes = [vp, C.c_int, C.c_int, C.POINTER(cfd_step_report), _ip]
+    L.cfd_timeLoop_timed.argtypes = [vp, C.c_int, C.POINTER(cfd_step_report), _dp]
+    L.cfd_timeStep_host.argtypes = [vp, _dp, _dp, C.POINTER(cfd_step_report), _dp]
     L.cfd_profile.argtypes = [vp, C.c_int]
     L.cfd_profile_get.argtypes = [vp, C.c_char_p, _dp, C.POINTER(C.c_longlong), _dp]
     L.cfd_kernel_launches.argtypes = [vp]
@@ -279,6 +281,27 @@ class Context:
         return [dict(timeN=r.timeN, iter=r.iter, cg_iterations=r.cg_iterations, cg_solves=r.cg_solves,
                      bicg_iterations=list(r.bicg_iterations), maxAcc=r.maxAcc, steady=bool(r.steady),
                      monitor=list(r.monitor)) for r in reps[:done.value]]
+
+    @staticmethod
+    def _rep(r):
+        return dict(timeN=r.timeN, iter=r.iter, cg_iterations=r.cg_iterations, cg_solves=r.cg_solves,
+                    bicg_iterations=list(r.bicg_iterations), maxAcc=r.maxAcc, steady=bool(r.steady),
+                    monitor=list(r.monitor))
+
+    def time_loop_timed(self, nsteps):
+        """nsteps time steps; returns (reports, device milliseconds by CUDA events on the launch stream)."""
+        reps = (cfd_step_report * nsteps)()
+        ms = C.c_double()
+        _check(self.L.cfd_timeLoop_timed(self.h, nsteps, reps, C.byref(ms)))
+        return [self._rep(r) for r in reps], ms.value
+
+    def time_step_host(self, U, P):
+        """One step from/to host buffers U [3NN], P [NNp] (in place); returns (report, device ms)."""
+        assert U.dtype == np.float64 and P.dtype == np.float64 and U.size == 3 * self.NN and P.size == self.NNp
+        rep = cfd_step_report()
+        ms = C.c_double()
+        _check(self.L.cfd_timeStep_host(self.h, _d(U), _d(P), C.byref(rep), C.byref(ms)))
+        return self._rep(rep), ms.value
 
     def profile(self, enable=True):
         _check(self.L.cfd_profile(self.h, int(enable)))

@@ -88,6 +88,7 @@ typedef struct cfd_options {
    int maxacc_rule;   /* 0 (default) = max|dU|/dt (BCH.cpp:3053); 1 = max|dU| (BCH.cu:107-117) */
    int device;        /* CUDA device ordinal; -1 = current device */
    int reserved[8];
+   void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 
 void cfd_default_options(cfd_options* opt);
@@ -151,10 +152,18 @@ typedef struct cfd_step_report {
  * Stops early (returning the number of steps done in *done) when a step reports steady state
  * and stop_on_steady != 0. */
 int cfd_timeLoop(cfd_ctx* ctx, int nsteps, int stop_on_steady, cfd_step_report* reports, int* done);
+/* same, bracketed by CUDA events on the context's stream: *device_ms = elapsed device time */
+int cfd_timeLoop_timed(cfd_ctx* ctx, int nsteps, cfd_step_report* reports, double* device_ms);
+/* One time step driven from HOST buffers (the call a host program makes): copies U [3NN] and P [NNp]
+ * to the device, runs one time-loop pass, copies the new U and P back into the same buffers.
+ * *device_ms (optional) = CUDA-event time of copy-in + step + copy-out. */
+int cfd_timeStep_host(cfd_ctx* ctx, double* U, double* P, cfd_step_report* report, double* device_ms);
 
 /* ---- timing / roofline instrumentation --------------------------------------------------------
- * Per-kernel-class accumulated CUDA-event time on the context's stream (enabled by cfd_profile(ctx,1)).
- * names: "ebe","spmv_k","spmv_g","spmv_gt","pcg","bicgstab","update","assemble". */
+ * Per-kernel-class CUDA-event time on the context's stream (enabled by cfd_profile(ctx,1)): event
+ * pairs are recorded around every launch without synchronising and resolved on cfd_profile_get.
+ * classes: "ebe","step1","gt_rhs","pcg","update","step3","spmv_k","assemble","gq_rhs","bicgstab";
+ * `bytes` = algorithmic bytes of the launches (DESIGN.md byte model). */
 int cfd_profile(cfd_ctx* ctx, int enable);
 int cfd_profile_get(cfd_ctx* ctx, const char* name, double* ms, long long* launches, double* bytes);
 long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context so far */
