@@ -5,6 +5,7 @@
 // and their call sites in blascoCodinaHuerta.cpp (BCH.cpp) / guermondQuartapelle.cpp (GQ.cpp).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -26,6 +27,10 @@ const char* last_error() { return g_err.c_str(); }
 // Sell: host conversion + upload
 // =================================================================================================
 int choose_T(int nrows, long long nnz) {
+   if (const char* e = getenv("CFD_Z_T")) {   // tuning override (experiments only)
+      const int t = atoi(e);
+      if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
+   }
    if (nrows <= 0) return 1;
    const double avg = (double)nnz / nrows;
    int T = 1;
@@ -110,9 +115,21 @@ void sell_free(Sell& s) {
 // =================================================================================================
 // Reference-element tables in constant memory
 // =================================================================================================
-__constant__ double cSv[8][27];       // [k][i]
-__constant__ double cdSv[3][27][8];   // [d][i][k]
-__constant__ double cdSp[3][8][8];    // [d][i][k]
+// Both element families are resident so that Q2/Q1 and Q1/Q1 contexts can coexist in one process.
+__constant__ double cSv27[8][27];       // [k][i]
+__constant__ double cdSv27[3][27][8];   // [d][i][k]
+__constant__ double cSv8[8][8];
+__constant__ double cdSv8[3][8][8];
+__constant__ double cdSp[3][8][8];      // [d][i][k] trilinear (geometry + pressure)
+template <int NV> struct Tab;
+template <> struct Tab<27> {
+   static __device__ __forceinline__ double Sv(int k, int i) { return cSv27[k][i]; }
+   static __device__ __forceinline__ double dSv(int d, int i, int k) { return cdSv27[d][i][k]; }
+};
+template <> struct Tab<8> {
+   static __device__ __forceinline__ double Sv(int k, int i) { return cSv8[k][i]; }
+   static __device__ __forceinline__ double dSv(int d, int i, int k) { return cdSv8[d][i][k]; }
+};
 
 // =================================================================================================
 // Row kernels (one thread per velocity row, T = 1 matrices)
@@ -126,7 +143,7 @@ __global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const doub
    const int row = blockIdx.x * blockDim.x + threadIdx.x;
    const int slice = row >> 5, lane = row & 31;
    if (slice >= A.nslices) return;
-   const double* __restrict__ val = A.vals[vidx];
+   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
    const long long off = A.sliceOff[slice];
    const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
    double acc[NV];
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(256) k_spmv_T(Sell A, int vidx, const double* 
    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
    const int slice = gthread >> 5, lane = gthread & 31;
    if (slice >= A.nslices) return;
-   const double* __restrict__ val = A.vals[vidx];
+   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
    const long long off = A.sliceOff[slice];
    const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
    double acc = 0.0;
@@ -362,7 +379,7 @@ __device__ __forceinline__ void ebe_gauss_b(const int (&nd)[NV], int NN, const d
       for (int i = 0; i < NV; i++) {
          const double v = __ldg(Uadv + (long long)c * NN + nd[i]);
 #pragma unroll
-         for (int k = 0; k < 8; k++) ug[k][c] += cSv[k][i] * v;
+         for (int k = 0; k < 8; k++) ug[k][c] += Tab<NV>::Sv(k, i) * v;
       }
    }
    double xc[8][3];
@@ -423,9 +440,9 @@ __global__ void __launch_bounds__(128) k_ebe_convect_apply(int NE, int NN, int l
          const double v = __ldg(Ux + (long long)c * NN + nd[j]);
 #pragma unroll
          for (int k = 0; k < 8; k++) {
-            g[k][0] += cdSv[0][j][k] * v;
-            g[k][1] += cdSv[1][j][k] * v;
-            g[k][2] += cdSv[2][j][k] * v;
+            g[k][0] += Tab<NV>::dSv(0, j, k) * v;
+            g[k][1] += Tab<NV>::dSv(1, j, k) * v;
+            g[k][2] += Tab<NV>::dSv(2, j, k) * v;
          }
       }
       double t[8];
@@ -435,7 +452,7 @@ __global__ void __launch_bounds__(128) k_ebe_convect_apply(int NE, int NN, int l
       for (int i = 0; i < NV; i++) {
          double r = 0;
 #pragma unroll
-         for (int k = 0; k < 8; k++) r += cSv[k][i] * t[k];
+         for (int k = 0; k < 8; k++) r += Tab<NV>::Sv(k, i) * t[k];
          atomicAdd(R1 + (long long)c * NN + nd[i], -r);
       }
    }
@@ -459,11 +476,11 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
    for (int j = 0; j < NV; j++) {
       double cj[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) cj[k] = b[k][0] * cdSv[0][j][k] + b[k][1] * cdSv[1][j][k] + b[k][2] * cdSv[2][j][k];
+      for (int k = 0; k < 8; k++) cj[k] = b[k][0] * Tab<NV>::dSv(0, j, k) + b[k][1] * Tab<NV>::dSv(1, j, k) + b[k][2] * Tab<NV>::dSv(2, j, k);
       for (int i = 0; i < NV; i++) {
          double a = 0;
 #pragma unroll
-         for (int k = 0; k < 8; k++) a += cSv[k][i] * cj[k];
+         for (int k = 0; k < 8; k++) a += Tab<NV>::Sv(k, i) * cj[k];
          const int pos = __ldg(mapT + (long long)(i * NV + j) * ldE + e);
          atomicAdd(Aval + pos, a);
       }
@@ -478,7 +495,7 @@ __global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restr
    const int slice = row >> 5, lane = row & 31;
    const long long off = A.sliceOff[slice];
    const int w = (int)((A.sliceOff[slice + 1] - off) >> 5);
-   double* val = A.vals[vidx];
+   double* val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
    bool diagDone = false;
    for (int j = 0; j < w; j++) {
       const long long pos = off + (long long)(j >> 1) * 64 + 2 * lane + (j & 1);
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(256) k_gq_rhs(Sell MK, int mIdx, Sell G, int N
    if (slice >= MK.nslices) return;
    double a0 = 0, a1 = 0, a2 = 0;
    {
-      const double* __restrict__ val = MK.vals[mIdx];
+      const double* __restrict__ val = mIdx == 0 ? MK.vals[0] : (mIdx == 1 ? MK.vals[1] : MK.vals[2]);
       const long long off = MK.sliceOff[slice];
       const int np = (int)((MK.sliceOff[slice + 1] - off) >> 6);
 #pragma unroll 2
@@ -555,6 +572,7 @@ __global__ void k_add(long long n, const double* __restrict__ a, const double* _
 // =================================================================================================
 struct PcgArgs {
    Sell Z;
+   const int* part;   // per-block slice ranges (may be NULL)
    int n;
    const double* b;
    double* x;
@@ -569,11 +587,30 @@ struct PcgArgs {
 
 // q = Z*p for the slices owned by this warp; returns the partial sum of p_i q_i over its rows.
 // p is written by this same kernel in other phases: plain (coherent) loads, not __ldg.
-__device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const double* p, double* q, int gwarp, int nwarps, int lane) {
+// Slice -> warp assignment inside the persistent kernels.  Many slices per warp: contiguous chunks per
+// block (block b owns [b*chunk, (b+1)*chunk)), so the vector entries a block gathers form one short
+// window that stays in its SM's L1 for the whole phase.  Few slices per warp: plain grid-stride, which
+// balances the load to within one slice.
+struct SliceRange { int begin, end, step; };
+__device__ __forceinline__ SliceRange slice_range(int nslices, const int* __restrict__ part, int gwarp, int nwarps) {
+   SliceRange r;
+   if (part && nslices >= 4 * nwarps) {
+      // part[b] .. part[b+1]: chunk of block b, balanced by stored entries (rows of a Q2 mesh differ 4.6x in length)
+      r.begin = part[blockIdx.x] + (threadIdx.x >> 5);
+      r.end = part[blockIdx.x + 1];
+      r.step = blockDim.x >> 5;
+   } else {
+      r.begin = gwarp; r.end = nslices; r.step = nwarps;
+   }
+   return r;
+}
+
+__device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const int* part, const double* p, double* q, int gwarp, int nwarps, int lane) {
    double pq = 0.0;
    const double* __restrict__ val = Z.vals[0];
    const int T = Z.T, sub = lane % T;
-   for (int s = gwarp; s < Z.nslices; s += nwarps) {
+   const SliceRange sr = slice_range(Z.nslices, part, gwarp, nwarps);
+   for (int s = sr.begin; s < sr.end; s += sr.step) {
       const long long off = Z.sliceOff[s];
       const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
       double acc = 0.0;
@@ -597,7 +634,7 @@ __device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const double* p,
 // Jacobi-preconditioned CG, whole solve in one launch (replaces CUSP_CG_solver, BCH.cu:418-451 /
 // GQ.cu:302-362: cusp::krylov::cg + diagonal preconditioner + default_monitor(b, maxit, tol)).
 // 3 grid syncs per iteration; all reductions on the device; no host round trip.
-__global__ void __launch_bounds__(512) k_pcg(PcgArgs a) {
+__global__ void __launch_bounds__(512, 3) k_pcg(PcgArgs a) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[3 * 32];
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -609,7 +646,7 @@ __global__ void __launch_bounds__(512) k_pcg(PcgArgs a) {
 
    if (!a.x0zero) {
       // r = b - Z x  (warm start, BCH.cu:418-451 keeps the previous Pdot)
-      pcg_spmv_phase(a.Z, a.x, a.q, gwarp, nwarps, lane);
+      pcg_spmv_phase(a.Z, a.part, a.x, a.q, gwarp, nwarps, lane);
       grid.sync();
    }
    double v3[3] = {0, 0, 0};
@@ -628,11 +665,21 @@ __global__ void __launch_bounds__(512) k_pcg(PcgArgs a) {
    double rr = v3[2];
    const double thresh = a.tol * sqrt(bb);
    int it = 0;
+   // phase clock of block 0 (diagnostics: info[8..12] = ns spent in spmv / reduce pq / update / reduce rz / p-update+sync)
+#ifdef CFD_PCG_PHASE_TIMERS
+   unsigned long long tph[5] = {0, 0, 0, 0, 0}, t0 = 0, t1;
+#define PCG_TICK(k) do { if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define PCG_TICK(k)
+#endif
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       double v1[1];
-      v1[0] = pcg_spmv_phase(a.Z, a.p, a.q, gwarp, nwarps, lane);
+      v1[0] = pcg_spmv_phase(a.Z, a.part, a.p, a.q, gwarp, nwarps, lane);
+      PCG_TICK(0);
       grid_sum<1>(grid, v1, buf1, sh);
+      PCG_TICK(1);
       const double alpha = rz / v1[0];
       double v2[2] = {0, 0};
       for (int i = tid; i < n; i += nthreads) {
@@ -642,19 +689,50 @@ __global__ void __launch_bounds__(512) k_pcg(PcgArgs a) {
          v2[0] += ri * (a.dinv[i] * ri);
          v2[1] += ri * ri;
       }
+      PCG_TICK(2);
       grid_sum<2>(grid, v2, buf0, sh);
+      PCG_TICK(3);
       const double beta = v2[0] / rz;
       rz = v2[0];
       rr = v2[1];
       for (int i = tid; i < n; i += nthreads) a.p[i] = a.dinv[i] * a.r[i] + beta * a.p[i];
       it++;
       grid.sync();
+      PCG_TICK(4);
    }
+#undef PCG_TICK
+#ifdef CFD_PCG_PHASE_TIMERS
+   if (tid == 0)
+      for (int k = 0; k < 5; k++) a.info[8 + k] = (double)tph[k];
+#endif
    if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
+}
+
+// Diagnostic: cost of the grid-wide primitives the persistent Krylov kernels are built from.
+// mode 0: grid.sync()   mode 1: grid_sum<1>   mode 2: grid_sum<3>
+__global__ void __launch_bounds__(1024) k_diag_sync(int iters, int mode, double* scratch, double* out) {
+   cg::grid_group grid = cg::this_grid();
+   __shared__ double sh[3 * 32];
+   double acc = 0.0;
+   for (int it = 0; it < iters; it++) {
+      if (mode == 0) {
+         grid.sync();
+      } else if (mode == 1) {
+         double v[1] = {1.0 + threadIdx.x};
+         grid_sum<1>(grid, v, scratch + (it & 1) * 3 * (size_t)gridDim.x, sh);
+         acc += v[0];
+      } else {
+         double v[3] = {1.0, 2.0, 3.0};
+         grid_sum<3>(grid, v, scratch + (it & 1) * 3 * (size_t)gridDim.x, sh);
+         acc += v[0] + v[1] + v[2];
+      }
+   }
+   if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = acc;
 }
 
 struct BicgArgs {
    Sell A;
+   const int* part;
    int vidx;
    int n;
    const double* b;   // [3][n]
@@ -670,10 +748,11 @@ struct BicgArgs {
 // out_s = A * in_s for the active systems (multi-RHS: one pass over A); returns nothing, the caller
 // computes its dots in the following elementwise sweep... except that fusing the dot here saves a pass:
 // dots[s][0] += l1_s[row]*out, dots[s][1] += out*out
-__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, int vidx, int n, const double* in, double* out, const bool (&act)[3],
+__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, int vidx, int n, const double* in, double* out, const bool (&act)[3],
                                                 const double* l1, double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
-   const double* __restrict__ val = A.vals[vidx];
-   for (int s = gwarp; s < A.nslices; s += nwarps) {
+   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
+   const SliceRange sr = slice_range(A.nslices, part, gwarp, nwarps);
+   for (int s = sr.begin; s < sr.end; s += sr.step) {
       const long long off = A.sliceOff[s];
       const int np = (int)((A.sliceOff[s + 1] - off) >> 6);
       double a0 = 0, a1 = 0, a2 = 0;
@@ -704,7 +783,7 @@ __device__ __forceinline__ void bicg_spmv_phase(const Sell& A, int vidx, int n, 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
 // CUSP_GMRES_solver -> cusp::krylov::bicgstab, GQ.cu:369-433, x0 = 0).  The three systems share A,
 // so each of the two SpMV phases per iteration streams A once for all still-active right-hand sides.
-__global__ void __launch_bounds__(512) k_bicgstab3(BicgArgs a) {
+__global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[6 * 32];
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -743,7 +822,7 @@ __global__ void __launch_bounds__(512) k_bicgstab3(BicgArgs a) {
       if (!act[0] && !act[1] && !act[2]) break;
       // ---- AMp = A (M p), d0 = rs . AMp
       double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
-      bicg_spmv_phase(a.A, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
+      bicg_spmv_phase(a.A, a.part, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
       for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = 0; }
       grid_sum<6>(grid, v6, buf1, sh);
       double alpha[3];
@@ -768,7 +847,7 @@ __global__ void __launch_bounds__(512) k_bicgstab3(BicgArgs a) {
       }
       // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
       for (int c = 0; c < 3; c++) { d0[c] = 0; d1[c] = 0; }
-      bicg_spmv_phase(a.A, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
+      bicg_spmv_phase(a.A, a.part, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
       for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = d1[c]; }
       grid_sum<6>(grid, v6, buf1, sh);
       double omega[3];
@@ -889,7 +968,7 @@ double spmv_bytes(const Sell& A, int nval, int nvec, bool accumulate) {
 
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    PcgArgs a;
-   a.Z = c->Z; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
+   a.Z = c->Z; a.part = c->pcgPart; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
    void* args[] = {&a};
    ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
@@ -1026,15 +1105,24 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    // reference-element tables -> constant memory
    {
       FeTables T;
-      build_fe_tables(nv, T);
-      CFD_CK(cudaMemcpyToSymbol(cSv, T.Sv, sizeof(T.Sv)));
-      CFD_CK(cudaMemcpyToSymbol(cdSv, T.dSv, sizeof(T.dSv)));
+      build_fe_tables(27, T);
+      CFD_CK(cudaMemcpyToSymbol(cSv27, T.Sv, sizeof(T.Sv)));
+      CFD_CK(cudaMemcpyToSymbol(cdSv27, T.dSv, sizeof(T.dSv)));
       CFD_CK(cudaMemcpyToSymbol(cdSp, T.dSp, sizeof(T.dSp)));
+      double sv8[8][8], dsv8[3][8][8];
+      for (int k = 0; k < 8; k++)
+         for (int i = 0; i < 8; i++) {
+            sv8[k][i] = T.Sp[k][i];
+            for (int d = 0; d < 3; d++) dsv8[d][i][k] = T.dSp[d][i][k];
+         }
+      CFD_CK(cudaMemcpyToSymbol(cSv8, sv8, sizeof sv8));
+      CFD_CK(cudaMemcpyToSymbol(cdSv8, dsv8, sizeof dsv8));
    }
    // ---- matrices -> Sell
    {
       SellHost h;
       sell_build_host(NN, NN, P->sparseMrowStarts, P->sparseMcol, 1, h);
+      c->hostOffK = h.sliceOff;
       if (P->scheme == CFD_EXPLICIT) {
          const double* v[1] = {P->sparseKvalue};
          TRY(sell_upload(h, 1, v, c->K));
@@ -1087,6 +1175,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    {
       SellHost h;
       sell_build_host(NNp, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NNp, P->sparseZ_nnz), h);
+      c->hostOffZ = h.sliceOff;
       const double* v[1] = {P->sparseZvalue};
       TRY(sell_upload(h, 1, v, c->Z));
       std::vector<double> dinv(NNp, 1.0);
@@ -1155,6 +1244,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       const int needed = (int)std::max<long long>(1, (wantWarps * 32 + c->pcg_threads - 1) / c->pcg_threads);
       if (needed < blocks) blocks = std::max(c->numSMs, ((needed + c->numSMs - 1) / c->numSMs) * c->numSMs);
       c->pcg_blocks = std::min(blocks, c->numSMs * occ);
+      if (const char* e = getenv("CFD_PCG_BLOCKS")) c->pcg_blocks = std::max(1, std::min(atoi(e), c->numSMs * occ));
       int occ2 = 0;
       CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_bicgstab3, c->bicg_threads, 0));
       if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
@@ -1163,6 +1253,25 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       if (needed2 < blocks2) blocks2 = std::max(c->numSMs, ((needed2 + c->numSMs - 1) / c->numSMs) * c->numSMs);
       c->bicg_blocks = std::min(blocks2, c->numSMs * occ2);
       TRY(dalloc(c, &c->partials, (size_t)2 * 6 * std::max(c->pcg_blocks, c->bicg_blocks)));
+      auto partition = [](const std::vector<long long>& off, int nblk) {
+         const int ns = (int)off.size() - 1;
+         std::vector<int> part(nblk + 1, ns);
+         const long long total = off[ns];
+         int s = 0;
+         for (int b = 0; b < nblk; b++) {
+            const long long target = (long long)((double)total * b / nblk);
+            while (s < ns && off[s] < target) s++;
+            part[b] = s;
+         }
+         part[0] = 0;
+         return part;
+      };
+      std::vector<int> pz = partition(c->hostOffZ, c->pcg_blocks);
+      TRY(dupload(c, &c->pcgPart, pz.data(), pz.size()));
+      if (P->scheme == CFD_IMPLICIT) {
+         std::vector<int> pk = partition(c->hostOffK, c->bicg_blocks);
+         TRY(dupload(c, &c->bicgPart, pk.data(), pk.size()));
+      }
    }
 #undef TRY
    // scalar fields stay; host pointers are not ours to keep
@@ -1365,7 +1474,7 @@ int gq_step1GPU(cfd_ctx* c) {
    }
    {
       BicgArgs a;
-      a.A = c->K; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
+      a.A = c->K; a.part = c->bicgPart; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
       a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
       void* args[] = {&a};
       ProfScope ps(c, "bicgstab", 0.0);
@@ -1573,6 +1682,29 @@ int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, con
    return CFD_OK;
 }
 
+int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_op) {
+   double *scr = nullptr, *out = nullptr;
+   CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
+   CFD_CK(cudaMalloc(&out, 8));
+   void* args[] = {&iters, &mode, &scr, &out};
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   float best = 1e30f;
+   for (int rep = 0; rep < 3; rep++) {
+      cudaEventRecord(e0);
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_diag_sync, dim3(blocks), dim3(threads), args, 0, 0));
+      cudaEventRecord(e1);
+      CFD_CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = std::min(best, ms);
+   }
+   if (us_per_op) *us_per_op = 1e3 * best / iters;
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(scr); cudaFree(out);
+   return CFD_OK;
+}
+
 int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x, double tol, int maxit,
                 int* its, double* ms) {
    int ndev = 0;
@@ -1589,8 +1721,8 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
       for (int k = rowStarts[r]; k < rowStarts[r + 1]; k++)
          if (col[k] == r) { dinv[r] = 1.0 / val[k]; break; }
    double *db, *dx, *dr, *dp, *dq, *dd, *scr, *info;
-   CFD_CK(cudaMalloc(&db, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dx, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dr, 8 * (size_t)n));
-   CFD_CK(cudaMalloc(&dp, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dq, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dd, 8 * (size_t)n));
+   CFD_CK(cudaMalloc(&db, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dx, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dr, 16 * (size_t)n));
+   CFD_CK(cudaMalloc(&dp, 16 * (size_t)n)); CFD_CK(cudaMalloc(&dq, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dd, 8 * (size_t)n));
    CFD_CK(cudaMalloc(&info, 8 * 16));
    CFD_CK(cudaMemcpy(db, b, 8 * (size_t)n, cudaMemcpyHostToDevice));
    CFD_CK(cudaMemcpy(dx, x, 8 * (size_t)n, cudaMemcpyHostToDevice));
@@ -1602,7 +1734,7 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    const int blocks = sms * std::max(1, occ);
    CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
    PcgArgs a;
-   a.Z = Z; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
+   a.Z = Z; a.part = nullptr; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
    a.tol = tol; a.maxit = maxit; a.x0zero = 0;
    void* args[] = {&a};
    cudaEvent_t e0, e1;
@@ -1618,6 +1750,9 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    CFD_CK(cudaMemcpy(x, dx, 8 * (size_t)n, cudaMemcpyDeviceToHost));
    if (its) *its = (int)hinfo[0];
    if (ms) *ms = t;
+   if (getenv("CFD_PCG_PHASES") && hinfo[0] > 0)
+      fprintf(stderr, "pcg phases (us/iter, block 0): spmv %.2f  reduce1 %.2f  update %.2f  reduce2 %.2f  pupdate+sync %.2f\n", hinfo[8] / hinfo[0] * 1e-3,
+              hinfo[9] / hinfo[0] * 1e-3, hinfo[10] / hinfo[0] * 1e-3, hinfo[11] / hinfo[0] * 1e-3, hinfo[12] / hinfo[0] * 1e-3);
    cudaEventDestroy(e0); cudaEventDestroy(e1);
    cudaFree(db); cudaFree(dx); cudaFree(dr); cudaFree(dp); cudaFree(dq); cudaFree(dd); cudaFree(scr); cudaFree(info);
    sell_free(Z);

@@ -104,6 +104,8 @@ struct cfd_ctx {
    double* scal = nullptr;      // device: [0..3] convergence sums, [4] maxAcc bits
    double* h_pinned = nullptr;  // pinned host mirror for read-backs (64 doubles)
    int pcg_blocks = 0, pcg_threads = 512, bicg_blocks = 0, bicg_threads = 512;
+   int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
+   std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
    int timeN = 0;
    int last_cg = 0, last_bicg[3] = {0, 0, 0};

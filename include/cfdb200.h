@@ -172,6 +172,8 @@ long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context
 /* y = alpha*A*x + beta*y for `nvec` vectors sharing one CSR matrix; x is [nvec][ncols], y [nvec][nrows] host arrays */
 int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, const double* val, int nvec,
                  const double* x, double* y, double alpha, double beta, int repeat, double* ms_per_call);
+/* diagnostic: microseconds per grid-wide sync (mode 0) / deterministic grid reduction of 1 (mode 1) or 3 (mode 2) values */
+int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_op);
 /* Jacobi-PCG on a CSR matrix: returns iterations in *its */
 int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x,
                 double tol, int maxit, int* its, double* ms);

@@ -94,6 +94,7 @@ struct Orc {
    std::vector<ivec> elemsOfPresNodes, elemNeighbors;
    ivec meshColors, NmeshColors, elementsOfColor;
    int nActiveColors = 0;
+   int colorConflicts = 0;   // pairs of corner-sharing elements that received the same colour
    ivec LtoGvel_1d;   // [e][3*NENv]
    ivec BCvelNodes;   // [i][2] = node, whichBC
    int BCnVelNodes = 0, monPoint = 0;
@@ -266,6 +267,15 @@ void setupMeshColoring(Orc& o) {
             if (o.meshColors[e] == c) o.elementsOfColor[count++] = e;
       }
    }
+   // The restart quirk above leaves same-coloured neighbours on some meshes (e.g. odd element counts
+   // per edge: 8 conflicting pairs on a 5^3 cube) -- a data race in the reference's coloured OpenMP /
+   // CUDA loops.  The oracle must be deterministic: when the colouring is
+   // invalid the element loops below run serially, i.e. they compute what the reference computes
+   // when the race does not strike.
+   o.colorConflicts = 0;
+   for (int e = 0; e < o.NE; e++)
+      for (int nb : o.elemNeighbors[e])
+         if (nb > e && o.meshColors[nb] == o.meshColors[e]) o.colorConflicts++;
 }
 
 // setupNonCornerNodes (BCH.cpp:954-1320): mid-edge, then mid-face, then centre
@@ -795,7 +805,7 @@ void bch_calculateMatrixA(Orc& o) {
       for (int c = 0; c < (int)o.NmeshColors.size(); c++)
          if (o.NmeshColors[c] > 0 && ++seen == color) { cid = c; break; }
       const int cnt = o.NmeshColors[cid];
-#pragma omp parallel
+#pragma omp parallel if (o.colorConflicts == 0)
       {
          dvec Ae(nv * nv), u0n(nv), v0n(nv), w0n(nv), up(nv), vp(nv), wp(nv);
 #pragma omp for schedule(static)
@@ -920,7 +930,7 @@ void gq_calculateMatrixA(Orc& o) {
       for (int c = 0; c < (int)o.NmeshColors.size(); c++)
          if (o.NmeshColors[c] > 0 && ++seen == color) { cid = c; break; }
       const int cnt = o.NmeshColors[cid];
-#pragma omp parallel
+#pragma omp parallel if (o.colorConflicts == 0)
       {
          dvec Ae(nv * nv), u0n(nv), v0n(nv), w0n(nv);
 #pragma omp for schedule(static)
@@ -1123,7 +1133,7 @@ long long orc_int(void* h, const char* name) {
    if (n == "nnzM") return o.Mp.nnz(); if (n == "nnzG") return o.Gp.nnz(); if (n == "nnzZ") return o.Zp.nnz();
    if (n == "BCnVelNodes") return o.BCnVelNodes; if (n == "BCnVelFaces") return o.BCnVelFaces; if (n == "nBC") return o.nBC;
    if (n == "zeroPressureNode") return o.zeroPressureNode; if (n == "monPoint") return o.monPoint;
-   if (n == "nActiveColors") return o.nActiveColors; if (n == "maxIter") return o.maxIter; if (n == "timeN") return o.timeN;
+   if (n == "nActiveColors") return o.nActiveColors; if (n == "colorConflicts") return o.colorConflicts; if (n == "maxIter") return o.maxIter; if (n == "timeN") return o.timeN;
    if (n == "lastIter") return o.lastIter; if (n == "isRestart") return o.isRestart;
    if (n == "n_cgIters") return (long long)o.cgIters.size(); if (n == "n_bicgIters") return (long long)o.bicgIters.size();
    if (n == "n_innerIters") return (long long)o.innerIters.size();

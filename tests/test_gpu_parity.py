@@ -144,7 +144,7 @@ def test_ebe_random_fields(mesh, name):
     c.upload("UnpHalf_prev", up)
     o.phase("bch_calculateMatrixA")
     c.call("bch_calculateMatrixAGPU")
-    assert rel(c.download("R1"), o.arr("R1")) < 1e-12
+    assert rel(c.download("R1"), o.arr("R1")) < 1e-11   # atomic scatter order varies run to run
 
 
 def test_spmv_and_pcg_kernels(mesh):
