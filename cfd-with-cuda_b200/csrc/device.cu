@@ -38,6 +38,19 @@ int choose_T(int nrows, long long nnz) {
    return T;
 }
 
+// lanes per row for the velocity-row matrices: 1 once there are enough rows to fill the machine
+int choose_Tv(int nrows, long long nnz) {
+   if (const char* e = getenv("CFD_V_T")) {   // tuning override (experiments only)
+      const int t = atoi(e);
+      if (t == 1 || t == 2 || t == 4 || t == 8) return t;
+   }
+   if (nrows <= 0) return 1;
+   const double avg = (double)nnz / nrows;
+   int T = 1;
+   while ((long long)nrows * T < 400000 && T < 4 && avg / (2 * T) >= 8.0) T *= 2;
+   return T;
+}
+
 void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T, SellHost& out) {
    const int R = 32 / T;
    const int ns = (nrows + R - 1) / R;
@@ -135,108 +148,114 @@ template <> struct Tab<8> {
 // Row kernels (one thread per velocity row, T = 1 matrices)
 // =================================================================================================
 
+// Thread -> (slice, lane, row, sub-lane) map shared by the row kernels: one warp per slice, T lanes per row.
+struct RowMap {
+   int slice, lane, row, sub;
+   bool owner;   // this lane writes the row's result
+};
+__device__ __forceinline__ bool row_map(const Sell& A, RowMap& m) {
+   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+   m.slice = (int)(g >> 5);
+   m.lane = (int)(g & 31);
+   if (m.slice >= A.nslices) { m.owner = false; return false; }   // warp-uniform
+   m.row = m.slice * A.R + m.lane / A.T;
+   m.sub = m.lane % A.T;
+   m.owner = (m.sub == 0) && (m.row < A.nrows);
+   return true;
+}
+__device__ __forceinline__ double lanes_sum(double v, int T) {
+   for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+__device__ __forceinline__ const double* sell_vals(const Sell& A, int vidx) {
+   return vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);   // no dynamic indexing of the by-value struct
+}
+
 // y_c = alpha * A x_c + beta * y_c for NV vectors sharing one Sell value array (vectors are
 // component-blocked with stride ldx / ldy).  Multi-RHS: the matrix stream is read once.
 template <int NV>
 __global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const double* __restrict__ x, long long ldx,
                                                     double* __restrict__ y, long long ldy, double alpha, double beta) {
-   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-   const int slice = row >> 5, lane = row & 31;
-   if (slice >= A.nslices) return;
-   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
-   const long long off = A.sliceOff[slice];
-   const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
+   RowMap m;
+   if (!row_map(A, m)) return;
+   const double* __restrict__ val = sell_vals(A, vidx);
+   const long long off = A.sliceOff[m.slice];
+   const int np = (int)((A.sliceOff[m.slice + 1] - off) >> 6);
    double acc[NV];
 #pragma unroll
    for (int c = 0; c < NV; c++) acc[c] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
    for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * lane;
+      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
       const int2 c2 = ldnc_i2(A.cols + e);
       const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
       for (int c = 0; c < NV; c++) acc[c] += v2.x * __ldg(x + c * ldx + c2.x) + v2.y * __ldg(x + c * ldx + c2.y);
    }
-   if (row < A.nrows) {
+#pragma unroll
+   for (int c = 0; c < NV; c++) acc[c] = lanes_sum(acc[c], A.T);
+   if (m.owner) {
 #pragma unroll
       for (int c = 0; c < NV; c++) {
          double r = alpha * acc[c];
-         if (beta != 0.0) r += beta * y[c * ldy + row];
-         y[c * ldy + row] = r;
+         if (beta != 0.0) r += beta * y[c * ldy + m.row];
+         y[c * ldy + m.row] = r;
       }
    }
 }
 
-// Generic y = alpha*A*x + beta*y for any T (pressure-row matrices), one vector.
-__global__ void __launch_bounds__(256) k_spmv_T(Sell A, int vidx, const double* __restrict__ x, double* __restrict__ y,
-                                                double alpha, double beta) {
-   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
-   const int slice = gthread >> 5, lane = gthread & 31;
-   if (slice >= A.nslices) return;
-   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
-   const long long off = A.sliceOff[slice];
-   const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
-   double acc = 0.0;
+// Accumulate a0..a2 += K * U_c (one value array, three component vectors) over this lane's entries.
+__device__ __forceinline__ void lane_dot_k3(const Sell& K, const double* __restrict__ val, const RowMap& m, const double* __restrict__ U,
+                                            long long NN, double& a0, double& a1, double& a2) {
+   const long long off = K.sliceOff[m.slice];
+   const int np = (int)((K.sliceOff[m.slice + 1] - off) >> 6);
+#pragma unroll 4
+   for (int jp = 0; jp < np; jp++) {
+      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
+      const int2 c2 = ldnc_i2(K.cols + e);
+      const double2 v2 = ldnc_d2(val + e);
+      a0 += v2.x * __ldg(U + c2.x) + v2.y * __ldg(U + c2.y);
+      a1 += v2.x * __ldg(U + NN + c2.x) + v2.y * __ldg(U + NN + c2.y);
+      a2 += v2.x * __ldg(U + 2 * NN + c2.x) + v2.y * __ldg(U + 2 * NN + c2.y);
+   }
+}
+// Accumulate a_c += sign * G_c * p (three value arrays, one vector); p(col) is supplied by a functor so
+// that callers can form it on the fly (e.g. 2 Pk_prev - Pk_prevprev).
+template <typename PF>
+__device__ __forceinline__ void lane_dot_g3(const Sell& G, const RowMap& m, PF pf, double sign, double& a0, double& a1, double& a2) {
+   const long long off = G.sliceOff[m.slice];
+   const int np = (int)((G.sliceOff[m.slice + 1] - off) >> 6);
 #pragma unroll 2
    for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * lane;
-      const int2 c2 = ldnc_i2(A.cols + e);
-      const double2 v2 = ldnc_d2(val + e);
-      acc += v2.x * __ldg(x + c2.x) + v2.y * __ldg(x + c2.y);
-   }
-   for (int o = A.T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-   const int row = slice * A.R + lane / A.T;
-   if ((lane % A.T) == 0 && row < A.nrows) {
-      double r = alpha * acc;
-      if (beta != 0.0) r += beta * y[row];
-      y[row] = r;
+      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
+      const int2 c2 = ldnc_i2(G.cols + e);
+      const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
+      const double px = sign * pf(c2.x), py = sign * pf(c2.y);
+      a0 += g1.x * px + g1.y * py;
+      a1 += g2.x * px + g2.y * py;
+      a2 += g3.x * px + g3.y * py;
    }
 }
 
 // step 1 of the explicit scheme, fused (replaces step1GPUpart, BCH.cu:946-973: 6 csrmv + applyVelBC +
 // calculate_UnpHalf):   R1_c = R1_c - K*Uprev_c - G_c*Pn ;  R1[bc] = 0 ;  UnpHalf = Un + dt*R1*MdInv
+// K and G share the row partition (same T), so one thread owns the same row in both.
 __global__ void __launch_bounds__(256) k_step1(Sell K, Sell G, int NN, const double* __restrict__ Uprev,
                                                const double* __restrict__ Pn, const double* __restrict__ Un,
                                                const double* __restrict__ MdInv, const int* __restrict__ bcIndex,
                                                double* __restrict__ R1, double* __restrict__ UnpHalf, double dt) {
-   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-   const int slice = row >> 5, lane = row & 31;
-   if (slice >= K.nslices) return;
+   RowMap m;
+   if (!row_map(K, m)) return;
    double a0 = 0, a1 = 0, a2 = 0;
-   {
-      const double* __restrict__ val = K.vals[0];
-      const long long off = K.sliceOff[slice];
-      const int np = (int)((K.sliceOff[slice + 1] - off) >> 6);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(K.cols + e);
-         const double2 v2 = ldnc_d2(val + e);
-         a0 += v2.x * __ldg(Uprev + c2.x) + v2.y * __ldg(Uprev + c2.y);
-         a1 += v2.x * __ldg(Uprev + NN + c2.x) + v2.y * __ldg(Uprev + NN + c2.y);
-         a2 += v2.x * __ldg(Uprev + 2 * (long long)NN + c2.x) + v2.y * __ldg(Uprev + 2 * (long long)NN + c2.y);
-      }
-   }
-   {
-      const long long off = G.sliceOff[slice];
-      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(G.cols + e);
-         const double px = __ldg(Pn + c2.x), py = __ldg(Pn + c2.y);
-         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
-         a0 += g1.x * px + g1.y * py;
-         a1 += g2.x * px + g2.y * py;
-         a2 += g3.x * px + g3.y * py;
-      }
-   }
-   if (row < NN) {
-      const bool bc = bcIndex[row] >= 0;
+   lane_dot_k3(K, K.vals[0], m, Uprev, NN, a0, a1, a2);
+   lane_dot_g3(G, m, [Pn](int c) { return __ldg(Pn + c); }, 1.0, a0, a1, a2);
+   a0 = lanes_sum(a0, K.T); a1 = lanes_sum(a1, K.T); a2 = lanes_sum(a2, K.T);
+   if (m.owner) {
+      const bool bc = bcIndex[m.row] >= 0;
       const double acc[3] = {a0, a1, a2};
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-         const long long i = (long long)c * NN + row;
+         const long long i = (long long)c * NN + m.row;
          const double r = bc ? 0.0 : (R1[i] - acc[c]);
          R1[i] = r;
          UnpHalf[i] = Un[i] + dt * r * MdInv[i];
@@ -255,29 +274,18 @@ __global__ void __launch_bounds__(256) k_step3(Sell G, int NN, const double* __r
                                                double* __restrict__ R3, double* __restrict__ Acc,
                                                double* __restrict__ Unp1, double dt, double* __restrict__ sums) {
    __shared__ double sh[64];
-   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-   const int slice = row >> 5, lane = row & 31;
+   RowMap m;
    double s[2] = {0.0, 0.0};
-   if (slice < G.nslices) {
+   if (row_map(G, m)) {
       double a0 = 0, a1 = 0, a2 = 0;
-      const long long off = G.sliceOff[slice];
-      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(G.cols + e);
-         const double px = __ldg(Pdot + c2.x), py = __ldg(Pdot + c2.y);
-         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
-         a0 += g1.x * px + g1.y * py;
-         a1 += g2.x * px + g2.y * py;
-         a2 += g3.x * px + g3.y * py;
-      }
-      if (row < NN) {
-         const bool bc = bcIndex[row] >= 0;
+      lane_dot_g3(G, m, [Pdot](int c) { return __ldg(Pdot + c); }, 1.0, a0, a1, a2);
+      a0 = lanes_sum(a0, G.T); a1 = lanes_sum(a1, G.T); a2 = lanes_sum(a2, G.T);
+      if (m.owner) {
+         const bool bc = bcIndex[m.row] >= 0;
          const double acc[3] = {a0, a1, a2};
 #pragma unroll
          for (int c = 0; c < 3; c++) {
-            const long long i = (long long)c * NN + row;
+            const long long i = (long long)c * NN + m.row;
             double r = -dt * acc[c];
             if (useKAcc) r = r - dt * KAcc[i];
             if (bc) r = 0.0;
@@ -487,21 +495,24 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
    }
 }
 
-// Dirichlet rows of A -> identity rows (applyVelBC_LHS, GQ.cu:478-498), on the Sell layout (T = 1).
+// Dirichlet rows of A -> identity rows (applyVelBC_LHS, GQ.cu:478-498), on the Sell layout.
 __global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restrict__ bcNodes) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= nbc) return;
    const int row = bcNodes[i];
-   const int slice = row >> 5, lane = row & 31;
+   const int slice = row / A.R, rl = row % A.R;
    const long long off = A.sliceOff[slice];
    const int w = (int)((A.sliceOff[slice + 1] - off) >> 5);
    double* val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
    bool diagDone = false;
-   for (int j = 0; j < w; j++) {
-      const long long pos = off + (long long)(j >> 1) * 64 + 2 * lane + (j & 1);
-      const bool isDiag = (!diagDone && A.cols[pos] == row);
-      val[pos] = isDiag ? 1.0 : 0.0;
-      diagDone = diagDone || isDiag;
+   for (int lane = 0; lane < A.T; lane++) {
+      const int t = rl * A.T + lane;
+      for (int j = 0; j < w; j++) {
+         const long long pos = off + (long long)(j >> 1) * 64 + 2 * t + (j & 1);
+         const bool isDiag = (!diagDone && A.cols[pos] == row);
+         val[pos] = isDiag ? 1.0 : 0.0;
+         diagDone = diagDone || isDiag;
+      }
    }
 }
 
@@ -517,44 +528,17 @@ __global__ void __launch_bounds__(256) k_gq_rhs(Sell MK, int mIdx, Sell G, int N
                                                 const double* __restrict__ Pk_prev, const double* __restrict__ Pk_prevprev,
                                                 const int* __restrict__ bcIndex, const double* __restrict__ BCstr,
                                                 double* __restrict__ R1) {
-   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-   const int slice = row >> 5, lane = row & 31;
-   if (slice >= MK.nslices) return;
+   RowMap m;
+   if (!row_map(MK, m)) return;
    double a0 = 0, a1 = 0, a2 = 0;
-   {
-      const double* __restrict__ val = mIdx == 0 ? MK.vals[0] : (mIdx == 1 ? MK.vals[1] : MK.vals[2]);
-      const long long off = MK.sliceOff[slice];
-      const int np = (int)((MK.sliceOff[slice + 1] - off) >> 6);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(MK.cols + e);
-         const double2 v2 = ldnc_d2(val + e);
-         a0 += v2.x * __ldg(Uprev + c2.x) + v2.y * __ldg(Uprev + c2.y);
-         a1 += v2.x * __ldg(Uprev + NN + c2.x) + v2.y * __ldg(Uprev + NN + c2.y);
-         a2 += v2.x * __ldg(Uprev + 2 * (long long)NN + c2.x) + v2.y * __ldg(Uprev + 2 * (long long)NN + c2.y);
-      }
-   }
-   {
-      const long long off = G.sliceOff[slice];
-      const int np = (int)((G.sliceOff[slice + 1] - off) >> 6);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(G.cols + e);
-         const double px = 2 * __ldg(Pk_prev + c2.x) - __ldg(Pk_prevprev + c2.x);
-         const double py = 2 * __ldg(Pk_prev + c2.y) - __ldg(Pk_prevprev + c2.y);
-         const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
-         a0 -= g1.x * px + g1.y * py;
-         a1 -= g2.x * px + g2.y * py;
-         a2 -= g3.x * px + g3.y * py;
-      }
-   }
-   if (row < NN) {
-      const int w = bcIndex[row];
-      R1[row] = (w >= 0) ? BCstr[3 * w + 0] : a0;
-      R1[(long long)NN + row] = (w >= 0) ? BCstr[3 * w + 1] : a1;
-      R1[2 * (long long)NN + row] = (w >= 0) ? BCstr[3 * w + 2] : a2;
+   lane_dot_k3(MK, sell_vals(MK, mIdx), m, Uprev, NN, a0, a1, a2);
+   lane_dot_g3(G, m, [Pk_prev, Pk_prevprev](int c) { return 2 * __ldg(Pk_prev + c) - __ldg(Pk_prevprev + c); }, -1.0, a0, a1, a2);
+   a0 = lanes_sum(a0, MK.T); a1 = lanes_sum(a1, MK.T); a2 = lanes_sum(a2, MK.T);
+   if (m.owner) {
+      const int w = bcIndex[m.row];
+      R1[m.row] = (w >= 0) ? BCstr[3 * w + 0] : a0;
+      R1[(long long)NN + m.row] = (w >= 0) ? BCstr[3 * w + 1] : a1;
+      R1[2 * (long long)NN + m.row] = (w >= 0) ? BCstr[3 * w + 2] : a2;
    }
 }
 
@@ -745,39 +729,56 @@ struct BicgArgs {
    int maxit;
 };
 
-// out_s = A * in_s for the active systems (multi-RHS: one pass over A); returns nothing, the caller
-// computes its dots in the following elementwise sweep... except that fusing the dot here saves a pass:
-// dots[s][0] += l1_s[row]*out, dots[s][1] += out*out
-__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, int vidx, int n, const double* in, double* out, const bool (&act)[3],
-                                                const double* l1, double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
-   const double* __restrict__ val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
+// out_s = A * in_s for the NA still-active systems sys[0..NA) (multi-RHS: one pass over A), fused with
+// the two dot products every BiCGStab SpMV is followed by: d0[s] += l1_s . out_s, d1[s] += out_s . out_s.
+// Specialised on NA so that the common late phase (one slow system left) runs a lean single-vector loop
+// with four matrix pairs in flight per lane.
+template <int NA>
+__device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, const double* __restrict__ val, int n, const double* in,
+                                             double* out, const int (&sys)[3], const double* l1, double (&d0)[3], double (&d1)[3],
+                                             int gwarp, int nwarps, int lane) {
+   const int T = A.T, sub = lane % T;
    const SliceRange sr = slice_range(A.nslices, part, gwarp, nwarps);
+   const double* inb[NA];
+#pragma unroll
+   for (int q = 0; q < NA; q++) inb[q] = in + (size_t)sys[q] * n;
    for (int s = sr.begin; s < sr.end; s += sr.step) {
       const long long off = A.sliceOff[s];
       const int np = (int)((A.sliceOff[s + 1] - off) >> 6);
-      double a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll 2
+      double acc[NA];
+#pragma unroll
+      for (int q = 0; q < NA; q++) acc[q] = 0.0;
+#pragma unroll 4
       for (int jp = 0; jp < np; jp++) {
          const long long e = off + ((long long)jp << 6) + 2 * lane;
          const int2 c2 = ldnc_i2(A.cols + e);
          const double2 v2 = ldnc_d2(val + e);
-         if (act[0]) a0 += v2.x * in[c2.x] + v2.y * in[c2.y];
-         if (act[1]) a1 += v2.x * in[(size_t)n + c2.x] + v2.y * in[(size_t)n + c2.y];
-         if (act[2]) a2 += v2.x * in[2 * (size_t)n + c2.x] + v2.y * in[2 * (size_t)n + c2.y];
-      }
-      const int row = s * 32 + lane;   // T = 1
-      if (row < n) {
-         const double acc[3] = {a0, a1, a2};
 #pragma unroll
-         for (int c = 0; c < 3; c++)
-            if (act[c]) {
-               const size_t i = (size_t)c * n + row;
-               out[i] = acc[c];
-               d0[c] += l1[i] * acc[c];
-               d1[c] += acc[c] * acc[c];
-            }
+         for (int q = 0; q < NA; q++) acc[q] += v2.x * inb[q][c2.x] + v2.y * inb[q][c2.y];
+      }
+#pragma unroll
+      for (int q = 0; q < NA; q++) acc[q] = lanes_sum(acc[q], T);
+      const int row = s * A.R + lane / T;
+      if (sub == 0 && row < n) {
+#pragma unroll
+         for (int q = 0; q < NA; q++) {
+            const size_t i = (size_t)sys[q] * n + row;
+            out[i] = acc[q];
+            d0[sys[q]] += l1[i] * acc[q];
+            d1[sys[q]] += acc[q] * acc[q];
+         }
       }
    }
+}
+__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, int vidx, int n, const double* in, double* out, const bool (&act)[3],
+                                                const double* l1, double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
+   const double* __restrict__ val = sell_vals(A, vidx);
+   int sys[3] = {0, 0, 0}, na = 0;
+   for (int c = 0; c < 3; c++)
+      if (act[c]) sys[na++] = c;
+   if (na == 1) bicg_spmv_na<1>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 2) bicg_spmv_na<2>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 3) bicg_spmv_na<3>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
 }
 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
@@ -1118,10 +1119,11 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       CFD_CK(cudaMemcpyToSymbol(cSv8, sv8, sizeof sv8));
       CFD_CK(cudaMemcpyToSymbol(cdSv8, dsv8, sizeof dsv8));
    }
-   // ---- matrices -> Sell
+   // ---- matrices -> Sell.  The velocity-row matrices (K/M/A and G) share one row partition (same T).
+   const int Tv = choose_Tv(NN, P->sparseM_nnz);
    {
       SellHost h;
-      sell_build_host(NN, NN, P->sparseMrowStarts, P->sparseMcol, 1, h);
+      sell_build_host(NN, NN, P->sparseMrowStarts, P->sparseMcol, Tv, h);
       c->hostOffK = h.sliceOff;
       if (P->scheme == CFD_EXPLICIT) {
          const double* v[1] = {P->sparseKvalue};
@@ -1149,7 +1151,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    {
       SellHost h;
-      sell_build_host(NN, NNp, P->sparseGrowStarts, P->sparseGcol, 1, h);
+      sell_build_host(NN, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, h);
       const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
       TRY(sell_upload(h, 3, v, c->G));
    }
@@ -1248,7 +1250,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       int occ2 = 0;
       CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_bicgstab3, c->bicg_threads, 0));
       if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
-      const int needed2 = std::max(1, (NN + c->bicg_threads - 1) / c->bicg_threads);
+      const int needed2 = (int)std::max<long long>(1, ((long long)c->K.nslices * 32 + c->bicg_threads - 1) / c->bicg_threads);
       int blocks2 = c->numSMs * occ2;
       if (needed2 < blocks2) blocks2 = std::max(c->numSMs, ((needed2 + c->numSMs - 1) / c->numSMs) * c->numSMs);
       c->bicg_blocks = std::min(blocks2, c->numSMs * occ2);
