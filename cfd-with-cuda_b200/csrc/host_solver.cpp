@@ -414,6 +414,16 @@ int cfd_solver_write_tecplot(cfd_solver* s, const char* dat_path, const char* ti
    return write_tecplot(s->mesh, U.data(), P.data(), dat_path, title) ? CFD_OK : CFD_ERR_IO;
 }
 
+int cfd_solver_write_tecplot_fields(cfd_solver* s, const char* dat_path, const char* title, const double* U, const double* P) {
+   if (!s || !U || !P) return CFD_ERR_ARG;
+   return write_tecplot(s->mesh, U, P, dat_path, title) ? CFD_OK : CFD_ERR_IO;
+}
+
+int cfd_solver_read_restart_fields(cfd_solver* s, const char* dat_path, double* U, double* P) {
+   if (!s || !U || !P) return CFD_ERR_ARG;
+   return read_restart(s->mesh, dat_path, U, P) ? CFD_OK : CFD_ERR_IO;
+}
+
 int cfd_solver_read_restart(cfd_solver* s, const char* dat_path) {
    std::vector<double> U((size_t)3 * s->mesh.NN, 0.0), P((size_t)s->mesh.NNp, 0.0);
    if (!read_restart(s->mesh, dat_path, U.data(), P.data())) return CFD_ERR_IO;

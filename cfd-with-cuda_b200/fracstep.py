@@ -124,6 +124,9 @@ def lib():
     L.cfd_solver_array.restype = vp
     L.cfd_solver_write_tecplot.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.cfd_solver_read_restart.argtypes = [vp, C.c_char_p]
+    L.cfd_solver_write_tecplot_fields.argtypes = [vp, C.c_char_p, C.c_char_p, _dp, _dp]
+    L.cfd_solver_read_restart_fields.argtypes = [vp, C.c_char_p, _dp, _dp]
+    L.cfd_diag_sync.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp]
     L.cfd_solver_main.argtypes = [C.c_char_p, C.c_int, C.c_int]
     _lib = L
     return L
@@ -388,6 +391,17 @@ class Solver:
 
     def write_tecplot(self, path, title):
         _check(self.L.cfd_solver_write_tecplot(self.h, os.fsencode(path), title.encode()))
+
+    def write_tecplot_fields(self, path, title, U, P):
+        U = np.ascontiguousarray(U, np.float64)
+        P = np.ascontiguousarray(P, np.float64)
+        _check(self.L.cfd_solver_write_tecplot_fields(self.h, os.fsencode(path), title.encode(), _d(U), _d(P)))
+
+    def read_restart_fields(self, path):
+        U = np.zeros(3 * self.i("NN"))
+        P = np.zeros(self.i("NNp"))
+        _check(self.L.cfd_solver_read_restart_fields(self.h, os.fsencode(path), _d(U), _d(P)))
+        return U, P
 
     def read_restart(self, path):
         _check(self.L.cfd_solver_read_restart(self.h, os.fsencode(path)))

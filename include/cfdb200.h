@@ -206,6 +206,10 @@ long long cfd_solver_int(cfd_solver* s, const char* name);
 const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, int* is_int);
 /* createTecplot() BCH.cpp:4249-4482 and readRestartFile() BCH.cpp:4214-4242 */
 int cfd_solver_write_tecplot(cfd_solver* s, const char* dat_path, const char* title);
+/* same writer on caller-supplied host fields U [3NN], P [NNp] (no GPU needed) */
+int cfd_solver_write_tecplot_fields(cfd_solver* s, const char* dat_path, const char* title, const double* U, const double* P);
+/* restart reader into host buffers U [3NN], P [NNp] (no GPU needed) */
+int cfd_solver_read_restart_fields(cfd_solver* s, const char* dat_path, double* U, double* P);
 int cfd_solver_read_restart(cfd_solver* s, const char* dat_path);
 /* the reference's main(): reads ./ProblemName.txt, runs to t_final, prints the monitor table,
  * writes <name>.dat.  max_steps > 0 bounds the run. */

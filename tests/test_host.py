@@ -1,0 +1,97 @@
+"""CPU: the product's own host code (mesh reader, hashed node generation, sparsity, step0 assembly,
+Tecplot / restart I/O) against the oracle's line-faithful restatement -- no GPU involved."""
+import os
+
+import numpy as np
+import pytest
+
+MESHES = {
+    "h_q2_c6": dict(n=6, cluster=2.0),
+    "h_q2_u5": dict(n=5, full_precision=True),
+    "h_q1_u7": dict(n=7, NENv=8, full_precision=True),
+    "h_q2_343": dict(n=3, ny=4, nz=3),
+}
+INT_ARRAYS = ["LtoGnode", "BCvelNodes", "sparseMrowStarts", "sparseMcol", "sparseGrowStarts", "sparseGcol", "sparseZrowStarts",
+              "sparseZcol", "sparseMapM_1d", "meshColors", "NmeshColors", "elementsOfColor"]
+
+
+@pytest.mark.parametrize("scheme", ["explicit", "implicit"])
+@pytest.mark.parametrize("name", list(MESHES))
+def test_preprocessing_and_step0_match_oracle(mesh, name, scheme):
+    import fracstep
+    import orc
+    path = mesh(name, **MESHES[name])
+    o = orc.Oracle(path, scheme)
+    s = fracstep.Solver(path, scheme, init_gpu=False)
+    for k in ("NE", "NN", "NNp", "BCnVelNodes", "monPoint", "zeroPressureNode", "maxIter"):
+        assert s.i(k) == o.i(k), k
+    for k in ("nnzM", "nnzG", "nnzZ", "nActiveColors"):
+        assert s.L.cfd_solver_int(s.h, k.encode()) == o.i(k), k
+    assert np.array_equal(s.arr("coord"), o.arr("coord"))   # same midpoint arithmetic, bit for bit
+    for k in INT_ARRAYS:
+        assert np.array_equal(s.arr(k), o.arr(k)), k
+    vals = ["sparseKvalue", "sparseMvalue", "sparseG1value", "sparseG2value", "sparseG3value", "sparseZvalue"]
+    if scheme == "explicit":
+        vals += ["MdInv", "MdOrigInv"]
+    for k in vals:
+        a, b = s.arr(k), o.arr(k)
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), k
+    for k in ("dt", "viscosity", "density", "tolerance", "convergenceCriteria"):
+        assert s.d(k) == o.d(k)
+
+
+def test_in_memory_cavity_equals_inp(mesh):
+    """cfd_solver_create_cavity numbers nodes / elements / BC faces exactly like the .inp written by the cube generator."""
+    import fracstep
+    for kw in (dict(n=4, cluster=2.0, full_precision=True), dict(n=5, NENv=8, full_precision=True)):
+        path = mesh("mem_%d_%d" % (kw["n"], kw.get("NENv", 27)), **kw)
+        a = fracstep.Solver(path, "explicit", init_gpu=False)
+        b = fracstep.Solver(scheme="explicit", init_gpu=False,
+                            cavity=dict(nx=kw["n"], cluster=kw.get("cluster", 0.0), NENv=kw.get("NENv", 27)))
+        for k in ("LtoGnode", "BCvelNodes", "sparseMcol", "sparseGcol", "sparseZcol"):
+            assert np.array_equal(a.arr(k), b.arr(k)), k
+        assert np.abs(a.arr("coord") - b.arr("coord")).max() < 1e-15
+        assert a.i("zeroPressureNode") == b.i("zeroPressureNode") and a.i("monPoint") == b.i("monPoint")
+
+
+def test_reader_rejects_bad_input(tmp_path, mesh):
+    import fracstep
+    with pytest.raises(fracstep.CfdError):
+        fracstep.Solver(str(tmp_path / "missing.inp"), "explicit", init_gpu=False)
+    good = open(mesh("h_q2_c6", **MESHES["h_q2_c6"])).read()
+    bad = tmp_path / "tet.inp"
+    bad.write_text(good.replace("eType    : 1", "eType    : 2"))
+    with pytest.raises(fracstep.CfdError):
+        fracstep.Solver(str(bad), "explicit", init_gpu=False)
+    trunc = tmp_path / "trunc.inp"
+    trunc.write_text(good[: len(good) // 3])
+    with pytest.raises(fracstep.CfdError):
+        fracstep.Solver(str(trunc), "explicit", init_gpu=False)
+
+
+@pytest.mark.parametrize("name", ["h_q2_c6", "h_q1_u7"])
+def test_tecplot_and_restart_formats(mesh, tmp_path, name):
+    """createTecplot bytes (BCH.cpp:4249-4482) and readRestartFile (BCH.cpp:4214-4242): product == oracle."""
+    import fracstep
+    import orc
+    path = mesh(name, **MESHES[name])
+    o = orc.Oracle(path, "explicit")
+    o.run(2)
+    s = fracstep.Solver(path, "explicit", init_gpu=False)
+    f_o, f_p = str(tmp_path / "o.dat"), str(tmp_path / "p.dat")
+    o.write_tecplot(f_o, "lidDrivenCavity")
+    s.write_tecplot_fields(f_p, "lidDrivenCavity", o.U, o.P)
+    a, b = open(f_o).read(), open(f_p).read()
+    assert a == b
+    lines = a.split("\n")
+    assert lines[0] == "TITLE = lidDrivenCavity" and lines[1] == "VARIABLES = x,  y,  z,  u, v, w, p"
+    NN, NE = o.i("NN"), o.i("NE")
+    nsub = 8 if o.i("NENv") == 27 else 1
+    assert lines[2] == "ZONE N=%d, E=%d, F=FEPOINT, ET=BRICK" % (NN, nsub * NE)
+    assert len(lines) == 3 + NN + nsub * NE + 1
+    # restart: 11 significant digits survive
+    U, P = s.read_restart_fields(f_p)
+    assert np.allclose(U, o.U, rtol=2e-11, atol=1e-300) and np.allclose(P, o.P, rtol=2e-11, atol=1e-300)
+    o2 = orc.Oracle(path, "explicit")
+    o2.read_restart(f_o)
+    assert np.array_equal(o2.U, U) and np.array_equal(o2.P, P)
