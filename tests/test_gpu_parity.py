@@ -19,6 +19,15 @@ def rel(a, b):
     return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
 
 
+def rel_free(U, Uref, src):
+    """rel-L2 over the non-Dirichlet velocity DOFs only (the lid values would otherwise dominate the norm)."""
+    NN = src.i("NN")
+    free = np.ones(NN, bool)
+    free[src.arr("BCvelNodes")[0::2]] = False
+    m = np.tile(free, 3)
+    return rel(U[m], Uref[m])
+
+
 def make_pair(mesh, name, scheme, **opt):
     import fracstep
     import orc
@@ -109,6 +118,7 @@ def test_time_loop_parity(mesh, name, scheme, setting):
     q2_implicit_ref = scheme == "implicit" and setting == "reference" and CASES[name].get("NENv", 27) == 27
     bar = 5e-3 if q2_implicit_ref else 1e-6
     assert rel(U, o.U) <= bar, rel(U, o.U)
+    assert rel_free(U, o.U, o) <= 20 * bar, rel_free(U, o.U, o)   # interior field is ~1e-3 of the lid speed this early
     assert rel(P, o.P) <= bar, rel(P, o.P)
     ocg = o.arr("cgIters")
     if scheme == "explicit":
@@ -172,3 +182,73 @@ def test_spmv_and_pcg_kernels(mesh):
     # empty right-hand side: zero iterations, x untouched (CUSP monitor semantics)
     x, its, _ = fracstep.csr_pcg(zr, zc, zv, np.zeros(NNp))
     assert its == 0 and not x.any()
+
+
+GOLDEN = ["q2_c4_explicit", "q2_c6_explicit", "q1_u8_explicit", "q1_u8_implicit", "q2_c4_implicit_tight"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_against_golden_fixtures(mesh, name):
+    """Whole product pipeline (own .inp reader, node generation, step0, CUDA time loop) against the
+    committed oracle fixtures (tests/golden/make_golden.py)."""
+    import ast
+    import os
+    import fracstep
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    mk, opt = ast.literal_eval(str(g["mesh"])), ast.literal_eval(str(g["options"]))
+    s = fracstep.Solver(mesh("gold_" + name, **mk), str(g["scheme"]), opts=fracstep.options(**opt) if opt else None)
+    reps = s.ctx.time_loop(int(g["steps"]))
+    U, P = s.ctx.fields()
+    assert rel(U, g["U"]) <= 1e-6 and rel_free(U, g["U"], s) <= 2e-5
+    assert rel(P, g["P"]) <= (1e-6 if "implicit" in name else 1e-5)   # explicit P: CG tolerance x cond(Z), see test_oracle
+    if str(g["scheme"]) == "explicit":
+        assert [r["iter"] for r in reps] == list(g["innerIters"])
+        assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cgIters"].sum())) <= 2 * len(g["cgIters"])
+    else:
+        assert all(abs(r["cg_iterations"] - k) <= 2 for r, k in zip(reps, g["cgIters"]))
+
+
+@pytest.mark.parametrize("scheme,steps", [("explicit", 3), ("implicit", 1)])
+def test_ne27000_full_size(mesh, scheme, steps):
+    """BASELINE configs[0]/[1] at full size: the shipped 30^3 Taylor-Hood cavity (regenerated byte-identically),
+    product pipeline on the GPU against the oracle."""
+    import fracstep
+    import orc
+    visc = 0.01 if scheme == "explicit" else 0.001
+    path = mesh("ne27000_%s" % scheme, n=30, cluster=2.0, viscosity=visc)
+    o = orc.Oracle(path, scheme)
+    s = fracstep.Solver(path, scheme)
+    o.run(steps)
+    reps = s.ctx.time_loop(steps)
+    U, P = s.ctx.fields()
+    if scheme == "explicit":
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-6
+        assert [r["iter"] for r in reps] == list(o.arr("innerIters"))
+        assert abs(sum(r["cg_iterations"] for r in reps) - int(o.arr("cgIters").sum())) <= 2 * len(o.arr("cgIters"))
+    else:
+        # first implicit step: u converges in a few BiCGStab iterations, v = w = 0; P to the CG tolerance
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-4
+        assert abs(reps[0]["cg_iterations"] - int(o.arr("cgIters")[0])) <= 2
+
+
+def test_large_mesh_properties():
+    """Size-independent properties on a mesh the oracle would take minutes for (64^3 Q1/Q1, implicit):
+    Dirichlet values are reproduced to the solver tolerance, the pressure solve meets its stopping rule, the velocity
+    systems are solved to their tolerance (checked through a host SpMV with the product's own CSR arrays)."""
+    import scipy.sparse as sp
+    import fracstep
+    s = fracstep.Solver(scheme="implicit", cavity=dict(nx=64, NENv=8))
+    c = s.ctx
+    reps = c.time_loop(2)
+    assert all(0 < r["cg_iterations"] < 1000 for r in reps)
+    U, P = c.fields()
+    NN, NNp = s.i("NN"), s.i("NNp")
+    bc = s.arr("BCvelNodes").reshape(-1, 2)
+    vals = s.arr("BCstr").reshape(-1, 3)
+    for d in range(3):
+        # identity rows go through BiCGStab like every other row (GQ.cpp:4614-4643): exact to the solver tolerance
+        assert np.allclose(U[d * NN + bc[:, 0]], vals[bc[:, 1], d], rtol=0, atol=1e-5)
+    Z = sp.csr_matrix((s.arr("sparseZvalue"), s.arr("sparseZcol"), s.arr("sparseZrowStarts")), shape=(NNp, NNp))
+    R2, Pdiff = c.download("R2"), c.download("Pdiff")
+    assert np.linalg.norm(Z @ Pdiff - R2) <= 1.05e-6 * np.linalg.norm(R2)
+    assert R2[s.i("zeroPressureNode")] == 0.0
