@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <dlfcn.h>
+
 #include "kernels.cuh"
 
 namespace cfdb {
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const
    }
    for (int o = GT.T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
    const int row = slice * GT.R + lane / GT.T;
-   if ((lane % GT.T) == 0 && row < GT.nrows) R2[row] = (pinNode > 0 && row == pinNode) ? 0.0 : acc;
+   if ((lane % GT.T) == 0 && row < GT.nrows) R2[row] = (row == pinNode) ? 0.0 : acc;   // pinNode = -1: no pin
 }
 
 // =================================================================================================
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
 #pragma unroll
          for (int k = 0; k < 8; k++) a += Tab<NV>::Sv(k, i) * cj[k];
          const int pos = __ldg(mapT + (long long)(i * NV + j) * ldE + e);
-         atomicAdd(Aval + pos, a);
+         if (pos >= 0) atomicAdd(Aval + pos, a);   // -1: row owned by another rank
       }
    }
 }
@@ -550,6 +552,8 @@ __global__ void k_add(long long n, const double* __restrict__ a, const double* _
    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
       out[i] = a[i] + b[i];
 }
+
+#include "dist.cuh"
 
 // =================================================================================================
 // Persistent cooperative Krylov kernels
@@ -967,7 +971,153 @@ double spmv_bytes(const Sell& A, int nval, int nvec, bool accumulate) {
    return (8.0 * nval + 4.0) * (double)A.nnz + 4.0 * (A.nrows + 1.0) + 8.0 * nvec * ((double)A.ncols + (double)A.nrows * (accumulate ? 2 : 1));
 }
 
+// ---- multi-GPU primitives -----------------------------------------------------------------------------------
+inline bool parted(const cfd_ctx* c) { return c->P.world > 1; }
+
+int need_comm(cfd_ctx* c) {
+   if (parted(c) && (!c->comm || !c->comm->comm)) { set_error("partitioned context without communicator: call cfd_comm_init first"); return CFD_ERR_STATE; }
+   return CFD_OK;
+}
+
+// Ghost entries of `vec` <- owners' values.  velocity = true: 3-component node vector (stride NN); false: pressure vector.
+int halo(cfd_ctx* c, double* vec, bool velocity) {
+   if (!parted(c)) return CFD_OK;
+   int rc = need_comm(c);
+   if (rc) return rc;
+   Comm* cm = c->comm;
+   const int np = (int)c->peerRank.size();
+   const std::vector<int>& ptr = velocity ? c->sendVptr : c->sendPptr;
+   const std::vector<int>& roff = velocity ? c->recvVoff : c->recvPoff;
+   const std::vector<int>& rcnt = velocity ? c->recvVcnt : c->recvPcnt;
+   const int ncomp = velocity ? 3 : 1;
+   const long long ld = velocity ? c->P.NN : c->P.NNp;
+   const int ns = ptr[np];
+   const int* plan = velocity ? c->sendVidx : c->sendPidx;
+   ProfScope ps(c, "halo", 8.0 * ncomp * ns);
+   if (ns > 0) {
+      k_pack<<<gridFor(ns, 256), 256, 0, c->stream>>>(ns, ncomp, ld, plan, plan + ns, plan + 2 * ns, vec, c->sendBuf);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+   }
+   CFD_NCCL(cm, cm->GroupStart());
+   for (int j = 0; j < np; j++) {
+      const int cnt = ptr[j + 1] - ptr[j];
+      for (int q = 0; q < ncomp; q++) {
+         if (cnt > 0) CFD_NCCL(cm, cm->Send(c->sendBuf + (size_t)ncomp * ptr[j] + (size_t)q * cnt, cnt, kNcclFloat64, c->peerRank[j], cm->comm, c->stream));
+         if (rcnt[j] > 0) CFD_NCCL(cm, cm->Recv(vec + q * ld + roff[j], rcnt[j], kNcclFloat64, c->peerRank[j], cm->comm, c->stream));
+      }
+   }
+   CFD_NCCL(cm, cm->GroupEnd());
+   return CFD_OK;
+}
+
+int allreduce(cfd_ctx* c, double* dev, int n, int op) {
+   if (!parted(c)) return CFD_OK;
+   int rc = need_comm(c);
+   if (rc) return rc;
+   CFD_NCCL(c->comm, c->comm->AllReduce(dev, dev, n, kNcclFloat64, op, c->comm->comm, c->stream));
+   return CFD_OK;
+}
+
+// Distributed Jacobi-PCG (phase kernels + NCCL; see dist.cuh).  State read back once per batch of iterations.
+int run_pcg_dist(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   const int n = c->NPo;
+   double* acc = c->dacc;
+   DPcgState* st = (DPcgState*)(c->dacc + 32);
+   const int gridV = std::min(gridFor(n, 256), 8 * c->numSMs);
+   const int gridS = gridFor((long long)c->Z.nslices * 32, 256);
+   int rc;
+   ProfScope ps(c, "pcg", 0.0);
+   c->lastPcgRec = ps.idx;
+   CFD_CK(cudaMemsetAsync(acc, 0, 8 * sizeof(double), c->stream));
+   if (!x0zero) {
+      if ((rc = halo(c, x, false))) return rc;
+      k_spmv_multi<1><<<gridS, 256, 0, c->stream>>>(c->Z, 0, x, 0, c->cg_q, 0, 1.0, 0.0);
+      c->launches++;
+   }
+   k_dpcg_init<<<gridV, 256, 0, c->stream>>>(n, x0zero ? 1 : 0, b, x, c->cg_q, c->Zdinv, c->cg_r, c->cg_p, acc);
+   if ((rc = allreduce(c, acc + 3, 3, kNcclSum))) return rc;
+   k_dpcg_begin<<<1, 1, 0, c->stream>>>(st, acc, c->opt.cg_tol, c->opt.cg_maxit);
+   c->launches += 2;
+   const int batch = 8;
+   for (int it0 = 0; it0 <= c->opt.cg_maxit; it0 += batch) {
+      for (int k = 0; k < batch; k++) {
+         if ((rc = halo(c, c->cg_p, false))) return rc;
+         k_dpcg_spmv<<<gridS, 256, 0, c->stream>>>(c->Z, st, c->cg_p, c->cg_q, acc);
+         if ((rc = allreduce(c, acc, 1, kNcclSum))) return rc;
+         k_dpcg_update<<<gridV, 256, 0, c->stream>>>(n, st, c->cg_p, c->cg_q, c->Zdinv, x, c->cg_r, acc);
+         if ((rc = allreduce(c, acc + 1, 2, kNcclSum))) return rc;
+         k_dpcg_pupdate<<<gridV, 256, 0, c->stream>>>(n, st, c->cg_r, c->Zdinv, c->cg_p, acc);
+         k_dpcg_next<<<1, 1, 0, c->stream>>>(st, acc);
+         c->launches += 4;
+      }
+      CFD_CK(cudaMemcpyAsync(c->h_pinned + 40, st, sizeof(DPcgState), cudaMemcpyDeviceToHost, c->stream));
+      CFD_CK(cudaStreamSynchronize(c->stream));
+      const DPcgState* hs = (const DPcgState*)(c->h_pinned + 40);
+      if (hs->done) {
+         // mirror the persistent kernel's result slots
+         const double info[3] = {(double)hs->it, hs->rr, hs->bb};
+         CFD_CK(cudaMemcpyAsync(c->kinfo, info, sizeof info, cudaMemcpyHostToDevice, c->stream));
+         CFD_CK(cudaStreamSynchronize(c->stream));
+         break;
+      }
+   }
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
+// Distributed Jacobi-BiCGStab for the three momentum systems (phase kernels + NCCL).
+int run_bicg_dist(cfd_ctx* c) {
+   const int n = c->NNo;
+   const long long ld = c->P.NN;
+   const size_t N3 = 3 * (size_t)ld;
+   double* acc = c->dacc;
+   DBicgState* st = (DBicgState*)(c->dacc + 32);
+   double *r = c->bw, *rs = c->bw + N3, *p = c->bw + 2 * N3, *ph = c->bw + 3 * N3, *AMp = c->bw + 4 * N3, *shv = c->bw + 5 * N3, *AMs = c->bw + 6 * N3;
+   const int gridV = std::min(gridFor(n, 256), 8 * c->numSMs);
+   const int gridS = gridFor((long long)c->K.nslices * 32, 256);
+   int rc;
+   ProfScope ps(c, "bicgstab", 0.0);
+   c->lastBicgRec = ps.idx;
+   CFD_CK(cudaMemsetAsync(acc, 0, 24 * sizeof(double), c->stream));
+   k_dbicg_init<<<gridV, 256, 0, c->stream>>>(n, ld, c->R1i, c->Adinv, c->Uk, r, rs, p, ph, acc);
+   if ((rc = allreduce(c, acc, 3, kNcclSum))) return rc;
+   k_dbicg_begin<<<1, 1, 0, c->stream>>>(st, acc, c->opt.bicg_tol, c->opt.bicg_maxit);
+   c->launches += 2;
+   const int batch = 4;
+   for (int it0 = 0; it0 <= c->opt.bicg_maxit; it0 += batch) {
+      for (int k = 0; k < batch; k++) {
+         if ((rc = halo(c, ph, true))) return rc;
+         k_dbicg_spmv<<<gridS, 256, 0, c->stream>>>(c->K, 2, ld, st, 0, ph, AMp, rs, acc, 0, 3);
+         if ((rc = allreduce(c, acc, 3, kNcclSum))) return rc;
+         k_dbicg_s<<<gridV, 256, 0, c->stream>>>(n, ld, st, AMp, c->Adinv, r, shv, acc);
+         if ((rc = allreduce(c, acc + 6, 3, kNcclSum))) return rc;
+         k_dbicg_mid<<<1, 1, 0, c->stream>>>(st, acc);
+         if ((rc = halo(c, shv, true))) return rc;
+         k_dbicg_spmv<<<gridS, 256, 0, c->stream>>>(c->K, 2, ld, st, 1, shv, AMs, r, acc, 12, 15);
+         if ((rc = allreduce(c, acc + 12, 6, kNcclSum))) return rc;
+         k_dbicg_x<<<gridV, 256, 0, c->stream>>>(n, ld, st, ph, shv, AMs, rs, c->Uk, r, acc);
+         if ((rc = allreduce(c, acc + 18, 6, kNcclSum))) return rc;
+         k_dbicg_p<<<gridV, 256, 0, c->stream>>>(n, ld, st, r, AMp, c->Adinv, p, ph, acc);
+         k_dbicg_next<<<1, 1, 0, c->stream>>>(st, acc);
+         c->launches += 7;
+      }
+      CFD_CK(cudaMemcpyAsync(c->h_pinned + 40, st, sizeof(DBicgState), cudaMemcpyDeviceToHost, c->stream));
+      CFD_CK(cudaStreamSynchronize(c->stream));
+      const DBicgState* hs = (const DBicgState*)(c->h_pinned + 40);
+      if (hs->done) {
+         const double info[3] = {(double)hs->its[0], (double)hs->its[1], (double)hs->its[2]};
+         CFD_CK(cudaMemcpyAsync(c->kinfo + 3, info, sizeof info, cudaMemcpyHostToDevice, c->stream));
+         CFD_CK(cudaStreamSynchronize(c->stream));
+         break;
+      }
+   }
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   if (parted(c)) return run_pcg_dist(c, b, x, x0zero);
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
@@ -1004,7 +1154,7 @@ int fetch_kinfo(cfd_ctx* c) {
 
 template <int NV>
 int launch_ebe_apply(cfd_ctx* c, const double* Uadv, const double* Ux, double* R1) {
-   const int NE = c->P.NE;
+   const int NE = c->NEa;   // elements touching an owned node
    k_ebe_convect_apply<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, Ux, R1);
    c->launches++;
    CFD_CK(cudaGetLastError());
@@ -1012,7 +1162,7 @@ int launch_ebe_apply(cfd_ctx* c, const double* Uadv, const double* Ux, double* R
 }
 template <int NV>
 int launch_ebe_assemble(cfd_ctx* c, const double* Uadv, double* Aval) {
-   const int NE = c->P.NE;
+   const int NE = c->NEa;
    k_ebe_convect_assemble<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, c->mapT, Aval);
    c->launches++;
    CFD_CK(cudaGetLastError());
@@ -1056,6 +1206,7 @@ void cfd_destroy(cfd_ctx* c) {
    if (c->stream) cudaStreamSynchronize(c->stream);
    for (void* p : c->allocs) cudaFree(p);
    sell_free(c->K); sell_free(c->G); sell_free(c->GT); sell_free(c->Z);
+   if (c->comm) { if (c->comm->comm) c->comm->CommDestroy(c->comm->comm); delete c->comm; }
    if (c->h_pinned) cudaFreeHost(c->h_pinned);
    if (c->ev0) cudaEventDestroy(c->ev0);
    if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1097,9 +1248,17 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    else CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
    CFD_CK(cudaEventCreate(&c->ev0));
    CFD_CK(cudaEventCreate(&c->ev1));
-   CFD_CK(cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double)));
+   CFD_CK(cudaMallocHost((void**)&c->h_pinned, 128 * sizeof(double)));
 
    const int NN = P->NN, NNp = P->NNp, NE = P->NE, nv = P->NENv;
+   // partition: NN / NNp are local (owned + ghost) counts, rows are the owned ones (numbered first)
+   const bool parted = P->world > 1;
+   const int NNo = (parted && P->NN_owned > 0) ? P->NN_owned : NN;
+   const int NPo = (parted && P->NNp_owned > 0) ? P->NNp_owned : NNp;
+   c->NNo = NNo; c->NPo = NPo;
+   c->NEa = (parted && P->NE_apply > 0) ? P->NE_apply : NE;
+   c->pin = parted ? P->pinLocal : (P->zeroPressureNode > 0 ? P->zeroPressureNode : -1);   // `node > 0` rule, BCH.cpp:4172
+   c->monOwned = parted ? (P->monOwned != 0) : true;
    int rc;
 #define TRY(x) do { rc = (x); if (rc) { cfd_destroy(c); return rc; } } while (0)
 
@@ -1120,18 +1279,19 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       CFD_CK(cudaMemcpyToSymbol(cdSv8, dsv8, sizeof dsv8));
    }
    // ---- matrices -> Sell.  The velocity-row matrices (K/M/A and G) share one row partition (same T).
-   const int Tv = choose_Tv(NN, P->sparseM_nnz);
+   const int Tv = choose_Tv(NNo, P->sparseMrowStarts[NNo]);
    {
       SellHost h;
-      sell_build_host(NN, NN, P->sparseMrowStarts, P->sparseMcol, Tv, h);
+      sell_build_host(NNo, NN, P->sparseMrowStarts, P->sparseMcol, Tv, h);
       c->hostOffK = h.sliceOff;
       if (P->scheme == CFD_EXPLICIT) {
          const double* v[1] = {P->sparseKvalue};
          TRY(sell_upload(h, 1, v, c->K));
       } else {
-         std::vector<double> mk((size_t)P->sparseM_nnz);
+         const long long nnzOwned = P->sparseMrowStarts[NNo];
+         std::vector<double> mk((size_t)nnzOwned);
 #pragma omp parallel for schedule(static)
-         for (long long k = 0; k < P->sparseM_nnz; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
+         for (long long k = 0; k < nnzOwned; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
          const double* v[3] = {mk.data(), P->sparseMvalue, nullptr};
          TRY(sell_upload(h, 3, v, c->K));
          // element -> Sell position map, transposed to [q][e]
@@ -1139,11 +1299,14 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          std::vector<int> mt((size_t)nv * nv * c->ldE, 0);
 #pragma omp parallel for schedule(static)
          for (int e = 0; e < NE; e++)
-            for (int q = 0; q < nv * nv; q++) mt[(size_t)q * c->ldE + e] = (int)h.perm[(size_t)P->sparseMapM_1d[(size_t)e * nv * nv + q]];
+            for (int q = 0; q < nv * nv; q++) {
+               const int row = P->LtoGnode[(size_t)e * nv + q / nv];
+               mt[(size_t)q * c->ldE + e] = row < NNo ? (int)h.perm[(size_t)P->sparseMapM_1d[(size_t)e * nv * nv + q]] : -1;
+            }
          TRY(dupload(c, &c->mapT, mt.data(), mt.size()));
-         std::vector<int> dp(NN, 0);
+         std::vector<int> dp(NNo, 0);
 #pragma omp parallel for schedule(static)
-         for (int r = 0; r < NN; r++)
+         for (int r = 0; r < NNo; r++)
             for (int k = P->sparseMrowStarts[r]; k < P->sparseMrowStarts[r + 1]; k++)
                if (P->sparseMcol[k] == r) { dp[r] = (int)h.perm[k]; break; }
          TRY(dupload(c, &c->diagPosA, dp.data(), dp.size()));
@@ -1151,7 +1314,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    {
       SellHost h;
-      sell_build_host(NN, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, h);
+      sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, h);
       const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
       TRY(sell_upload(h, 3, v, c->G));
    }
@@ -1170,19 +1333,19 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             tcol[p] = r; t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k];
          }
       SellHost h;
-      sell_build_host(NNp, NN, ts.data(), tcol.data(), choose_T(NNp, nnzG), h);
+      sell_build_host(NPo, NN, ts.data(), tcol.data(), choose_T(NPo, ts[NPo]), h);   // rows = owned pressure DOFs, all local velocity columns
       const double* v[3] = {t1.data(), t2.data(), t3.data()};
       TRY(sell_upload(h, 3, v, c->GT));
    }
    {
       SellHost h;
-      sell_build_host(NNp, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NNp, P->sparseZ_nnz), h);
+      sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NPo, P->sparseZrowStarts[NPo]), h);
       c->hostOffZ = h.sliceOff;
       const double* v[1] = {P->sparseZvalue};
       TRY(sell_upload(h, 1, v, c->Z));
-      std::vector<double> dinv(NNp, 1.0);
+      std::vector<double> dinv(NPo, 1.0);
 #pragma omp parallel for schedule(static)
-      for (int r = 0; r < NNp; r++)
+      for (int r = 0; r < NPo; r++)
          for (int k = P->sparseZrowStarts[r]; k < P->sparseZrowStarts[r + 1]; k++)
             if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
       TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
@@ -1196,8 +1359,13 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          for (int i = 0; i < nv; i++) lt[(size_t)i * c->ldE + e] = P->LtoGnode[(size_t)e * nv + i];
       TRY(dupload(c, &c->LtoGT, lt.data(), lt.size()));
       TRY(dupload(c, &c->coord, P->coord, (size_t)NN * 3));
-      std::vector<int> bi(NN, -1), bn(P->BCnVelNodes);
-      for (int i = 0; i < P->BCnVelNodes; i++) { bn[i] = P->BCvelNodes[2 * i]; bi[bn[i]] = P->BCvelNodes[2 * i + 1]; }
+      std::vector<int> bi(NN, -1), bn;
+      for (int i = 0; i < P->BCnVelNodes; i++) {
+         const int node = P->BCvelNodes[2 * i];
+         bi[node] = P->BCvelNodes[2 * i + 1];
+         if (node < NNo) bn.push_back(node);   // identity rows only for owned Dirichlet nodes
+      }
+      c->P.BCnVelNodes = (int)bn.size();
       TRY(dupload(c, &c->bcIndex, bi.data(), bi.size()));
       TRY(dupload(c, &c->bcNodes, bn.data(), bn.size()));
       TRY(dupload(c, &c->BCstr, P->BCstr, (size_t)3 * P->nBC));
@@ -1235,6 +1403,30 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       double* Pd = P->scheme == CFD_EXPLICIT ? c->Pn : c->Pk_prev;
       CFD_CK(cudaMemcpy(Ud, u0.data(), sizeof(double) * N3, cudaMemcpyHostToDevice));
       if (P->P0) CFD_CK(cudaMemcpy(Pd, P->P0, sizeof(double) * NNp, cudaMemcpyHostToDevice));
+   }
+   // ---- partition plan
+   if (parted) {
+      const int np = P->nPeers;
+      c->peerRank.assign(P->peerRank, P->peerRank + np);
+      c->sendVptr.assign(P->sendVptr, P->sendVptr + np + 1); c->sendPptr.assign(P->sendPptr, P->sendPptr + np + 1);
+      c->recvVoff.assign(P->recvVoff, P->recvVoff + np); c->recvVcnt.assign(P->recvVcnt, P->recvVcnt + np);
+      c->recvPoff.assign(P->recvPoff, P->recvPoff + np); c->recvPcnt.assign(P->recvPcnt, P->recvPcnt + np);
+      const int nsV = c->sendVptr[np], nsP = c->sendPptr[np];
+      // device copies: idx, segment-of-entry, ptr  (velocity plan then pressure plan)
+      std::vector<int> segV(nsV), segP(nsP);
+      for (int j = 0; j < np; j++) {
+         for (int k = c->sendVptr[j]; k < c->sendVptr[j + 1]; k++) segV[k] = j;
+         for (int k = c->sendPptr[j]; k < c->sendPptr[j + 1]; k++) segP[k] = j;
+      }
+      std::vector<int> packV, packP;
+      packV.insert(packV.end(), P->sendVidx, P->sendVidx + nsV); packV.insert(packV.end(), segV.begin(), segV.end());
+      packV.insert(packV.end(), c->sendVptr.begin(), c->sendVptr.end());
+      packP.insert(packP.end(), P->sendPidx, P->sendPidx + nsP); packP.insert(packP.end(), segP.begin(), segP.end());
+      packP.insert(packP.end(), c->sendPptr.begin(), c->sendPptr.end());
+      TRY(dupload(c, &c->sendVidx, packV.data(), packV.size()));
+      TRY(dupload(c, &c->sendPidx, packP.data(), packP.size()));
+      TRY(dalloc(c, &c->sendBuf, (size_t)std::max(3 * nsV, nsP) + 1));
+      TRY(dalloc(c, &c->dacc, 64));
    }
    // ---- cooperative launch geometry: persistent kernels, a whole number of CTAs per SM
    {
@@ -1284,6 +1476,29 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    c->P.MdInv = c->P.MdOrigInv = nullptr; c->P.BCvelNodes = nullptr; c->P.BCstr = nullptr; c->P.U0 = c->P.P0 = nullptr;
    CFD_CK(cudaDeviceSynchronize());
    *out = c;
+   return CFD_OK;
+}
+
+int cfd_nccl_unique_id(char out[128]) {
+   Comm tmp;
+   if (!nccl_load(tmp)) return CFD_ERR_NCCL;
+   NcclUniqueId id;
+   CFD_NCCL(&tmp, tmp.GetUniqueId(&id));
+   memcpy(out, id.internal, 128);
+   return CFD_OK;
+}
+
+int cfd_comm_init(cfd_ctx* c, const char id[128]) {
+   if (!c || !id) return CFD_ERR_ARG;
+   if (c->P.world <= 1) return CFD_OK;
+   if (!c->comm) c->comm = new Comm();
+   if (!nccl_load(*c->comm)) return CFD_ERR_NCCL;
+   c->comm->world = c->P.world; c->comm->rank = c->P.rank;
+   NcclUniqueId uid;
+   memcpy(uid.internal, id, 128);
+   CFD_CK(cudaSetDevice(c->device));
+   CFD_NCCL(c->comm, c->comm->CommInitRank(&c->comm->comm, c->P.world, uid, c->P.rank));
+   // initial halo of the state vectors (the host supplied owned + ghost values, but be safe)
    return CFD_OK;
 }
 
@@ -1348,7 +1563,7 @@ int bch_step1GPUpart(cfd_ctx* c, int /*iter*/) {
                                                                                 c->bcIndex, c->R1, c->UnpHalf, c->P.dt);
    c->launches++;
    CFD_CK(cudaGetLastError());
-   return CFD_OK;
+   return halo(c, c->UnpHalf, true);   // gathered by step 2 (G^T) and, as UnpHalf_prev, by the next inner iteration
 }
 
 int bch_step2GPU(cfd_ctx* c, int iter) {
@@ -1357,7 +1572,7 @@ int bch_step2GPU(cfd_ctx* c, int iter) {
    {
       ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
       k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 0, c->UnpHalf, c->KtimesAcc_prev, iter != 1,
-                                                                                    c->MdOrigInv, 1.0 / (dt * dt), c->P.zeroPressureNode, c->R2);
+                                                                                    c->MdOrigInv, 1.0 / (dt * dt), c->pin, c->R2);
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
@@ -1366,11 +1581,12 @@ int bch_step2GPU(cfd_ctx* c, int iter) {
    {
       ProfScope ps(c, "update", 40.0 * NNp);
       CFD_CK(cudaMemsetAsync(c->scal, 0, 4 * sizeof(double), c->stream));
-      k_pressure_update<<<std::min(gridFor(NNp, 256), 4 * c->numSMs), 256, 0, c->stream>>>(NNp, c->Pn, c->Pdot, c->Pnp1_prev, c->Pnp1, dt, c->scal);
+      k_pressure_update<<<std::min(gridFor(c->NPo, 256), 4 * c->numSMs), 256, 0, c->stream>>>(c->NPo, c->Pn, c->Pdot, c->Pnp1_prev, c->Pnp1, dt, c->scal);
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
-   return CFD_OK;
+   if ((rc = halo(c, c->Pdot, false))) return rc;    // gathered by step 3 (G Pdot)
+   return halo(c, c->Pnp1, false);                     // becomes Pn, gathered by step 1 (G Pn)
 }
 
 int bch_step3GPU(cfd_ctx* c, int iter) {
@@ -1380,10 +1596,14 @@ int bch_step3GPU(cfd_ctx* c, int iter) {
                                                                                 c->UnpHalf, c->Unp1_prev, c->R3, c->Acc, c->Unp1, c->P.dt, c->scal);
    c->launches++;
    CFD_CK(cudaGetLastError());
-   return CFD_OK;
+   int rc = halo(c, c->Acc, true);        // gathered by K * Acc_prev
+   if (rc) return rc;
+   return halo(c, c->Unp1, true);          // becomes Un, gathered by the next step's operators
 }
 
 int bch_checkConvergenceGPU(cfd_ctx* c, int* converged) {
+   int rca = allreduce(c, c->scal, 4, kNcclSum);
+   if (rca) return rca;
    CFD_CK(cudaMemcpyAsync(c->h_pinned, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    int rc = fetch_kinfo(c);
    if (rc) return rc;
@@ -1409,7 +1629,7 @@ int bch_calculate_KtimesAcc_prevGPU(cfd_ctx* c) {
    k_spmv_multi<3><<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, 0, c->Acc_prev, NN, c->KtimesAcc_prev, NN, 1.0, 0.0);
    c->launches++;
    CFD_CK(cudaGetLastError());
-   return CFD_OK;
+   return halo(c, c->KtimesAcc_prev, true);   // gathered by step 2 (G^T)
 }
 
 static int max_acc(cfd_ctx* c, const double* a, const double* b, int* steady, double* maxAcc) {
@@ -1417,9 +1637,13 @@ static int max_acc(cfd_ctx* c, const double* a, const double* b, int* steady, do
    {
       ProfScope ps(c, "update", 16.0 * N3);
       CFD_CK(cudaMemsetAsync(c->scal + 4, 0, sizeof(double), c->stream));
-      k_max_abs_diff<<<std::min(gridFor(N3, 256), 8 * c->numSMs), 256, 0, c->stream>>>(N3, a, b, c->scal + 4);
+      k_max_abs_diff3<<<std::min(gridFor(c->NNo, 256), 8 * c->numSMs), 256, 0, c->stream>>>(c->NNo, c->P.NN, a, b, c->scal + 4);
       c->launches++;
       CFD_CK(cudaGetLastError());
+   }
+   {
+      int rca = allreduce(c, c->scal + 4, 1, kNcclMax);
+      if (rca) return rca;
    }
    CFD_CK(cudaMemcpyAsync(c->h_pinned + 8, c->scal + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    CFD_CK(cudaStreamSynchronize(c->stream));
@@ -1463,7 +1687,7 @@ int gq_step1GPU(cfd_ctx* c) {
          k_bc_rows_identity<<<gridFor(c->P.BCnVelNodes, 128), 128, 0, c->stream>>>(c->K, 2, c->P.BCnVelNodes, c->bcNodes);
          c->launches++;
       }
-      k_extract_dinv<<<gridFor(NN, 256), 256, 0, c->stream>>>(NN, c->K.vals[2], c->diagPosA, c->Adinv);
+      k_extract_dinv<<<gridFor(c->NNo, 256), 256, 0, c->stream>>>(c->NNo, c->K.vals[2], c->diagPosA, c->Adinv);
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
@@ -1473,6 +1697,11 @@ int gq_step1GPU(cfd_ctx* c) {
                                                                                    c->bcIndex, c->BCstr, c->R1i);
       c->launches++;
       CFD_CK(cudaGetLastError());
+   }
+   if (parted(c)) {
+      int rcd = run_bicg_dist(c);
+      if (rcd) return rcd;
+      return halo(c, c->Uk, true);   // gathered by step 2 (G^T Uk) and, as Uk_prev, by the next step
    }
    {
       BicgArgs a;
@@ -1492,7 +1721,7 @@ int gq_step2GPU(cfd_ctx* c) {
    {
       ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
       k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 1, c->Uk, nullptr, 0, nullptr, -1.0 / c->P.dt,
-                                                                                    c->P.zeroPressureNode, c->R2);
+                                                                                    c->pin, c->R2);
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
@@ -1500,11 +1729,11 @@ int gq_step2GPU(cfd_ctx* c) {
    if (rc) return rc;
    {
       ProfScope ps(c, "update", 24.0 * NNp);
-      k_add<<<std::min(gridFor(NNp, 256), 4 * c->numSMs), 256, 0, c->stream>>>(NNp, c->Pk_prev, c->Pdiff, c->Pk);   // calculate_Pk, GQ.cu:554-565
+      k_add<<<std::min(gridFor(c->NPo, 256), 4 * c->numSMs), 256, 0, c->stream>>>(c->NPo, c->Pk_prev, c->Pdiff, c->Pk);   // calculate_Pk, GQ.cu:554-565
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
-   return CFD_OK;
+   return halo(c, c->Pk, false);   // gathered by the next step's right-hand sides
 }
 
 int gq_checkConvergenceInTimeGPU(cfd_ctx* c, int* steady, double* maxAcc) { return max_acc(c, c->Uk, c->Uk_prev, steady, maxAcc); }
@@ -1526,6 +1755,16 @@ int cfd_printMonitorDataGPU(cfd_ctx* c, double out[4]) {
    CFD_CK(cudaMemcpyAsync(c->h_pinned + 35, Pp + m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    CFD_CK(cudaStreamSynchronize(c->stream));
    for (int d = 0; d < 4; d++) out[d] = c->h_pinned[32 + d];
+   if (parted(c)) {   // the owner of the monitor node reports, the others contribute zeros
+      double v[4];
+      for (int d = 0; d < 4; d++) v[d] = c->monOwned ? out[d] : 0.0;
+      CFD_CK(cudaMemcpyAsync(c->dacc + 60, v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+      int rca = allreduce(c, c->dacc + 60, 4, kNcclSum);
+      if (rca) return rca;
+      CFD_CK(cudaMemcpyAsync(c->h_pinned + 32, c->dacc + 60, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+      CFD_CK(cudaStreamSynchronize(c->stream));
+      for (int d = 0; d < 4; d++) out[d] = c->h_pinned[32 + d];
+   }
    return CFD_OK;
 }
 

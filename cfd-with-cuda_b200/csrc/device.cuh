@@ -54,6 +54,8 @@ void sell_build_host(int nrows, int ncols, const int* rowStarts, const int* col,
 int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell& dev);
 void sell_free(Sell& s);
 
+struct Comm;   // NCCL communicator wrapper (dist.cuh)
+
 // per kernel-class profile (CUDA events on the context stream)
 struct ProfEntry {
    double ms = 0;
@@ -119,4 +121,13 @@ struct cfd_ctx {
    bool ownStream = true;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    std::vector<void*> allocs;
+   // ---- partition (multi-GPU).  NN / NNp in P are LOCAL counts (owned + ghost); rows = owned.
+   int NNo = 0, NPo = 0, NEa = 0;
+   int pin = -1;                    // pressure DOF to pin (local), -1 = none
+   bool monOwned = true;
+   cfdb::Comm* comm = nullptr;      // NCCL communicator (world > 1)
+   std::vector<int> peerRank, sendVptr, recvVoff, recvVcnt, sendPptr, recvPoff, recvPcnt;
+   int *sendVidx = nullptr, *sendPidx = nullptr;   // device
+   double* sendBuf = nullptr;                        // device staging for packed interface values
+   double* dacc = nullptr;                           // device: distributed-Krylov accumulators + state
 };

@@ -30,6 +30,9 @@ struct Mesh {
    std::vector<int> BCvelNodes;   // [i][2]
    int BCnVelNodes = 0;
    int monPoint = 0;
+   // Partitioned (multi-GPU) sub-meshes number their pressure DOFs separately from the nodes (owned first):
+   // presIndex[node] = pressure DOF of a corner node, -1 otherwise.  Empty = identity (the reference's convention).
+   std::vector<int> presIndex;
    std::vector<int> meshColors, NmeshColors, elementsOfColor;   // setupMeshColoring (kept for API parity; kernels use atomics)
    int nActiveColors = 0;
 };
@@ -53,9 +56,31 @@ void generate_midnodes(Mesh& m);
 void find_bc_nodes(Mesh& m);
 void find_monitor(Mesh& m);
 void color_mesh(Mesh& m);
-void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map);
+void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map,
+                   const std::vector<int>* rowIndex = nullptr, const std::vector<int>* colIndex = nullptr);
 void assemble_step0(const Mesh& m, int scheme, Assembled& A);
 bool write_tecplot(const Mesh& m, const double* U, const double* P, const std::string& path, const std::string& title);
 bool read_restart(const Mesh& m, const std::string& path, double* U, double* P);
+
+// ---- element-block partition for multi-GPU runs -------------------------------------
+struct PeerPlan {
+   int rank = 0;
+   std::vector<int> sendV, sendP;   // my OWNED local velocity-node / pressure-DOF indices the peer holds as ghosts
+   int recvVoff = 0, recvVcnt = 0;  // my ghost range [off, off+cnt) filled by this peer (velocity nodes)
+   int recvPoff = 0, recvPcnt = 0;  // same for pressure DOFs
+};
+struct Partition {
+   int rank = 0, world = 1;
+   int NEa = 0;                     // local elements that touch an owned node (the EBE kernels loop over these)
+   int NNo = 0, NPo = 0;            // owned velocity nodes / pressure DOFs (numbered first)
+   std::vector<int> elemGlobal;     // local element -> global element
+   std::vector<int> nodeGlobal;     // local node -> global node
+   std::vector<int> presGlobal;     // local pressure DOF -> global corner node
+   std::vector<PeerPlan> peers;
+   int pinLocal = -1;               // local pressure DOF of the pinned node (reference rule: global id > 0), -1 if absent
+   int monLocal = -1;               // local node of the monitor point if owned here, else -1
+};
+// Extracts rank's sub-mesh (own elements + `layers` halo layers) from the global mesh with generated nodes.
+void partition_mesh(const Mesh& global, int world, int rank, int layers, Mesh& local, Partition& part);
 
 }   // namespace cfdb

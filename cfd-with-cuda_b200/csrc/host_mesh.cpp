@@ -354,32 +354,39 @@ void color_mesh(Mesh& m) {
 // CSR pattern of (row nodes = first nRowLoc local nodes) x (column nodes = first nColLoc local nodes)
 // with ascending columns, plus the [e][i][j] -> CSR position map (setupSparseM / setupSparseG,
 // blascoCodinaHuerta.cpp:1675-2159; setupSparseZGPU, guermondQuartapelle.cpp:2418-2647).
-void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map) {
+void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map,
+                   const std::vector<int>* rowIndex, const std::vector<int>* colIndex) {
    const int NE = m.NE, nv = m.NENv;
+   auto R = [&](int node) { return rowIndex ? (*rowIndex)[node] : node; };
+   auto C = [&](int node) { return colIndex ? (*colIndex)[node] : node; };
    std::vector<int> start((size_t)nrows + 1, 0), items((size_t)NE * nRowLoc);
    for (int e = 0; e < NE; e++)
-      for (int i = 0; i < nRowLoc; i++) start[m.LtoGnode[(size_t)e * nv + i] + 1]++;
+      for (int i = 0; i < nRowLoc; i++) start[R(m.LtoGnode[(size_t)e * nv + i]) + 1]++;
    for (int i = 0; i < nrows; i++) start[i + 1] += start[i];
    {
       std::vector<int> fill(start.begin(), start.end() - 1);
       for (int e = 0; e < NE; e++)
-         for (int i = 0; i < nRowLoc; i++) items[fill[m.LtoGnode[(size_t)e * nv + i]]++] = e;
+         for (int i = 0; i < nRowLoc; i++) items[fill[R(m.LtoGnode[(size_t)e * nv + i])]++] = e;
    }
    P.nrows = nrows; P.ncols = ncols;
    P.rowStarts.assign((size_t)nrows + 1, 0);
    std::vector<int> cnt(nrows, 0);
+   auto gather = [&](int r, std::vector<int>& tmp) {
+      tmp.clear();
+      for (int t = start[r]; t < start[r + 1]; t++) {
+         const int* L = &m.LtoGnode[(size_t)items[t] * nv];
+         for (int j = 0; j < nColLoc; j++) tmp.push_back(C(L[j]));
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+   };
 #pragma omp parallel
    {
       std::vector<int> tmp;
 #pragma omp for schedule(static)
       for (int r = 0; r < nrows; r++) {
-         tmp.clear();
-         for (int t = start[r]; t < start[r + 1]; t++) {
-            const int* L = &m.LtoGnode[(size_t)items[t] * nv];
-            tmp.insert(tmp.end(), L, L + nColLoc);
-         }
-         std::sort(tmp.begin(), tmp.end());
-         cnt[r] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+         gather(r, tmp);
+         cnt[r] = (int)tmp.size();
       }
    }
    for (int r = 0; r < nrows; r++) P.rowStarts[r + 1] = P.rowStarts[r] + cnt[r];
@@ -389,13 +396,7 @@ void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols
       std::vector<int> tmp;
 #pragma omp for schedule(static)
       for (int r = 0; r < nrows; r++) {
-         tmp.clear();
-         for (int t = start[r]; t < start[r + 1]; t++) {
-            const int* L = &m.LtoGnode[(size_t)items[t] * nv];
-            tmp.insert(tmp.end(), L, L + nColLoc);
-         }
-         std::sort(tmp.begin(), tmp.end());
-         tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+         gather(r, tmp);
          std::copy(tmp.begin(), tmp.end(), P.col.begin() + P.rowStarts[r]);
       }
    }
@@ -405,13 +406,152 @@ void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols
       for (int e = 0; e < NE; e++) {
          const int* L = &m.LtoGnode[(size_t)e * nv];
          for (int i = 0; i < nRowLoc; i++) {
-            const int* b = P.col.data() + P.rowStarts[L[i]];
-            const int* en = P.col.data() + P.rowStarts[L[i] + 1];
+            const int r = R(L[i]);
+            const int* b = P.col.data() + P.rowStarts[r];
+            const int* en = P.col.data() + P.rowStarts[r + 1];
             for (int j = 0; j < nColLoc; j++)
-               (*map)[((size_t)e * nRowLoc + i) * nColLoc + j] = (int)(std::lower_bound(b, en, L[j]) - P.col.data());
+               (*map)[((size_t)e * nRowLoc + i) * nColLoc + j] = (int)(std::lower_bound(b, en, C(L[j])) - P.col.data());
          }
       }
    }
+}
+
+// Element-block partition: rank r owns the contiguous element range [r*NE/world, (r+1)*NE/world) (z-slabs on
+// the generators' x-fastest numbering) and every node whose lowest-ranked touching element it owns.  Its
+// sub-mesh holds all elements within `layers` element layers of an owned node, so that every owned ROW of
+// every operator (and, with 2 layers, of Z = G^T Md^-1 G) is assembled completely from local data.  All ranks
+// derive the same plan from the same global mesh, so no set-up communication is needed.
+void partition_mesh(const Mesh& g, int world, int rank, int layers, Mesh& loc, Partition& part) {
+   const int NE = g.NE, nv = g.NENv, NN = g.NN;
+   auto eOwner = [&](int e) { return (int)(((long long)e * world) / NE); };
+   // rank r owns element e iff eOwner(e) == r  (monotone, contiguous)
+   std::vector<int> nOwner((size_t)NN, world);
+   for (int e = 0; e < NE; e++) {
+      const int o = eOwner(e);
+      const int* L = &g.LtoGnode[(size_t)e * nv];
+      for (int i = 0; i < nv; i++) nOwner[L[i]] = std::min(nOwner[L[i]], o);
+   }
+   typedef unsigned long long mask_t;
+   // ranks whose sub-mesh contains element e, grown layer by layer
+   std::vector<mask_t> eMask((size_t)NE, 0), nMask((size_t)NN, 0);
+   for (int e = 0; e < NE; e++) {
+      const int* L = &g.LtoGnode[(size_t)e * nv];
+      mask_t mk = 0;
+      for (int i = 0; i < nv; i++) mk |= (mask_t)1 << nOwner[L[i]];
+      eMask[e] = mk;
+   }
+   std::vector<mask_t> eMaskA = eMask;   // layer 1: elements touching an owned node
+   for (int l = 1; l < layers; l++) {
+      std::fill(nMask.begin(), nMask.end(), 0);
+      for (int e = 0; e < NE; e++) {
+         const int* L = &g.LtoGnode[(size_t)e * nv];
+         for (int i = 0; i < nv; i++) nMask[L[i]] |= eMask[e];
+      }
+      for (int e = 0; e < NE; e++) {
+         const int* L = &g.LtoGnode[(size_t)e * nv];
+         mask_t mk = eMask[e];
+         for (int i = 0; i < nv; i++) mk |= nMask[L[i]];
+         eMask[e] = mk;
+      }
+   }
+   std::fill(nMask.begin(), nMask.end(), 0);   // ranks that hold node n (owned or ghost)
+   for (int e = 0; e < NE; e++) {
+      const int* L = &g.LtoGnode[(size_t)e * nv];
+      for (int i = 0; i < nv; i++) nMask[L[i]] |= eMask[e];
+   }
+   const mask_t me = (mask_t)1 << rank;
+   part = Partition();
+   part.rank = rank; part.world = world;
+   // ---- local elements: those touching an owned node first (EBE range), then the outer layer(s)
+   for (int e = 0; e < NE; e++)
+      if (eMaskA[e] & me) part.elemGlobal.push_back(e);
+   part.NEa = (int)part.elemGlobal.size();
+   for (int e = 0; e < NE; e++)
+      if ((eMask[e] & me) && !(eMaskA[e] & me)) part.elemGlobal.push_back(e);
+   const int NEl = (int)part.elemGlobal.size();
+   // ---- local nodes: owned (ascending global id), then ghosts grouped by owner (ascending global id inside)
+   std::vector<std::vector<int> > ghostsOf(world);
+   for (int n = 0; n < NN; n++) {
+      if (!(nMask[n] & me)) continue;
+      if (nOwner[n] == rank) part.nodeGlobal.push_back(n);
+      else ghostsOf[nOwner[n]].push_back(n);
+   }
+   part.NNo = (int)part.nodeGlobal.size();
+   std::vector<int> g2l((size_t)NN, -1);
+   for (int q = 0; q < world; q++) {
+      if (ghostsOf[q].empty()) continue;
+      PeerPlan pp;
+      pp.rank = q;
+      pp.recvVoff = (int)part.nodeGlobal.size();
+      pp.recvVcnt = (int)ghostsOf[q].size();
+      part.nodeGlobal.insert(part.nodeGlobal.end(), ghostsOf[q].begin(), ghostsOf[q].end());
+      part.peers.push_back(pp);
+   }
+   const int NNl = (int)part.nodeGlobal.size();
+   for (int i = 0; i < NNl; i++) g2l[part.nodeGlobal[i]] = i;
+   // ---- pressure DOFs = corner nodes (global id < NCN), same ordering rule
+   std::vector<int> presLocalOfNode((size_t)NNl, -1);
+   for (int i = 0; i < part.NNo; i++)
+      if (part.nodeGlobal[i] < g.NCN) { presLocalOfNode[i] = (int)part.presGlobal.size(); part.presGlobal.push_back(part.nodeGlobal[i]); }
+   part.NPo = (int)part.presGlobal.size();
+   for (PeerPlan& pp : part.peers) {
+      pp.recvPoff = (int)part.presGlobal.size();
+      for (int i = pp.recvVoff; i < pp.recvVoff + pp.recvVcnt; i++)
+         if (part.nodeGlobal[i] < g.NCN) { presLocalOfNode[i] = (int)part.presGlobal.size(); part.presGlobal.push_back(part.nodeGlobal[i]); }
+      pp.recvPcnt = (int)part.presGlobal.size() - pp.recvPoff;
+   }
+   // ---- what I send: my owned nodes that rank q holds, ascending global id (= q's ghost order for owner me)
+   auto peerOf = [&](int q) -> PeerPlan& {
+      for (PeerPlan& pp : part.peers)
+         if (pp.rank == q) return pp;
+      PeerPlan pp;
+      pp.rank = q;
+      pp.recvVoff = NNl; pp.recvPoff = (int)part.presGlobal.size();
+      part.peers.push_back(pp);
+      return part.peers.back();
+   };
+   for (int i = 0; i < part.NNo; i++) {
+      const int n = part.nodeGlobal[i];
+      mask_t others = nMask[n] & ~me;
+      while (others) {
+         const int q = __builtin_ctzll(others);
+         others &= others - 1;
+         PeerPlan& pp = peerOf(q);
+         pp.sendV.push_back(i);
+         if (n < g.NCN) pp.sendP.push_back(presLocalOfNode[i]);
+      }
+   }
+   std::sort(part.peers.begin(), part.peers.end(), [](const PeerPlan& a, const PeerPlan& b) { return a.rank < b.rank; });
+   // ---- the local mesh
+   loc = Mesh();
+   loc.eType = g.eType; loc.NENv = nv; loc.NENp = g.NENp; loc.NGP = g.NGP;
+   loc.alpha = g.alpha; loc.dt = g.dt; loc.t_ini = g.t_ini; loc.t_final = g.t_final; loc.maxIter = g.maxIter;
+   loc.tolerance = g.tolerance; loc.converge = g.converge; loc.isRestart = g.isRestart; loc.density = g.density;
+   loc.viscosity = g.viscosity; loc.fx = g.fx; loc.fy = g.fy;
+   loc.NE = NEl; loc.NN = NNl; loc.NNp = (int)part.presGlobal.size(); loc.NCN = loc.NNp;
+   loc.coord.resize((size_t)NNl * 3);
+   for (int i = 0; i < NNl; i++)
+      for (int d = 0; d < 3; d++) loc.coord[3 * (size_t)i + d] = g.coord[3 * (size_t)part.nodeGlobal[i] + d];
+   loc.LtoGnode.resize((size_t)NEl * nv);
+   std::vector<int> e2l((size_t)NE, -1);
+   for (int el = 0; el < NEl; el++) {
+      const int e = part.elemGlobal[el];
+      e2l[e] = el;
+      for (int i = 0; i < nv; i++) loc.LtoGnode[(size_t)el * nv + i] = g2l[g.LtoGnode[(size_t)e * nv + i]];
+   }
+   loc.presIndex = presLocalOfNode;
+   loc.nBC = g.nBC; loc.BCtype = g.BCtype; loc.BCstr = g.BCstr;
+   for (size_t f = 0; f < g.velFaces.size() / 3; f++) {   // file order kept: later faces still win
+      const int el = e2l[g.velFaces[3 * f]];
+      if (el >= 0) { loc.velFaces.push_back(el); loc.velFaces.push_back(g.velFaces[3 * f + 1]); loc.velFaces.push_back(g.velFaces[3 * f + 2]); }
+   }
+   find_bc_nodes(loc);
+   const int pin = g.zeroPressureNode;
+   part.pinLocal = (pin > 0 && g2l[pin] >= 0) ? presLocalOfNode[g2l[pin]] : -1;
+   loc.zeroPressureNode = part.pinLocal;
+   part.monLocal = (g2l[g.monPoint] >= 0 && g2l[g.monPoint] < part.NNo) ? g2l[g.monPoint] : -1;
+   loc.monPoint = std::max(part.monLocal, 0);
+   for (int d = 0; d < 3; d++) loc.monCoord[d] = g.monCoord[d];
 }
 
 }   // namespace cfdb

@@ -79,15 +79,16 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
    const int NE = m.NE, nv = m.NENv, NN = m.NN, NNp = m.NNp;
    FeTables T;
    build_fe_tables(nv, T);
-   build_pattern(m, nv, nv, NN, NN, A.Mp, scheme == CFD_IMPLICIT ? &A.mapM : &A.mapM);
-   build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG);
+   const std::vector<int>* pidx = m.presIndex.empty() ? nullptr : &m.presIndex;
+   build_pattern(m, nv, nv, NN, NN, A.Mp, &A.mapM);
+   build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG, nullptr, pidx);
    const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp.nnz();
    A.Mval.assign(nnzM, 0.0); A.Kval.assign(nnzM, 0.0);
    A.G1.assign(nnzG, 0.0); A.G2.assign(nnzG, 0.0); A.G3.assign(nnzG, 0.0);
    const double invDens = 1.0 / m.density;
    const double mscale = scheme == CFD_IMPLICIT ? 1.0 / m.dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
    if (scheme == CFD_IMPLICIT) {
-      build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ);
+      build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ, pidx, pidx);
       A.Zval.assign((size_t)A.Zp.nnz(), 0.0);
    }
 #pragma omp parallel
@@ -195,8 +196,9 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
       }
    }
    // pressure pin: diagonal * 1000, only for node > 0 (applyBC_Step2(1), BCH.cpp:4167-4180)
-   const int pin = m.zeroPressureNode;
-   if (pin > 0)
+   // (a partitioned sub-mesh carries the rule already applied: local DOF or -1)
+   const int pin = m.presIndex.empty() ? (m.zeroPressureNode > 0 ? m.zeroPressureNode : -1) : m.zeroPressureNode;
+   if (pin >= 0)
       for (int k = A.Zp.rowStarts[pin]; k < A.Zp.rowStarts[pin + 1]; k++)
          if (A.Zp.col[k] == pin) { A.Zval[k] *= 1000.0; break; }
 }
@@ -275,7 +277,11 @@ bool read_restart(const Mesh& m, const std::string& path, double* U, double* P) 
 using namespace cfdb;
 
 struct cfd_solver {
-   Mesh mesh;
+   Mesh mesh;          // the mesh this process computes on (the whole mesh, or its partition's sub-mesh)
+   Partition part;
+   bool partitioned = false;
+   int globalNN = 0, globalNNp = 0, globalNE = 0;
+   std::vector<int> peerRank, sendVptr, sendVidx, recvVoff, recvVcnt, sendPptr, sendPidx, recvPoff, recvPcnt;
    Assembled A;
    cfd_problem prob;
    cfd_options opt;
@@ -293,13 +299,24 @@ double now_s() {
    return tv.tv_sec + 1e-6 * tv.tv_usec;
 }
 
-int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::string& restartPath, int init_gpu) {
-   Mesh& m = s->mesh;
+int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::string& restartPath, int init_gpu, int world = 1,
+                  int rank = 0) {
    s->scheme = scheme;
    if (opt) s->opt = *opt; else cfd_default_options(&s->opt);
-   generate_midnodes(m);
-   find_bc_nodes(m);
-   find_monitor(m);
+   generate_midnodes(s->mesh);
+   find_bc_nodes(s->mesh);
+   find_monitor(s->mesh);
+   s->globalNN = s->mesh.NN; s->globalNNp = s->mesh.NNp; s->globalNE = s->mesh.NE;
+   if (world > 1) {
+      if (world > 64 || rank < 0 || rank >= world) { set_error("bad partition %d/%d", rank, world); return CFD_ERR_ARG; }
+      if (s->mesh.isRestart == 1) { set_error("restart files are not supported on partitioned runs"); return CFD_ERR_ARG; }
+      Mesh local;
+      // explicit: rows of Z = G^T Md^-1 G reach two element layers; implicit: one
+      partition_mesh(s->mesh, world, rank, scheme == CFD_EXPLICIT ? 2 : 1, local, s->part);
+      s->mesh = std::move(local);
+      s->partitioned = true;
+   }
+   Mesh& m = s->mesh;
    assemble_step0(m, scheme, s->A);
    cfd_problem& P = s->prob;
    memset(&P, 0, sizeof P);
@@ -318,6 +335,26 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    P.MdOrigInv = s->A.MdOrigInv.empty() ? nullptr : s->A.MdOrigInv.data();
    P.BCnVelNodes = m.BCnVelNodes; P.BCvelNodes = m.BCvelNodes.data(); P.nBC = m.nBC; P.BCstr = m.BCstr.data();
    P.zeroPressureNode = m.zeroPressureNode; P.monPoint = m.monPoint;
+   if (s->partitioned) {
+      const Partition& pt = s->part;
+      P.world = pt.world; P.rank = pt.rank; P.NN_owned = pt.NNo; P.NNp_owned = pt.NPo; P.NE_apply = pt.NEa;
+      P.pinLocal = pt.pinLocal; P.monOwned = pt.monLocal >= 0 ? 1 : 0;
+      s->sendVptr.assign(1, 0); s->sendPptr.assign(1, 0);
+      for (const PeerPlan& pp : pt.peers) {
+         s->peerRank.push_back(pp.rank);
+         s->sendVidx.insert(s->sendVidx.end(), pp.sendV.begin(), pp.sendV.end());
+         s->sendVptr.push_back((int)s->sendVidx.size());
+         s->sendPidx.insert(s->sendPidx.end(), pp.sendP.begin(), pp.sendP.end());
+         s->sendPptr.push_back((int)s->sendPidx.size());
+         s->recvVoff.push_back(pp.recvVoff); s->recvVcnt.push_back(pp.recvVcnt);
+         s->recvPoff.push_back(pp.recvPoff); s->recvPcnt.push_back(pp.recvPcnt);
+      }
+      P.nPeers = (int)pt.peers.size();
+      P.peerRank = s->peerRank.data(); P.sendVptr = s->sendVptr.data(); P.sendVidx = s->sendVidx.data();
+      P.recvVoff = s->recvVoff.data(); P.recvVcnt = s->recvVcnt.data();
+      P.sendPptr = s->sendPptr.data(); P.sendPidx = s->sendPidx.data();
+      P.recvPoff = s->recvPoff.data(); P.recvPcnt = s->recvPcnt.data();
+   }
    if (m.isRestart == 1 && !restartPath.empty()) {
       s->U0.assign((size_t)3 * m.NN, 0.0); s->P0.assign((size_t)m.NNp, 0.0);
       if (!read_restart(m, restartPath, s->U0.data(), s->P0.data())) return CFD_ERR_IO;
@@ -361,6 +398,32 @@ int cfd_solver_create_cavity(int nx, int ny, int nz, double cluster, int NENv, i
    return CFD_OK;
 }
 
+int cfd_solver_create_from_inp_part(const char* inp_path, int scheme, const cfd_options* opt, int init_gpu, int world, int rank,
+                                    cfd_solver** out) {
+   if (!inp_path || !out) { set_error("null argument"); return CFD_ERR_ARG; }
+   *out = nullptr;
+   cfd_solver* s = new cfd_solver();
+   if (!read_inp(inp_path, s->mesh)) { delete s; return CFD_ERR_IO; }
+   int rc = finish_create(s, scheme, opt, "", init_gpu, world, rank);
+   if (rc) { delete s; return rc; }
+   *out = s;
+   return CFD_OK;
+}
+
+int cfd_solver_create_cavity_part(int nx, int ny, int nz, double cluster, int NENv, int scheme, double dt, double viscosity, int maxIter,
+                                  double tolerance, const cfd_options* opt, int init_gpu, int world, int rank, cfd_solver** out) {
+   if (!out || nx < 1 || ny < 1 || nz < 1 || (NENv != 8 && NENv != 27)) { set_error("bad cavity arguments"); return CFD_ERR_ARG; }
+   *out = nullptr;
+   cfd_solver* s = new cfd_solver();
+   make_cavity(nx, ny, nz, cluster, NENv, s->mesh);
+   s->mesh.dt = dt; s->mesh.viscosity = viscosity; s->mesh.maxIter = maxIter; s->mesh.tolerance = tolerance;
+   s->mesh.converge = 1e-6; s->mesh.t_final = 1e30; s->mesh.density = 1.0;
+   int rc = finish_create(s, scheme, opt, "", init_gpu, world, rank);
+   if (rc) { delete s; return rc; }
+   *out = s;
+   return CFD_OK;
+}
+
 int cfd_solver_init_gpu(cfd_solver* s) {
    if (!s) return CFD_ERR_ARG;
    if (s->ctx) return CFD_OK;
@@ -379,6 +442,11 @@ long long cfd_solver_int(cfd_solver* s, const char* name) {
    const std::string n(name);
    const Mesh& m = s->mesh;
    if (n == "NE") return m.NE; if (n == "NCN") return m.NCN; if (n == "NN") return m.NN; if (n == "NNp") return m.NNp;
+   if (n == "globalNN") return s->globalNN; if (n == "globalNNp") return s->globalNNp; if (n == "globalNE") return s->globalNE;
+   if (n == "NN_owned") return s->partitioned ? s->part.NNo : m.NN; if (n == "NNp_owned") return s->partitioned ? s->part.NPo : m.NNp;
+   if (n == "NE_apply") return s->partitioned ? s->part.NEa : m.NE; if (n == "nPeers") return (long long)s->part.peers.size();
+   if (n == "pinLocal") return s->partitioned ? s->part.pinLocal : (m.zeroPressureNode > 0 ? m.zeroPressureNode : -1);
+   if (n == "monLocal") return s->partitioned ? s->part.monLocal : m.monPoint;
    if (n == "NENv") return m.NENv; if (n == "nnzM") return s->A.Mp.nnz(); if (n == "nnzG") return s->A.Gp.nnz();
    if (n == "nnzZ") return s->A.Zp.nnz(); if (n == "BCnVelNodes") return m.BCnVelNodes; if (n == "monPoint") return m.monPoint;
    if (n == "zeroPressureNode") return m.zeroPressureNode; if (n == "maxIter") return m.maxIter; if (n == "isRestart") return m.isRestart;
@@ -392,6 +460,9 @@ const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, 
    Assembled& A = s->A;
 #define DV(nm, v) if (n == nm) { *count = (long long)(v).size(); *is_int = 0; return (v).data(); }
 #define IV(nm, v) if (n == nm) { *count = (long long)(v).size(); *is_int = 1; return (v).data(); }
+   IV("part_nodeGlobal", s->part.nodeGlobal) IV("part_presGlobal", s->part.presGlobal) IV("part_elemGlobal", s->part.elemGlobal)
+   IV("peerRank", s->peerRank) IV("sendVptr", s->sendVptr) IV("sendVidx", s->sendVidx) IV("recvVoff", s->recvVoff) IV("recvVcnt", s->recvVcnt)
+   IV("sendPptr", s->sendPptr) IV("sendPidx", s->sendPidx) IV("recvPoff", s->recvPoff) IV("recvPcnt", s->recvPcnt)
    DV("coord", m.coord) IV("LtoGnode", m.LtoGnode) IV("BCvelNodes", m.BCvelNodes) DV("BCstr", m.BCstr)
    IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp.rowStarts) IV("sparseGcol", A.Gp.col)
    IV("sparseZrowStarts", A.Zp.rowStarts) IV("sparseZcol", A.Zp.col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG)

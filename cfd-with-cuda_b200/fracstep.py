@@ -42,6 +42,10 @@ class cfd_problem(C.Structure):
         ("sparseMapM_1d", _ip), ("MdInv", _dp), ("MdOrigInv", _dp),
         ("BCnVelNodes", C.c_int), ("BCvelNodes", _ip), ("nBC", C.c_int), ("BCstr", _dp),
         ("zeroPressureNode", C.c_int), ("monPoint", C.c_int), ("U0", _dp), ("P0", _dp),
+        ("world", C.c_int), ("rank", C.c_int), ("NN_owned", C.c_int), ("NNp_owned", C.c_int), ("NE_apply", C.c_int),
+        ("pinLocal", C.c_int), ("monOwned", C.c_int), ("nPeers", C.c_int),
+        ("peerRank", _ip), ("sendVptr", _ip), ("sendVidx", _ip), ("recvVoff", _ip), ("recvVcnt", _ip),
+        ("sendPptr", _ip), ("sendPidx", _ip), ("recvPoff", _ip), ("recvPcnt", _ip),
     ]
 
 
@@ -112,6 +116,11 @@ def lib():
     L.cfd_solver_create_from_inp.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
     L.cfd_solver_create_cavity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                            C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
+    L.cfd_solver_create_from_inp_part.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.cfd_solver_create_cavity_part.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.cfd_nccl_unique_id.argtypes = [C.c_char_p]
+    L.cfd_comm_init.argtypes = [vp, C.c_char_p]
     L.cfd_solver_init_gpu.argtypes = [vp]
     L.cfd_solver_destroy.argtypes = [vp]
     L.cfd_solver_ctx.argtypes = [vp]
@@ -323,13 +332,22 @@ class Context:
 class Solver:
     """`cfd_solver`: the reference's solverGPU program as an object."""
 
-    def __init__(self, inp_path=None, scheme="explicit", cavity=None, opts=None, init_gpu=True):
+    def __init__(self, inp_path=None, scheme="explicit", cavity=None, opts=None, init_gpu=True, world=1, rank=0):
         self.L = lib()
         self.scheme = EXPLICIT if scheme in (0, "explicit") else IMPLICIT
+        self.world, self.rank = world, rank
         h = C.c_void_p()
         o = C.byref(opts) if opts is not None else None
-        if inp_path is not None:
+        if inp_path is not None and world > 1:
+            _check(self.L.cfd_solver_create_from_inp_part(os.fsencode(inp_path), self.scheme, o, int(init_gpu), world, rank, C.byref(h)))
+        elif inp_path is not None:
             _check(self.L.cfd_solver_create_from_inp(os.fsencode(inp_path), self.scheme, o, int(init_gpu), C.byref(h)))
+        elif world > 1:
+            cv = dict(nx=8, ny=None, nz=None, cluster=0.0, NENv=27, dt=1e-3, viscosity=0.01, maxIter=4, tolerance=1e-3)
+            cv.update(cavity or {})
+            _check(self.L.cfd_solver_create_cavity_part(cv["nx"], cv["ny"] or cv["nx"], cv["nz"] or cv["nx"], cv["cluster"], cv["NENv"],
+                                                        self.scheme, cv["dt"], cv["viscosity"], cv["maxIter"], cv["tolerance"], o,
+                                                        int(init_gpu), world, rank, C.byref(h)))
         else:
             cv = dict(nx=8, ny=None, nz=None, cluster=0.0, NENv=27, dt=1e-3, viscosity=0.01, maxIter=4, tolerance=1e-3)
             cv.update(cavity or {})
@@ -354,6 +372,23 @@ class Solver:
     def init_gpu(self):
         _check(self.L.cfd_solver_init_gpu(self.h))
 
+    def comm_init(self, unique_id):
+        """Attach the NCCL communicator (partitioned runs): `unique_id` = the 128 bytes from nccl_unique_id() on rank 0."""
+        ch = self.L.cfd_solver_ctx(self.h)
+        if not ch:
+            raise CfdError("solver has no GPU context")
+        _check(self.L.cfd_comm_init(C.c_void_p(ch), bytes(unique_id)))
+
+    def owned_fields(self):
+        """(global node ids, U[3, n_owned], global pressure ids, P[n_owned]) of the entries this rank owns."""
+        U, P = self.ctx.fields()
+        NN, NNo, NPo = self.i("NN"), self.i("NN_owned"), self.i("NNp_owned")
+        if self.world > 1:
+            ng, pg = self.arr("part_nodeGlobal")[:NNo], self.arr("part_presGlobal")[:NPo]
+        else:
+            ng, pg = np.arange(NNo), np.arange(NPo)
+        return ng, U.reshape(3, NN)[:, :NNo].copy(), pg, P[:NPo].copy()
+
     def problem_struct(self):
         return self.L.cfd_solver_problem(self.h).contents
 
@@ -368,7 +403,7 @@ class Solver:
 
     def i(self, name):
         p = self.problem_struct()
-        if hasattr(p, name) and name not in ("coord",):
+        if hasattr(p, name) and name not in ("coord", "NN_owned", "NNp_owned", "NE_apply", "pinLocal", "nPeers"):
             return int(getattr(p, name))
         v = self.L.cfd_solver_int(self.h, name.encode())
         if v == -999999:
@@ -431,6 +466,12 @@ def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000):
     ms = C.c_double()
     _check(lib().cfd_csr_pcg(len(b), _i(rs), _i(cl), _d(vl), _d(b), _d(x), tol, maxit, C.byref(its), C.byref(ms)))
     return x, its.value, ms.value
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().cfd_nccl_unique_id(buf))
+    return buf.raw
 
 
 def solver_main(workdir, scheme="explicit", max_steps=0):

@@ -75,6 +75,24 @@ typedef struct cfd_problem {
    int monPoint;              /* monitor node (BCH.cpp:1646-1668) */
    const double* U0;          /* [3NN] initial Un (explicit) / Uk_prev (implicit), BCs applied; NULL = zeros + BCs */
    const double* P0;          /* [NNp] initial pressure; NULL = zeros */
+   /* ---- element-block partition (multi-GPU; all zero / NULL for a whole mesh) -------------------------------
+    * The reference is single-GPU; this part has no counterpart there.  NN / NNp above are then the
+    * LOCAL counts (owned + ghost), owned entries numbered first; CSR rows beyond the owned ones are ignored. */
+   int world, rank;
+   int NN_owned, NNp_owned;   /* 0 = all */
+   int NE_apply;              /* leading elements the element-by-element kernels loop over (0 = NE) */
+   int pinLocal;              /* partitioned runs: local pressure DOF to pin or -1 (zeroPressureNode's `> 0` rule already applied) */
+   int monOwned;              /* partitioned runs: 1 if monPoint is owned by this rank */
+   int nPeers;
+   const int* peerRank;       /* [nPeers] */
+   const int* sendVptr;       /* [nPeers+1] offsets into sendVidx */
+   const int* sendVidx;       /* owned local velocity nodes each peer holds as ghosts */
+   const int* recvVoff;       /* [nPeers] first ghost node filled by the peer */
+   const int* recvVcnt;       /* [nPeers] */
+   const int* sendPptr;       /* same for pressure DOFs */
+   const int* sendPidx;
+   const int* recvPoff;
+   const int* recvPcnt;
 } cfd_problem;
 
 /* Solver settings the reference hard-codes (BCH.cu:433, GQ.cu:344,404) plus the
@@ -101,6 +119,13 @@ int cfd_selectCUDAdevice(int device);
  * the CSR matrices to the device layout, allocates every work vector. */
 int cfd_initializeAndAllocateGPU(const cfd_problem* prob, const cfd_options* opt, cfd_ctx** out);
 void cfd_destroy(cfd_ctx* ctx);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------------------------------------------
+ * rank 0 calls cfd_nccl_unique_id, the bytes are broadcast by the launcher (torch.distributed / MPI), then every
+ * rank attaches its partitioned context.  Collectives used: grouped send/recv of interface nodal values before
+ * each operator application, allreduce (sum / max) of Krylov dot products, convergence sums and maxAcc. */
+int cfd_nccl_unique_id(char out[128]);
+int cfd_comm_init(cfd_ctx* ctx, const char id[128]);
 
 /* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
  * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);
@@ -193,6 +218,12 @@ int cfd_solver_create_from_inp(const char* inp_path, int scheme, const cfd_optio
 int cfd_solver_create_cavity(int nx, int ny, int nz, double cluster, int NENv, int scheme, double dt,
                              double viscosity, int maxIter, double tolerance, const cfd_options* opt,
                              int init_gpu, cfd_solver** out);
+/* Partitioned variants: this process holds rank `rank` of `world` element blocks (own elements + halo layers). */
+int cfd_solver_create_from_inp_part(const char* inp_path, int scheme, const cfd_options* opt, int init_gpu, int world, int rank,
+                                    cfd_solver** out);
+int cfd_solver_create_cavity_part(int nx, int ny, int nz, double cluster, int NENv, int scheme, double dt, double viscosity,
+                                  int maxIter, double tolerance, const cfd_options* opt, int init_gpu, int world, int rank,
+                                  cfd_solver** out);
 /* init_gpu = 0 above stops after step0 (host arrays only, no CUDA call: what the CPU-side tests
  * use); this uploads the problem afterwards. */
 int cfd_solver_init_gpu(cfd_solver* s);
