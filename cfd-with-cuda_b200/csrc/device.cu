@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include <dlfcn.h>
 
@@ -1262,6 +1263,10 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    int rc;
 #define TRY(x) do { rc = (x); if (rc) { cfd_destroy(c); return rc; } } while (0)
 
+   const bool verb = getenv("CFD_VERBOSE") != nullptr;
+   auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+   double tph = now();
+#define IPHASE(msg) do { if (verb) { cudaDeviceSynchronize(); double t_ = now(); fprintf(stderr, "[cfdb200 init] %-28s %8.2f s\n", msg, t_ - tph); tph = t_; } } while (0)
    // reference-element tables -> constant memory
    {
       FeTables T;
@@ -1312,12 +1317,14 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          TRY(dupload(c, &c->diagPosA, dp.data(), dp.size()));
       }
    }
+   IPHASE("Sell K/M/A + maps");
    {
       SellHost h;
       sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, h);
       const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
       TRY(sell_upload(h, 3, v, c->G));
    }
+   IPHASE("Sell G");
    {
       // explicit transpose of the G pattern: rows = pressure nodes (instead of the reference's
       // OPERATION_TRANSPOSE csrmv scatter, BCH.cu:1006-1009)
@@ -1337,6 +1344,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       const double* v[3] = {t1.data(), t2.data(), t3.data()};
       TRY(sell_upload(h, 3, v, c->GT));
    }
+   IPHASE("Sell G^T");
    {
       SellHost h;
       sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NPo, P->sparseZrowStarts[NPo]), h);
@@ -1350,6 +1358,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
       TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
    }
+   IPHASE("Sell Z");
    // ---- mesh tables
    {
       if (!c->ldE) c->ldE = (NE + 31) & ~31;
@@ -1404,6 +1413,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       CFD_CK(cudaMemcpy(Ud, u0.data(), sizeof(double) * N3, cudaMemcpyHostToDevice));
       if (P->P0) CFD_CK(cudaMemcpy(Pd, P->P0, sizeof(double) * NNp, cudaMemcpyHostToDevice));
    }
+   IPHASE("tables + vectors");
    // ---- partition plan
    if (parted) {
       const int np = P->nPeers;

@@ -3,7 +3,9 @@
 // (blascoCodinaHuerta.cpp:732-2159) as hashed / sort-based O(NE) passes with OpenMP, producing the
 // same numbering and the same CSR arrays.
 #pragma once
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.hpp"
@@ -37,6 +39,22 @@ struct Mesh {
    int nActiveColors = 0;
 };
 
+// std::vector whose resize() leaves new elements uninitialised, so that multi-GB arrays can be first-touched
+// (zeroed) in parallel instead of serially inside the constructor.
+template <class T>
+struct default_init_alloc : std::allocator<T> {
+   template <class U> struct rebind { typedef default_init_alloc<U> other; };
+   template <class U> void construct(U* p) { ::new ((void*)p) U; }
+   template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+typedef std::vector<double, default_init_alloc<double> > big_dvec;
+inline void par_zero(big_dvec& v, size_t n) {
+   v.resize(n);
+   double* p = v.data();
+#pragma omp parallel for schedule(static)
+   for (long long i = 0; i < (long long)n; i++) p[i] = 0.0;
+}
+
 struct CsrPattern {
    int nrows = 0, ncols = 0;
    std::vector<int> rowStarts, col;
@@ -46,7 +64,7 @@ struct CsrPattern {
 struct Assembled {
    CsrPattern Mp, Gp, Zp;
    std::vector<int> mapM, mapG, mapZ;   // [e][i][j] CSR positions
-   std::vector<double> Mval, Kval, G1, G2, G3, Zval;
+   big_dvec Mval, Kval, G1, G2, G3, Zval;
    std::vector<double> MdInv, MdOrigInv;
 };
 

@@ -10,6 +10,10 @@
 #include <cstring>
 #include <fstream>
 
+#include <omp.h>
+
+#include <thread>
+
 #include "host.hpp"
 
 namespace cfdb {
@@ -75,28 +79,67 @@ inline void atomic_add(double& t, double v) {
 // step0 (BCH.cpp:3127-3315, GQ.cpp:3425-3572): M, K, G1..3; lumped mass and Z = sum_c G_c^T Md^-1 G_c
 // (explicit, BCH.cpp:3322-3479 / BCH.cu:281-411) or the FE Laplacian Z (implicit, GQ.cpp:3677-3772).
 // Element loop in parallel with atomic adds instead of the reference's serial loop.
+static double wall_s() {
+   timeval tv;
+   gettimeofday(&tv, nullptr);
+   return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+static bool verbose() { return getenv("CFD_VERBOSE") != nullptr; }
+#define PHASE(msg) do { if (verbose()) { double t_ = wall_s(); fprintf(stderr, "[cfdb200 host] %-28s %8.2f s\n", msg, t_ - tph); tph = t_; } } while (0)
+
 void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
    const int NE = m.NE, nv = m.NENv, NN = m.NN, NNp = m.NNp;
+   double tph = wall_s();
    FeTables T;
    build_fe_tables(nv, T);
    const std::vector<int>* pidx = m.presIndex.empty() ? nullptr : &m.presIndex;
    build_pattern(m, nv, nv, NN, NN, A.Mp, &A.mapM);
-   build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG, nullptr, pidx);
+   const bool samePattern = (nv == 8 && !pidx);   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z share one pattern
+   if (samePattern) { A.Gp = A.Mp; A.mapG = A.mapM; }
+   else build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG, nullptr, pidx);
+   PHASE("patterns M, G");
    const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp.nnz();
-   A.Mval.assign(nnzM, 0.0); A.Kval.assign(nnzM, 0.0);
-   A.G1.assign(nnzG, 0.0); A.G2.assign(nnzG, 0.0); A.G3.assign(nnzG, 0.0);
+   par_zero(A.Mval, nnzM); par_zero(A.Kval, nnzM);
+   par_zero(A.G1, nnzG); par_zero(A.G2, nnzG); par_zero(A.G3, nnzG);
    const double invDens = 1.0 / m.density;
    const double mscale = scheme == CFD_IMPLICIT ? 1.0 / m.dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
    if (scheme == CFD_IMPLICIT) {
-      build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ, pidx, pidx);
-      A.Zval.assign((size_t)A.Zp.nnz(), 0.0);
+      if (samePattern) { A.Zp = A.Mp; A.mapZ = A.mapM; }
+      else build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ, pidx, pidx);
+      par_zero(A.Zval, (size_t)A.Zp.nnz());
+      PHASE("pattern Z");
    }
+   // Elements are dealt to threads in contiguous chunks.  A node touched only by elements of one chunk is
+   // private to that thread: elements whose nodes are all private add without atomics (all but the chunk
+   // boundary layers); the others use atomic adds.
+   int nthr = 1;
 #pragma omp parallel
    {
-      ElemGeom* g = new ElemGeom;
-#pragma omp for schedule(static)
+#pragma omp single
+      nthr = omp_get_num_threads();
+   }
+   auto chunkOf = [&](int e) { return (int)(((long long)e * nthr) / NE); };
+   std::vector<unsigned char> shared((size_t)NN, 0);
+   {
+      std::vector<short> lo((size_t)NN, 32767), hi((size_t)NN, -1);
       for (int e = 0; e < NE; e++) {
+         const short ch = (short)chunkOf(e);
+         const int* L = &m.LtoGnode[(size_t)e * nv];
+         for (int i = 0; i < nv; i++) { lo[L[i]] = std::min(lo[L[i]], ch); hi[L[i]] = std::max(hi[L[i]], ch); }
+      }
+      for (int n = 0; n < NN; n++) shared[n] = lo[n] != hi[n];
+   }
+#pragma omp parallel num_threads(nthr)
+   {
+      ElemGeom* g = new ElemGeom;
+      const int tid = omp_get_thread_num();
+      const int e0 = (int)(((long long)NE * tid + nthr - 1) / nthr), e1 = (int)(((long long)NE * (tid + 1) + nthr - 1) / nthr);
+      for (int e = e0; e < e1; e++) {
          element_geometry(m, T, e, *g);
+         const int* L = &m.LtoGnode[(size_t)e * nv];
+         bool priv = true;
+         for (int i = 0; i < nv; i++) priv = priv && !shared[L[i]];
+         auto add = [priv](double& t, double v) { if (priv) t += v; else atomic_add(t, v); };
          const int* mm = &A.mapM[(size_t)e * nv * nv];
          for (int i = 0; i < nv; i++)
             for (int j = 0; j < nv; j++) {
@@ -105,8 +148,8 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                   me += T.Sv[k][i] * T.Sv[k][j] * g->fac[k];
                   ke += (g->gv[k][i][0] * g->gv[k][j][0] + g->gv[k][i][1] * g->gv[k][j][1] + g->gv[k][i][2] * g->gv[k][j][2]) * g->fac[k];
                }
-               atomic_add(A.Mval[mm[i * nv + j]], mscale * me);
-               atomic_add(A.Kval[mm[i * nv + j]], m.viscosity * ke);
+               add(A.Mval[mm[i * nv + j]], mscale * me);
+               add(A.Kval[mm[i * nv + j]], m.viscosity * ke);
             }
          const int* mg = &A.mapG[(size_t)e * nv * 8];
          for (int i = 0; i < nv; i++)
@@ -116,9 +159,9 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                   const double w = T.Sp[k][j] * g->fac[k];
                   g1 += w * g->gv[k][i][0]; g2 += w * g->gv[k][i][1]; g3 += w * g->gv[k][i][2];
                }
-               atomic_add(A.G1[mg[i * 8 + j]], -invDens * g1);
-               atomic_add(A.G2[mg[i * 8 + j]], -invDens * g2);
-               atomic_add(A.G3[mg[i * 8 + j]], -invDens * g3);
+               add(A.G1[mg[i * 8 + j]], -invDens * g1);
+               add(A.G2[mg[i * 8 + j]], -invDens * g2);
+               add(A.G3[mg[i * 8 + j]], -invDens * g3);
             }
          if (scheme == CFD_IMPLICIT) {
             const int* mz = &A.mapZ[(size_t)e * 64];
@@ -127,12 +170,13 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                   double z = 0;
                   for (int k = 0; k < 8; k++)
                      z += (g->gp[k][i][0] * g->gp[k][j][0] + g->gp[k][i][1] * g->gp[k][j][1] + g->gp[k][i][2] * g->gp[k][j][2]) * g->fac[k];
-                  atomic_add(A.Zval[mz[i * 8 + j]], -z);
+                  add(A.Zval[mz[i * 8 + j]], -z);
                }
          }
       }
       delete g;
    }
+   PHASE("element assembly");
    if (scheme == CFD_EXPLICIT) {
       // lumped mass, BC rows -> 1 (BCH.cpp:3254-3292)
       std::vector<double> md((size_t)NN, 0.0);
@@ -195,6 +239,7 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
          std::copy(zv[i].begin(), zv[i].end(), A.Zval.begin() + A.Zp.rowStarts[i]);
       }
    }
+   PHASE("Z");
    // pressure pin: diagonal * 1000, only for node > 0 (applyBC_Step2(1), BCH.cpp:4167-4180)
    // (a partitioned sub-mesh carries the rule already applied: local DOF or -1)
    const int pin = m.presIndex.empty() ? (m.zeroPressureNode > 0 ? m.zeroPressureNode : -1) : m.zeroPressureNode;
@@ -303,6 +348,13 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
                   int rank = 0) {
    s->scheme = scheme;
    if (opt) s->opt = *opt; else cfd_default_options(&s->opt);
+   {
+      // one process per GPU: launchers such as torchrun pin OMP_NUM_THREADS=1; give each rank its share of the cores
+      int want = 0;
+      if (const char* e = getenv("CFD_HOST_THREADS")) want = atoi(e);
+      if (want <= 0 && world > 1) want = std::max(1u, std::thread::hardware_concurrency() / (unsigned)world);
+      if (want > 0) omp_set_num_threads(want);
+   }
    generate_midnodes(s->mesh);
    find_bc_nodes(s->mesh);
    find_monitor(s->mesh);
