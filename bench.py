@@ -211,11 +211,9 @@ def main():
                             cavity=dict(nx=w["n"], cluster=w["cluster"], NENv=w["NENv"], dt=w["dt"], viscosity=w["viscosity"]))
     if world > 1:
         # element-block partition: rank r holds block r; NCCL communicator for halo swaps and allreduces
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(fracstep.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        s.comm_init(idt.cpu().numpy().tobytes())
+        # (+ CUDA-IPC exchange windows: the pressure solve then runs as one persistent kernel per GPU that talks to
+        #  its neighbours through peer memory; CFD_NO_P2P=1 keeps the host-driven NCCL version)
+        fracstep.setup_distributed(s, dist, torch, peer_memory=True)
     setup_s = time.time() - t0
     c = s.ctx
 

@@ -697,6 +697,79 @@ __global__ void __launch_bounds__(512, 3) k_pcg(PcgArgs a) {
    if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
 }
 
+struct PcgP2PArgs {
+   PcgArgs a;   // a.p lives in this rank's exchange window
+   XComm xc;
+};
+
+// Multi-GPU Jacobi-PCG: k_pcg with the two exchange steps folded in (fused compute + collective over peer memory).
+// One persistent cooperative kernel per GPU; per iteration: q = Z p on the owned rows (ghost p entries were written by
+// the neighbours), p.q all-reduced through mailboxes, fused x/r update, (r.z, r.r) all-reduced, p update whose
+// interface values are stored directly into the neighbours' ghost entries over NVLink.  Identical recurrences and
+// stopping rule on every rank (the reduced scalars are bit-identical everywhere), so all ranks leave together.
+__global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
+   cg::grid_group grid = cg::this_grid();
+   __shared__ double sh[3 * 32];
+   const PcgArgs& a = pa.a;
+   const XComm& xc = pa.xc;
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
+   double* buf0 = a.scratch;
+   double* buf1 = a.scratch + 3 * (size_t)gridDim.x;
+   const int n = a.n;
+   unsigned long long epoch = xc.xstate[0], hepoch = xc.xstate[1];
+
+   if (!a.x0zero) {   // ghost entries of x were refreshed by the caller
+      pcg_spmv_phase(a.Z, a.part, a.x, a.q, gwarp, nwarps, lane);
+      grid.sync();
+   }
+   double v3[3] = {0, 0, 0};
+   for (int i = tid; i < n; i += nthreads) {
+      const double bi = a.b[i];
+      double ri = bi;
+      if (a.x0zero) a.x[i] = 0.0; else ri = bi - a.q[i];
+      a.r[i] = ri;
+      const double zi = a.dinv[i] * ri;
+      v3[0] += ri * zi; v3[1] += bi * bi; v3[2] += ri * ri;
+   }
+   xgrid_sum<3>(grid, v3, buf0, sh, xc, epoch);
+   double rz = v3[0];
+   const double bb = v3[1];
+   double rr = v3[2];
+   const double thresh = a.tol * sqrt(bb);
+   int it = 0;
+   if (!(sqrt(rr) <= thresh || it >= a.maxit))
+      p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i]; });
+   while (true) {
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;
+      double v1[1];
+      v1[0] = pcg_spmv_phase(a.Z, a.part, a.p, a.q, gwarp, nwarps, lane);
+      xgrid_sum<1>(grid, v1, buf1, sh, xc, epoch);
+      const double alpha = rz / v1[0];
+      double v2[2] = {0, 0};
+      for (int i = tid; i < n; i += nthreads) {
+         a.x[i] += alpha * a.p[i];
+         const double ri = a.r[i] - alpha * a.q[i];
+         a.r[i] = ri;
+         v2[0] += ri * (a.dinv[i] * ri);
+         v2[1] += ri * ri;
+      }
+      xgrid_sum<2>(grid, v2, buf0, sh, xc, epoch);
+      const double beta = v2[0] / rz;
+      rz = v2[0];
+      rr = v2[1];
+      it++;
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;   // converged: the next search direction is never used
+      p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i] + beta * a.p[i]; });
+   }
+   grid.sync();
+   if (tid == 0) {
+      a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
+      xc.xstate[0] = epoch; xc.xstate[1] = hepoch;
+   }
+}
+
 // Diagnostic: cost of the grid-wide primitives the persistent Krylov kernels are built from.
 // mode 0: grid.sync()   mode 1: grid_sum<1>   mode 2: grid_sum<3>
 __global__ void __launch_bounds__(1024) k_diag_sync(int iters, int mode, double* scratch, double* out) {
@@ -1117,7 +1190,28 @@ int run_bicg_dist(cfd_ctx* c) {
    return CFD_OK;
 }
 
+// Peer-memory PCG: one cooperative launch per rank, all exchange inside the kernel (k_pcg_p2p).
+int run_pcg_p2p(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   int rc;
+   if (!x0zero && (rc = halo(c, x, false))) return rc;
+   PcgP2PArgs pa;
+   PcgArgs& a = pa.a;
+   a.Z = c->Z; a.part = c->pcgPart; a.n = c->NPo; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
+   a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
+   XComm& xc = pa.xc;
+   xc.world = c->P.world; xc.rank = c->P.rank; xc.npeers = (int)c->peerRank.size();
+   xc.peerWin = c->dPeerWin; xc.peerRank = c->dPeerRank; xc.peerP = c->dPeerP; xc.pushPtr = c->pushPtrP; xc.pushDst = c->pushDstP;
+   xc.xstate = c->xstate;
+   void* args[] = {&pa};
+   ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
+   c->lastPcgRec = ps.idx;
+   CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_p2p, dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
+   c->launches++;
+   return CFD_OK;
+}
+
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   if (parted(c) && c->p2p) return run_pcg_p2p(c, b, x, x0zero);
    if (parted(c)) return run_pcg_dist(c, b, x, x0zero);
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
@@ -1208,6 +1302,9 @@ void cfd_destroy(cfd_ctx* c) {
    for (void* p : c->allocs) cudaFree(p);
    sell_free(c->K); sell_free(c->G); sell_free(c->GT); sell_free(c->Z);
    if (c->comm) { if (c->comm->comm) c->comm->CommDestroy(c->comm->comm); delete c->comm; }
+   for (size_t q = 0; q < c->peerWin.size(); q++)
+      if (c->peerWin[q] && c->peerWin[q] != c->win) cudaIpcCloseMemHandle(c->peerWin[q]);
+   if (c->win) cudaFree(c->win);
    if (c->h_pinned) cudaFreeHost(c->h_pinned);
    if (c->ev0) cudaEventDestroy(c->ev0);
    if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1437,6 +1534,15 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       TRY(dupload(c, &c->sendPidx, packP.data(), packP.size()));
       TRY(dalloc(c, &c->sendBuf, (size_t)std::max(3 * nsV, nsP) + 1));
       TRY(dalloc(c, &c->dacc, 64));
+      c->remoteVoff.assign(P->remoteVoff ? P->remoteVoff : P->recvVoff, (P->remoteVoff ? P->remoteVoff : P->recvVoff) + np);
+      c->remotePoff.assign(P->remotePoff ? P->remotePoff : P->recvPoff, (P->remotePoff ? P->remotePoff : P->recvPoff) + np);
+      // exchange window for the peer-memory path: flags | mailboxes | p  (p moves into the window)
+      c->winOffP = kWinHeader;
+      c->winBytes = (size_t)kWinHeader + sizeof(double) * (size_t)NNp;
+      CFD_CK(cudaMalloc((void**)&c->win, c->winBytes));
+      CFD_CK(cudaMemset(c->win, 0, c->winBytes));
+      c->cg_p = (double*)(c->win + c->winOffP);
+      TRY(dalloc(c, &c->xstate, 4));
    }
    // ---- cooperative launch geometry: persistent kernels, a whole number of CTAs per SM
    {
@@ -1509,6 +1615,61 @@ int cfd_comm_init(cfd_ctx* c, const char id[128]) {
    CFD_CK(cudaSetDevice(c->device));
    CFD_NCCL(c->comm, c->comm->CommInitRank(&c->comm->comm, c->P.world, uid, c->P.rank));
    // initial halo of the state vectors (the host supplied owned + ghost values, but be safe)
+   return CFD_OK;
+}
+
+int cfd_p2p_export(cfd_ctx* c, char desc[96]) {
+   if (!c || !desc) return CFD_ERR_ARG;
+   if (!c->win) { set_error("no exchange window (context is not partitioned)"); return CFD_ERR_STATE; }
+   memset(desc, 0, 96);
+   cudaIpcMemHandle_t h;
+   CFD_CK(cudaIpcGetMemHandle(&h, c->win));
+   memcpy(desc, &h, sizeof h);
+   memcpy(desc + 64, &c->winOffP, sizeof(long long));
+   return CFD_OK;
+}
+
+int cfd_p2p_attach(cfd_ctx* c, const char* all) {
+   if (!c || !all) return CFD_ERR_ARG;
+   if (!c->win) { set_error("no exchange window (context is not partitioned)"); return CFD_ERR_STATE; }
+   const int world = c->P.world, rank = c->P.rank;
+   if (world > kMaxRanks) { set_error("peer-memory path supports up to %d ranks", (int)kMaxRanks); return CFD_ERR_ARG; }
+   CFD_CK(cudaSetDevice(c->device));
+   c->peerWin.assign(world, nullptr);
+   c->peerOffP.assign(world, 0);
+   for (int q = 0; q < world; q++) {
+      memcpy(&c->peerOffP[q], all + 96 * q + 64, sizeof(long long));
+      if (q == rank) { c->peerWin[q] = c->win; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all + 96 * q, sizeof h);
+      void* ptr = nullptr;
+      CFD_CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peerWin[q] = (char*)ptr;
+   }
+   const int np = (int)c->peerRank.size();
+   std::vector<double*> peerP(np);
+   for (int j = 0; j < np; j++)
+      peerP[j] = (double*)(c->peerWin[c->peerRank[j]] + c->peerOffP[c->peerRank[j]]) + c->remotePoff[j];
+   // push list per owned pressure DOF: (peer index, slot inside my block of the peer's ghosts)
+   const int NPo = c->NPo;
+   std::vector<int> sendP((size_t)c->sendPptr[np]);
+   CFD_CK(cudaMemcpy(sendP.data(), c->sendPidx, sizeof(int) * sendP.size(), cudaMemcpyDeviceToHost));
+   std::vector<int> ptr((size_t)NPo + 1, 0);
+   for (int t = 0; t < (int)sendP.size(); t++) ptr[sendP[t] + 1]++;
+   for (int i = 0; i < NPo; i++) ptr[i + 1] += ptr[i];
+   std::vector<int2> dst((size_t)ptr[NPo]);
+   {
+      std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+      for (int j = 0; j < np; j++)
+         for (int t = c->sendPptr[j]; t < c->sendPptr[j + 1]; t++) dst[fill[sendP[t]]++] = make_int2(j, t - c->sendPptr[j]);
+   }
+   int rc;
+   if ((rc = dupload(c, &c->dPeerWin, c->peerWin.data(), c->peerWin.size()))) return rc;
+   if ((rc = dupload(c, &c->dPeerP, peerP.data(), peerP.size()))) return rc;
+   if ((rc = dupload(c, &c->dPeerRank, c->peerRank.data(), c->peerRank.size()))) return rc;
+   if ((rc = dupload(c, &c->pushPtrP, ptr.data(), ptr.size()))) return rc;
+   if ((rc = dupload(c, &c->pushDstP, dst.data(), dst.size()))) return rc;
+   c->p2p = getenv("CFD_NO_P2P") == nullptr;
    return CFD_OK;
 }
 

@@ -130,4 +130,18 @@ struct cfd_ctx {
    int *sendVidx = nullptr, *sendPidx = nullptr;   // device
    double* sendBuf = nullptr;                        // device staging for packed interface values
    double* dacc = nullptr;                           // device: distributed-Krylov accumulators + state
+   // ---- peer-memory (CUDA IPC over NVLink) exchange window, optional
+   bool p2p = false;
+   char* win = nullptr;             // this rank's window: flags | mailboxes | p
+   size_t winBytes = 0;
+   long long winOffP = 0;
+   std::vector<char*> peerWin;      // [world] mapped peer windows (own included)
+   std::vector<long long> peerOffP; // [world]
+   char** dPeerWin = nullptr;       // device copy
+   double** dPeerP = nullptr;       // [nPeers] start of my block inside each peer's p ghosts
+   int* dPeerRank = nullptr;
+   int* pushPtrP = nullptr;         // [NPo+1] CSR of (peer, slot) pushes per owned pressure DOF
+   int2* pushDstP = nullptr;
+   unsigned long long* xstate = nullptr;   // device: [0] allreduce epoch [1] halo epoch [2] error
+   std::vector<int> remoteVoff, remotePoff;
 };

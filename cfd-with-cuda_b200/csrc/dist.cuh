@@ -342,3 +342,101 @@ __global__ void __launch_bounds__(256) k_max_abs_diff3(int n, long long ld, cons
    }
 }
 
+
+// =================================================================================================
+// Peer-memory path: the pressure solve as ONE persistent cooperative kernel per GPU.  Interface values of p are
+// stored straight into the neighbours' ghost entries over NVLink, dot products are all-reduced through mailboxes in
+// the peers' windows; ordering by system-scope release/acquire flags carrying monotonically increasing epochs.
+// =================================================================================================
+enum { kWinFlagsBytes = 4096, kWinMailBytes = 12288, kWinHeader = 16384, kMaxRanks = 64 };
+
+struct XComm {
+   int world, rank, npeers;
+   char* const* peerWin;               // [world] window bases (own included)
+   const int* peerRank;                // [npeers]
+   double* const* peerP;               // [npeers]
+   const int* pushPtr;                 // [n+1]
+   const int2* pushDst;                // (peer index, slot)
+   unsigned long long* xstate;         // [0] allreduce epoch [1] halo epoch [2] error
+};
+__device__ __forceinline__ unsigned long long* win_arflag(char* w, int slot, int src) { return (unsigned long long*)w + slot * kMaxRanks + src; }
+__device__ __forceinline__ unsigned long long* win_haloflag(char* w, int src) { return (unsigned long long*)w + 3 * kMaxRanks + src; }
+__device__ __forceinline__ double* win_mail(char* w, int slot, int src) { return (double*)(w + kWinFlagsBytes) + (slot * kMaxRanks + src) * 8; }
+
+__device__ __forceinline__ void st_rel_sys(unsigned long long* p, unsigned long long v) {
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acq_sys(const unsigned long long* p) {
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+   double v;
+   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+   return t;
+}
+// Spin until *f >= want.  Never hangs: after 4 s (a peer died) the error word is set and every later wait returns at once.
+__device__ __forceinline__ void wait_flag(const unsigned long long* f, unsigned long long want, unsigned long long* err) {
+   const unsigned long long t0 = gtimer();
+   unsigned spins = 0;
+   while (ld_acq_sys(f) < want) {
+      if ((++spins & 255u) == 0) {
+         if (*(volatile unsigned long long*)err) return;
+         if (gtimer() - t0 > 4000000000ull) { *(volatile unsigned long long*)err = 1; return; }
+      }
+   }
+}
+
+// Sum N values over all blocks of all ranks; the result is bit-identical in every block of every rank
+// (local partials in block order, then ranks in rank order).
+template <int N>
+__device__ __forceinline__ void xgrid_sum(cg::grid_group& grid, double (&v)[N], double* buf, double* sh, const XComm& xc,
+                                          unsigned long long& epoch) {
+   grid_sum<N>(grid, v, buf, sh);
+   epoch++;
+   const int slot = (int)(epoch % 3);
+   char* mine = xc.peerWin[xc.rank];
+   if (blockIdx.x == 0 && threadIdx.x < xc.world) {   // thread q delivers this rank's sums to rank q
+      char* w = xc.peerWin[threadIdx.x];
+      double* mb = win_mail(w, slot, xc.rank);
+#pragma unroll
+      for (int i = 0; i < N; i++) st_sys_f64(mb + i, v[i]);
+      __threadfence_system();
+      st_rel_sys(win_arflag(w, slot, xc.rank), epoch);
+   }
+   if (threadIdx.x < xc.world) wait_flag(win_arflag(mine, slot, threadIdx.x), epoch, xc.xstate + 2);
+   __syncthreads();
+#pragma unroll
+   for (int i = 0; i < N; i++) {
+      double s = 0.0;
+      for (int q = 0; q < xc.world; q++) s += ld_sys_f64(win_mail(mine, slot, q) + i);
+      v[i] = s;
+   }
+}
+
+// p <- values (owned rows), pushed to the neighbours' ghost entries; then signal and wait for their pushes.
+template <typename F>
+__device__ __forceinline__ void p_update_and_push(cg::grid_group& grid, int n, double* p, const XComm& xc, unsigned long long& hepoch,
+                                                  int tid, int nthreads, F value) {
+   for (int i = tid; i < n; i += nthreads) {
+      const double pn = value(i);
+      p[i] = pn;
+      for (int e = xc.pushPtr[i]; e < xc.pushPtr[i + 1]; e++) {
+         const int2 d = xc.pushDst[e];
+         st_sys_f64(xc.peerP[d.x] + d.y, pn);
+      }
+   }
+   __threadfence_system();
+   grid.sync();
+   hepoch++;
+   if (blockIdx.x == 0 && threadIdx.x < xc.npeers) st_rel_sys(win_haloflag(xc.peerWin[xc.peerRank[threadIdx.x]], xc.rank), hepoch);
+   if (threadIdx.x < xc.npeers) wait_flag(win_haloflag(xc.peerWin[xc.rank], xc.peerRank[threadIdx.x]), hepoch, xc.xstate + 2);
+   __syncthreads();
+}

@@ -86,6 +86,7 @@ struct PeerPlan {
    std::vector<int> sendV, sendP;   // my OWNED local velocity-node / pressure-DOF indices the peer holds as ghosts
    int recvVoff = 0, recvVcnt = 0;  // my ghost range [off, off+cnt) filled by this peer (velocity nodes)
    int recvPoff = 0, recvPcnt = 0;  // same for pressure DOFs
+   int remoteVoff = 0, remotePoff = 0;   // where MY values start inside the PEER's ghost ranges (its recvVoff / recvPoff for me)
 };
 struct Partition {
    int rank = 0, world = 1;

@@ -522,6 +522,26 @@ void partition_mesh(const Mesh& g, int world, int rank, int layers, Mesh& loc, P
       }
    }
    std::sort(part.peers.begin(), part.peers.end(), [](const PeerPlan& a, const PeerPlan& b) { return a.rank < b.rank; });
+   // remote offsets (for direct peer-memory pushes): rank q numbers its owned entries first, then its ghosts
+   // grouped by owner in ascending owner order -> my block starts at owned(q) + sum_{o < me} ghosts(q, o)
+   {
+      std::vector<long long> ownedV(world, 0), ownedP(world, 0), cntV((size_t)world * world, 0), cntP((size_t)world * world, 0);
+      for (int n = 0; n < NN; n++) {
+         const int o = nOwner[n];
+         mask_t mk = nMask[n];
+         while (mk) {
+            const int q = __builtin_ctzll(mk);
+            mk &= mk - 1;
+            if (q == o) { ownedV[q]++; if (n < g.NCN) ownedP[q]++; }
+            else { cntV[(size_t)q * world + o]++; if (n < g.NCN) cntP[(size_t)q * world + o]++; }
+         }
+      }
+      for (PeerPlan& pp : part.peers) {
+         long long ov = ownedV[pp.rank], op = ownedP[pp.rank];
+         for (int o = 0; o < rank; o++) { ov += cntV[(size_t)pp.rank * world + o]; op += cntP[(size_t)pp.rank * world + o]; }
+         pp.remoteVoff = (int)ov; pp.remotePoff = (int)op;
+      }
+   }
    // ---- the local mesh
    loc = Mesh();
    loc.eType = g.eType; loc.NENv = nv; loc.NENp = g.NENp; loc.NGP = g.NGP;

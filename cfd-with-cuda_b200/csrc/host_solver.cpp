@@ -326,7 +326,7 @@ struct cfd_solver {
    Partition part;
    bool partitioned = false;
    int globalNN = 0, globalNNp = 0, globalNE = 0;
-   std::vector<int> peerRank, sendVptr, sendVidx, recvVoff, recvVcnt, sendPptr, sendPidx, recvPoff, recvPcnt;
+   std::vector<int> peerRank, sendVptr, sendVidx, recvVoff, recvVcnt, sendPptr, sendPidx, recvPoff, recvPcnt, remoteVoff, remotePoff;
    Assembled A;
    cfd_problem prob;
    cfd_options opt;
@@ -400,12 +400,14 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
          s->sendPptr.push_back((int)s->sendPidx.size());
          s->recvVoff.push_back(pp.recvVoff); s->recvVcnt.push_back(pp.recvVcnt);
          s->recvPoff.push_back(pp.recvPoff); s->recvPcnt.push_back(pp.recvPcnt);
+         s->remoteVoff.push_back(pp.remoteVoff); s->remotePoff.push_back(pp.remotePoff);
       }
       P.nPeers = (int)pt.peers.size();
       P.peerRank = s->peerRank.data(); P.sendVptr = s->sendVptr.data(); P.sendVidx = s->sendVidx.data();
       P.recvVoff = s->recvVoff.data(); P.recvVcnt = s->recvVcnt.data();
       P.sendPptr = s->sendPptr.data(); P.sendPidx = s->sendPidx.data();
       P.recvPoff = s->recvPoff.data(); P.recvPcnt = s->recvPcnt.data();
+      P.remoteVoff = s->remoteVoff.data(); P.remotePoff = s->remotePoff.data();
    }
    if (m.isRestart == 1 && !restartPath.empty()) {
       s->U0.assign((size_t)3 * m.NN, 0.0); s->P0.assign((size_t)m.NNp, 0.0);
@@ -514,7 +516,7 @@ const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, 
 #define IV(nm, v) if (n == nm) { *count = (long long)(v).size(); *is_int = 1; return (v).data(); }
    IV("part_nodeGlobal", s->part.nodeGlobal) IV("part_presGlobal", s->part.presGlobal) IV("part_elemGlobal", s->part.elemGlobal)
    IV("peerRank", s->peerRank) IV("sendVptr", s->sendVptr) IV("sendVidx", s->sendVidx) IV("recvVoff", s->recvVoff) IV("recvVcnt", s->recvVcnt)
-   IV("sendPptr", s->sendPptr) IV("sendPidx", s->sendPidx) IV("recvPoff", s->recvPoff) IV("recvPcnt", s->recvPcnt)
+   IV("remoteVoff", s->remoteVoff) IV("remotePoff", s->remotePoff) IV("sendPptr", s->sendPptr) IV("sendPidx", s->sendPidx) IV("recvPoff", s->recvPoff) IV("recvPcnt", s->recvPcnt)
    DV("coord", m.coord) IV("LtoGnode", m.LtoGnode) IV("BCvelNodes", m.BCvelNodes) DV("BCstr", m.BCstr)
    IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp.rowStarts) IV("sparseGcol", A.Gp.col)
    IV("sparseZrowStarts", A.Zp.rowStarts) IV("sparseZcol", A.Zp.col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG)

@@ -46,6 +46,7 @@ class cfd_problem(C.Structure):
         ("pinLocal", C.c_int), ("monOwned", C.c_int), ("nPeers", C.c_int),
         ("peerRank", _ip), ("sendVptr", _ip), ("sendVidx", _ip), ("recvVoff", _ip), ("recvVcnt", _ip),
         ("sendPptr", _ip), ("sendPidx", _ip), ("recvPoff", _ip), ("recvPcnt", _ip),
+        ("remoteVoff", _ip), ("remotePoff", _ip),
     ]
 
 
@@ -121,6 +122,8 @@ def lib():
                                                 C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.cfd_nccl_unique_id.argtypes = [C.c_char_p]
     L.cfd_comm_init.argtypes = [vp, C.c_char_p]
+    L.cfd_p2p_export.argtypes = [vp, C.c_char_p]
+    L.cfd_p2p_attach.argtypes = [vp, C.c_char_p]
     L.cfd_solver_init_gpu.argtypes = [vp]
     L.cfd_solver_destroy.argtypes = [vp]
     L.cfd_solver_ctx.argtypes = [vp]
@@ -379,6 +382,14 @@ class Solver:
             raise CfdError("solver has no GPU context")
         _check(self.L.cfd_comm_init(C.c_void_p(ch), bytes(unique_id)))
 
+    def p2p_export(self):
+        buf = C.create_string_buffer(96)
+        _check(self.L.cfd_p2p_export(C.c_void_p(self.L.cfd_solver_ctx(self.h)), buf))
+        return buf.raw
+
+    def p2p_attach(self, all_desc):
+        _check(self.L.cfd_p2p_attach(C.c_void_p(self.L.cfd_solver_ctx(self.h)), bytes(all_desc)))
+
     def owned_fields(self):
         """(global node ids, U[3, n_owned], global pressure ids, P[n_owned]) of the entries this rank owns."""
         U, P = self.ctx.fields()
@@ -466,6 +477,23 @@ def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000):
     ms = C.c_double()
     _check(lib().cfd_csr_pcg(len(b), _i(rs), _i(cl), _d(vl), _d(b), _d(x), tol, maxit, C.byref(its), C.byref(ms)))
     return x, its.value, ms.value
+
+
+def setup_distributed(solver, dist, torch, peer_memory=True):
+    """Attach communicators to a partitioned Solver using an initialised torch.distributed (NCCL) group:
+    broadcast of the NCCL unique id, then (optionally) all-gather of the CUDA-IPC window descriptors."""
+    rank = dist.get_rank()
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    solver.comm_init(idt.cpu().numpy().tobytes())
+    if peer_memory:
+        mine = torch.frombuffer(bytearray(solver.p2p_export()), dtype=torch.uint8).cuda()
+        allb = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(dist.get_world_size())]
+        dist.all_gather(allb, mine)
+        solver.p2p_attach(b"".join(t.cpu().numpy().tobytes() for t in allb))
+        dist.barrier()
 
 
 def nccl_unique_id():

@@ -93,6 +93,8 @@ typedef struct cfd_problem {
    const int* sendPidx;
    const int* recvPoff;
    const int* recvPcnt;
+   const int* remoteVoff;     /* [nPeers] start of MY values inside the peer's velocity ghost range (peer-memory pushes) */
+   const int* remotePoff;     /* [nPeers] same for pressure DOFs */
 } cfd_problem;
 
 /* Solver settings the reference hard-codes (BCH.cu:433, GQ.cu:344,404) plus the
@@ -126,6 +128,12 @@ void cfd_destroy(cfd_ctx* ctx);
  * each operator application, allreduce (sum / max) of Krylov dot products, convergence sums and maxAcc. */
 int cfd_nccl_unique_id(char out[128]);
 int cfd_comm_init(cfd_ctx* ctx, const char id[128]);
+/* Optional peer-memory path (NVLink P2P through CUDA IPC): each rank exports its exchange window, the launcher
+ * all-gathers the 96-byte descriptors, every rank maps its peers' windows.  With it the whole pressure solve runs
+ * as ONE persistent kernel per GPU that pushes interface values of p straight into the neighbours' ghost entries
+ * and all-reduces its dot products through peer mailboxes -- no host round trip and no NCCL call per iteration. */
+int cfd_p2p_export(cfd_ctx* ctx, char desc[96]);
+int cfd_p2p_attach(cfd_ctx* ctx, const char* all_desc /* [world][96] */);
 
 /* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
  * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);

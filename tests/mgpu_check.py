@@ -1,7 +1,7 @@
 """torchrun --nproc-per-node N scratch/mgpu_check.py : partitioned run vs single-GPU run of the same problem."""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, 'cfd-with-cuda_b200')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'cfd-with-cuda_b200'))
 import fracstep
 rank, world, lr = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(lr)
@@ -16,7 +16,7 @@ cases = [(dict(nx=8, NENv=27), 'explicit', 3, {}), (dict(nx=12, NENv=8), 'implic
 for cav, scheme, steps, kw in cases:
     opts = fracstep.options(device=lr, **kw)
     s = fracstep.Solver(scheme=scheme, cavity=cav, opts=opts, world=world, rank=rank)
-    s.comm_init(bcast_id())
+    fracstep.setup_distributed(s, dist, torch, peer_memory=os.environ.get('NO_P2P') is None)
     reps = s.ctx.time_loop(steps)
     ng, U, pg, P = s.owned_fields()
     if rank == 0:

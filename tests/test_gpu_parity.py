@@ -252,3 +252,29 @@ def test_large_mesh_properties():
     R2, Pdiff = c.download("R2"), c.download("Pdiff")
     assert np.linalg.norm(Z @ Pdiff - R2) <= 1.05e-6 * np.linalg.norm(R2)
     assert R2[s.i("zeroPressureNode")] == 0.0
+
+
+@pytest.mark.parametrize("peer_memory", [True, False])
+def test_two_gpu_partitioned_run(peer_memory, tmp_path):
+    """Multi-GPU: the partitioned run (element blocks, halo swap, all-reduced dot products) reproduces the single-GPU
+    fields -- with the peer-memory persistent PCG and with the host-driven NCCL PCG.  Needs 2 GPUs on the box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if not peer_memory:
+        env["NO_P2P"] = "1"
+    port = 29600 + os.getpid() % 300 + (7 if peer_memory else 0)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(root, "tests", "mgpu_check.py")], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = [l for l in out.stdout.split("\n") if "relU" in l]
+    assert len(lines) == 4, out.stdout[-3000:]
+    for l in lines:
+        relU, relP = float(l.split("relU")[1].split()[0]), float(l.split("relP")[1].split()[0])
+        assert relU <= 1e-6 and relP <= 1e-5, l

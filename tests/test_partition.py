@@ -53,6 +53,10 @@ def test_partition_consistency(cav, scheme, W):
             assert np.array_equal(ng[svi[svp[k]:svp[k + 1]]], t.arr("part_nodeGlobal")[off:off + cnt])
             off, cnt = t.arr("recvPoff")[kk], t.arr("recvPcnt")[kk]
             assert np.array_equal(pg[spi[spp[k]:spp[k + 1]]], t.arr("part_presGlobal")[off:off + cnt])
+            if svp[k + 1] > svp[k]:   # peer-memory pushes: my block inside the peer's ghost range
+                assert s.arr("remoteVoff")[k] == t.arr("recvVoff")[kk]
+            if spp[k + 1] > spp[k]:
+                assert s.arr("remotePoff")[k] == off
     assert (ownedV == 1).all() and (ownedP == 1).all()
     pins = [s.i("pinLocal") for s in locs]
     owners = [r for r, s in enumerate(locs) if 0 <= pins[r] < s.i("NNp_owned")]
