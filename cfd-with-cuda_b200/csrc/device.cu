@@ -817,9 +817,10 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
                                              int gwarp, int nwarps, int lane) {
    const int T = A.T, sub = lane % T;
    const SliceRange sr = slice_range(A.nslices, part, gwarp, nwarps);
-   const double* inb[NA];
+   size_t base[NA];
+   double s0[NA], s1[NA];   // dot-product partials stay in registers (no dynamically indexed local arrays in the loop)
 #pragma unroll
-   for (int q = 0; q < NA; q++) inb[q] = in + (size_t)sys[q] * n;
+   for (int q = 0; q < NA; q++) { base[q] = (size_t)sys[q] * n; s0[q] = 0.0; s1[q] = 0.0; }
    for (int s = sr.begin; s < sr.end; s += sr.step) {
       const long long off = A.sliceOff[s];
       const int np = (int)((A.sliceOff[s + 1] - off) >> 6);
@@ -832,7 +833,7 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
          const int2 c2 = ldnc_i2(A.cols + e);
          const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
-         for (int q = 0; q < NA; q++) acc[q] += v2.x * inb[q][c2.x] + v2.y * inb[q][c2.y];
+         for (int q = 0; q < NA; q++) acc[q] += v2.x * in[base[q] + c2.x] + v2.y * in[base[q] + c2.y];
       }
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = lanes_sum(acc[q], T);
@@ -840,12 +841,19 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
       if (sub == 0 && row < n) {
 #pragma unroll
          for (int q = 0; q < NA; q++) {
-            const size_t i = (size_t)sys[q] * n + row;
+            const size_t i = base[q] + row;
             out[i] = acc[q];
-            d0[sys[q]] += l1[i] * acc[q];
-            d1[sys[q]] += acc[q] * acc[q];
+            s0[q] += l1[i] * acc[q];
+            s1[q] += acc[q] * acc[q];
          }
       }
+   }
+#pragma unroll
+   for (int q = 0; q < NA; q++) {
+      const int c = sys[q];   // uniform; resolved with selects, not local-memory indexing
+      if (c == 0) { d0[0] += s0[q]; d1[0] += s1[q]; }
+      else if (c == 1) { d0[1] += s0[q]; d1[1] += s1[q]; }
+      else { d0[2] += s0[q]; d1[2] += s1[q]; }
    }
 }
 __device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, int vidx, int n, const double* in, double* out, const bool (&act)[3],
@@ -862,9 +870,16 @@ __device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
 // CUSP_GMRES_solver -> cusp::krylov::bicgstab, GQ.cu:369-433, x0 = 0).  The three systems share A,
 // so each of the two SpMV phases per iteration streams A once for all still-active right-hand sides.
+// Per-system scalars are block-uniform and live in shared memory (written by thread 0 after each grid
+// reduction), which keeps the register budget for the SpMV sweep.
+struct BicgScalars {
+   double bb[3], rr[3], rrs[3], thresh[3], alpha[3], omega[3];
+   int its[3], act[3], half[3], act2[3];
+};
 __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[6 * 32];
+   __shared__ BicgScalars S;
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
    const int nthreads = gridDim.x * blockDim.x;
    const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
@@ -881,95 +896,120 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    double* AMs = a.w + 6 * N3;
 
    double v6[6] = {0, 0, 0, 0, 0, 0};
-   for (int c = 0; c < 3; c++)
+   for (int c = 0; c < 3; c++) {
+      double acc = 0.0;
       for (int i = tid; i < n; i += nthreads) {
          const size_t k = (size_t)c * n + i;
          const double bi = a.b[k];
          a.x[k] = 0.0;
          r[k] = bi; rs[k] = bi; p[k] = bi;
          ph[k] = a.dinv[i] * bi;
-         v6[c] += bi * bi;
+         acc += bi * bi;
       }
+      v6[c] = acc;
+   }
    grid_sum<6>(grid, v6, buf0, sh);
-   double bb[3], rr[3], rrs[3], thresh[3];
-   int its[3] = {0, 0, 0};
-   bool act[3];
-   for (int c = 0; c < 3; c++) { bb[c] = v6[c]; rr[c] = v6[c]; rrs[c] = v6[c]; thresh[c] = a.tol * sqrt(bb[c]); act[c] = true; }
+   if (threadIdx.x == 0)
+      for (int c = 0; c < 3; c++) {
+         S.bb[c] = S.rr[c] = S.rrs[c] = v6[c];
+         S.thresh[c] = a.tol * sqrt(v6[c]);
+         S.its[c] = 0; S.act[c] = 1; S.half[c] = 0; S.act2[c] = 0; S.alpha[c] = 0.0; S.omega[c] = 0.0;
+      }
+   __syncthreads();
    while (true) {
-      for (int c = 0; c < 3; c++)
-         if (act[c] && (sqrt(rr[c]) <= thresh[c] || its[c] >= a.maxit)) act[c] = false;
-      if (!act[0] && !act[1] && !act[2]) break;
+      if (threadIdx.x == 0)
+         for (int c = 0; c < 3; c++)
+            if (S.act[c] && (sqrt(S.rr[c]) <= S.thresh[c] || S.its[c] >= a.maxit)) S.act[c] = 0;
+      __syncthreads();
+      if (!S.act[0] && !S.act[1] && !S.act[2]) break;
       // ---- AMp = A (M p), d0 = rs . AMp
-      double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
-      bicg_spmv_phase(a.A, a.part, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
-      for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = 0; }
+      {
+         double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+         const bool act[3] = {S.act[0] != 0, S.act[1] != 0, S.act[2] != 0};
+         bicg_spmv_phase(a.A, a.part, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
+         v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = 0; v6[4] = 0; v6[5] = 0;
+      }
       grid_sum<6>(grid, v6, buf1, sh);
-      double alpha[3];
-      for (int c = 0; c < 3; c++) alpha[c] = act[c] ? rrs[c] / v6[c] : 0.0;
+      if (threadIdx.x == 0)
+         for (int c = 0; c < 3; c++) S.alpha[c] = S.act[c] ? S.rrs[c] / v6[c] : 0.0;
+      __syncthreads();
       // ---- s = r - alpha AMp (stored in r), sh = M s, |s|^2
-      for (int c = 0; c < 3; c++) { v6[c] = 0; v6[3 + c] = 0; }
-      for (int c = 0; c < 3; c++)
-         if (act[c])
+      for (int c = 0; c < 3; c++) {
+         double acc = 0.0;
+         if (S.act[c]) {
+            const double alpha = S.alpha[c];
             for (int i = tid; i < n; i += nthreads) {
                const size_t k = (size_t)c * n + i;
-               const double si = r[k] - alpha[c] * AMp[k];
+               const double si = r[k] - alpha * AMp[k];
                r[k] = si;
                shv[k] = a.dinv[i] * si;
-               v6[c] += si * si;
-            }
-      grid_sum<6>(grid, v6, buf0, sh);
-      bool half[3];   // converged at the half step: x += alpha M p and stop
-      bool act2[3];
-      for (int c = 0; c < 3; c++) {
-         half[c] = act[c] && (sqrt(v6[c]) <= thresh[c]);
-         act2[c] = act[c] && !half[c];
-      }
-      // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
-      for (int c = 0; c < 3; c++) { d0[c] = 0; d1[c] = 0; }
-      bicg_spmv_phase(a.A, a.part, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
-      for (int c = 0; c < 3; c++) { v6[c] = d0[c]; v6[3 + c] = d1[c]; }
-      grid_sum<6>(grid, v6, buf1, sh);
-      double omega[3];
-      for (int c = 0; c < 3; c++) omega[c] = act2[c] ? v6[c] / v6[3 + c] : 0.0;
-      // ---- x += alpha M p + omega M s ; r = s - omega AMs ; rs.r , r.r
-      for (int c = 0; c < 3; c++) { v6[c] = 0; v6[3 + c] = 0; }
-      for (int c = 0; c < 3; c++) {
-         if (half[c]) {
-            for (int i = tid; i < n; i += nthreads) {
-               const size_t k = (size_t)c * n + i;
-               a.x[k] += alpha[c] * ph[k];
-            }
-         } else if (act2[c]) {
-            for (int i = tid; i < n; i += nthreads) {
-               const size_t k = (size_t)c * n + i;
-               a.x[k] += alpha[c] * ph[k] + omega[c] * shv[k];
-               const double ri = r[k] - omega[c] * AMs[k];
-               r[k] = ri;
-               v6[c] += rs[k] * ri;
-               v6[3 + c] += ri * ri;
+               acc += si * si;
             }
          }
+         v6[c] = acc; v6[3 + c] = 0.0;
+      }
+      grid_sum<6>(grid, v6, buf0, sh);
+      if (threadIdx.x == 0)
+         for (int c = 0; c < 3; c++) {   // converged at the half step: x += alpha M p and stop
+            S.half[c] = (S.act[c] && sqrt(v6[c]) <= S.thresh[c]) ? 1 : 0;
+            S.act2[c] = (S.act[c] && !S.half[c]) ? 1 : 0;
+         }
+      __syncthreads();
+      // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
+      {
+         double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+         const bool act2[3] = {S.act2[0] != 0, S.act2[1] != 0, S.act2[2] != 0};
+         bicg_spmv_phase(a.A, a.part, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
+         v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = d1[0]; v6[4] = d1[1]; v6[5] = d1[2];
+      }
+      grid_sum<6>(grid, v6, buf1, sh);
+      if (threadIdx.x == 0)
+         for (int c = 0; c < 3; c++) S.omega[c] = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
+      __syncthreads();
+      // ---- x += alpha M p + omega M s ; r = s - omega AMs ; rs.r , r.r
+      for (int c = 0; c < 3; c++) {
+         double a0 = 0.0, a1 = 0.0;
+         const double alpha = S.alpha[c], omega = S.omega[c];
+         if (S.half[c]) {
+            for (int i = tid; i < n; i += nthreads) {
+               const size_t k = (size_t)c * n + i;
+               a.x[k] += alpha * ph[k];
+            }
+         } else if (S.act2[c]) {
+            for (int i = tid; i < n; i += nthreads) {
+               const size_t k = (size_t)c * n + i;
+               a.x[k] += alpha * ph[k] + omega * shv[k];
+               const double ri = r[k] - omega * AMs[k];
+               r[k] = ri;
+               a0 += rs[k] * ri;
+               a1 += ri * ri;
+            }
+         }
+         v6[c] = a0; v6[3 + c] = a1;
       }
       grid_sum<6>(grid, v6, buf0, sh);
       // ---- p = r + beta (p - omega AMp) ; ph = M p
       for (int c = 0; c < 3; c++) {
-         if (half[c]) { its[c]++; act[c] = false; continue; }
-         if (!act2[c]) continue;
-         const double beta = (v6[c] / rrs[c]) * (alpha[c] / omega[c]);
-         rrs[c] = v6[c];
-         rr[c] = v6[3 + c];
+         if (!S.act2[c]) continue;
+         const double omega = S.omega[c];
+         const double beta = (v6[c] / S.rrs[c]) * (S.alpha[c] / omega);
          for (int i = tid; i < n; i += nthreads) {
             const size_t k = (size_t)c * n + i;
-            const double pi = r[k] + beta * (p[k] - omega[c] * AMp[k]);
+            const double pi = r[k] + beta * (p[k] - omega * AMp[k]);
             p[k] = pi;
             ph[k] = a.dinv[i] * pi;
          }
-         its[c]++;
       }
+      __syncthreads();   // every thread has read S.rrs before thread 0 replaces it
+      if (threadIdx.x == 0)
+         for (int c = 0; c < 3; c++) {
+            if (S.half[c]) { S.its[c]++; S.act[c] = 0; }
+            else if (S.act2[c]) { S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++; }
+         }
       grid.sync();
    }
    if (tid == 0)
-      for (int c = 0; c < 3; c++) { a.info[3 + c] = (double)its[c]; a.info[6 + c] = rr[c]; }
+      for (int c = 0; c < 3; c++) { a.info[3 + c] = (double)S.its[c]; a.info[6 + c] = S.rr[c]; }
 }
 
 }   // namespace cfdb

@@ -278,3 +278,50 @@ def test_two_gpu_partitioned_run(peer_memory, tmp_path):
     for l in lines:
         relU, relP = float(l.split("relU")[1].split()[0]), float(l.split("relP")[1].split()[0])
         assert relU <= 1e-6 and relP <= 1e-5, l
+
+
+def test_channel_standin_implicit(mesh):
+    """BASELINE configs[2] stand-in (straight channel, uniform inlet, free outlet, pin at the outlet): implicit scheme
+    against the oracle, Krylov tolerances tightened on both sides (see TIGHT above)."""
+    import fracstep
+    import orc
+    path = mesh("chan_gpu", kind="channel", nx=12, ny=8, nz=8, full_precision=True)
+    o = orc.Oracle(path, "implicit", **TIGHT)
+    s = fracstep.Solver(path, "implicit", opts=fracstep.options(**TIGHT))
+    o.run(3)
+    s.ctx.time_loop(3)
+    U, P = s.ctx.fields()
+    assert rel(U, o.U) <= 1e-6 and rel_free(U, o.U, o) <= 1e-5 and rel(P, o.P) <= 1e-6
+
+
+def test_solver_main_drop_in(mesh, tmp_path):
+    """The whole-program drop-in: ProblemName.txt -> <name>.inp -> monitor table -> <name>.dat, like the reference's
+    executable (BCH.cpp:383-520).  The .dat written at t_final equals the oracle's createTecplot output to 1e-6."""
+    import shutil
+    import subprocess
+    import sys
+    import orc
+    src = mesh("main_q2", n=4, cluster=2.0, t_final=0.003)     # 3 steps of dt = 1e-3
+    shutil.copy(src, tmp_path / "cavity.inp")
+    (tmp_path / "ProblemName.txt").write_text("cavity\n")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import sys; sys.path.insert(0, %r); import fracstep; fracstep.solver_main(%r, 'explicit')" % (
+        os.path.join(root, "cfd-with-cuda_b200"), str(tmp_path))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [l for l in out.stdout.split("\n") if l.strip() and l.split()[0].isdigit()]
+    assert len(rows) == 3 and [int(r.split()[0]) for r in rows] == [1, 2, 3]          # one monitor line per time step
+    assert "Time step  Iter     Time       u_monitor" in out.stdout
+    o = orc.Oracle(src, "explicit")
+    o.run(3)
+    o.write_tecplot(str(tmp_path / "oracle.dat"), "cavity")
+    a = open(tmp_path / "cavity.dat").read().split("\n")
+    b = open(tmp_path / "oracle.dat").read().split("\n")
+    assert a[:3] == b[:3] and len(a) == len(b)
+    NN = o.i("NN")
+    A = np.array([l.split() for l in a[3:3 + NN]], float)
+    B = np.array([l.split() for l in b[3:3 + NN]], float)
+    assert np.array_equal(A[:, :3], B[:, :3])                                           # coordinates: same bytes
+    assert rel(A[:, 3:6], B[:, 3:6]) <= 1e-6 and rel(A[:, 6], B[:, 6]) <= 1e-5
+    assert a[3 + NN:] == b[3 + NN:]                                                     # connectivity: same bytes
