@@ -44,12 +44,14 @@ def full(path):
             if k in h:
                 print("%-85s %-14s %s" % (k, u[h.index(k)], v[h.index(k)]))
         try:
-            r = float(v[h.index("dram__bytes_read.sum")].replace(",", ""))
-            w = float(v[h.index("dram__bytes_write.sum")].replace(",", ""))
-            t = float(v[h.index("gpu__time_duration.sum")].replace(",", ""))
-            print("derived: dram read+write = %.4g %s over %.4g %s" % (r + w, u[h.index("dram__bytes_read.sum")], t, u[h.index("gpu__time_duration.sum")]))
-        except Exception:
-            pass
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            tm = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+            r = float(v[h.index("dram__bytes_read.sum")].replace(",", "")) * mult[u[h.index("dram__bytes_read.sum")]]
+            w = float(v[h.index("dram__bytes_write.sum")].replace(",", "")) * mult[u[h.index("dram__bytes_write.sum")]]
+            t = float(v[h.index("gpu__time_duration.sum")].replace(",", "")) * tm[u[h.index("gpu__time_duration.sum")]]
+            print("derived: dram read+write = %.4g bytes per launch over %.4g s -> %.1f GB/s (under the profiler)" % (r + w, t, (r + w) / t / 1e9))
+        except Exception as e:
+            print("derived: n/a (%s)" % e)
 
 
 if __name__ == "__main__":
