@@ -2100,7 +2100,7 @@ int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, con
    CFD_CK(cudaGetDeviceCount(&ndev));
    if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
    SellHost h;
-   sell_build_host(nrows, ncols, rowStarts, col, 1, h);
+   sell_build_host(nrows, ncols, rowStarts, col, choose_T(nrows, rowStarts[nrows]), h);
    Sell A;
    const double* v[1] = {val};
    int rc = sell_upload(h, 1, v, A);

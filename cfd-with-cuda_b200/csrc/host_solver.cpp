@@ -11,6 +11,7 @@
 #include <fstream>
 
 #include <omp.h>
+#include <sched.h>
 
 #include <thread>
 
@@ -352,7 +353,12 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
       // one process per GPU: launchers such as torchrun pin OMP_NUM_THREADS=1; give each rank its share of the cores
       int want = 0;
       if (const char* e = getenv("CFD_HOST_THREADS")) want = atoi(e);
-      if (want <= 0 && world > 1) want = std::max(1u, std::thread::hardware_concurrency() / (unsigned)world);
+      if (want <= 0 && world > 1) {
+         cpu_set_t set;
+         int ncpu = (int)std::thread::hardware_concurrency();
+         if (sched_getaffinity(0, sizeof set, &set) == 0) ncpu = CPU_COUNT(&set);   // what `nproc` reports (cpuset-aware)
+         want = std::max(1, ncpu / world);
+      }
       if (want > 0) omp_set_num_threads(want);
    }
    generate_midnodes(s->mesh);
