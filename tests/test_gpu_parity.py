@@ -325,3 +325,65 @@ def test_solver_main_drop_in(mesh, tmp_path):
     assert np.array_equal(A[:, :3], B[:, :3])                                           # coordinates: same bytes
     assert rel(A[:, 3:6], B[:, 3:6]) <= 1e-6 and rel(A[:, 6], B[:, 6]) <= 1e-5
     assert a[3 + NN:] == b[3 + NN:]                                                     # connectivity: same bytes
+
+
+def test_reference_gpu_build_switches(mesh):
+    """The reference's own GPU build differs from its CPU build: CG warm start from the previous
+    Pdot (BCH.cu:418-451) and maxAcc without the 1/dt factor (BCH.cu:107-117).  Both are switches on both sides."""
+    import fracstep
+    import orc
+    path = mesh("q2_c4", **CASES["q2_c4"])
+    o = orc.Oracle(path, "explicit", cg_warm=1, maxacc_rule=1)
+    c = fracstep.Context(fracstep.Problem(o, "explicit"), fracstep.options(cg_warm_start=1, maxacc_rule=1))
+    o.run(4)
+    reps = c.time_loop(4)
+    U, P = c.fields()
+    assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-6
+    assert abs(sum(r["cg_iterations"] for r in reps) - int(o.arr("cgIters").sum())) <= 2 * len(o.arr("cgIters"))
+    assert abs(reps[-1]["maxAcc"] - o.d("maxAcc")) <= 1e-5 * o.d("maxAcc")
+    # warm start must actually save iterations compared with the zero start
+    o0 = orc.Oracle(path, "explicit")
+    o0.run(4)
+    assert o.arr("cgIters").sum() < o0.arr("cgIters").sum()
+
+
+def test_no_pressure_pin_and_restart(mesh, tmp_path):
+    """Edge cases of the input grammar: pin node 0 (1-based; 0-based -1 = "no pin", and node 1 = 0-based 0 is never
+    pinned either, BCH.cpp:4172) and a restart from <name>_restart.dat (isRestart 1, BCH.cpp:4214-4242)."""
+    import shutil
+    import fracstep
+    import orc
+    src = open(mesh("q1_u8", **CASES["q1_u8"])).read()
+    lines = src.split("\n")
+    k = lines.index("Node number where pressure is taken to be zero")
+    for pin in ("0", "1"):
+        lines[k + 1] = pin
+        p = tmp_path / ("nopin%s.inp" % pin)
+        p.write_text("\n".join(lines))
+        o = orc.Oracle(str(p), "implicit")
+        s = fracstep.Solver(str(p), "implicit")
+        assert s.i("pinLocal") == -1
+        o.run(2)
+        reps = s.ctx.time_loop(2)
+        U, P = s.ctx.fields()
+        # without a pin the pressure is defined up to a constant: compare after removing the mean
+        assert rel(U, o.U) <= 1e-6 and rel(P - P.mean(), o.P - o.P.mean()) <= 1e-4
+        assert all(abs(r["cg_iterations"] - k) <= 2 for r, k in zip(reps, o.arr("cgIters")))
+    # restart: run 2 steps, write the Tecplot file, restart a new solver from it and continue 2 steps
+    base = mesh("q2_c4", **CASES["q2_c4"])
+    a = fracstep.Solver(base, "explicit")
+    a.ctx.time_loop(2)
+    rdir = tmp_path / "restart"
+    rdir.mkdir()
+    a.write_tecplot(str(rdir / "cav_restart.dat"), "cav")
+    (rdir / "cav.inp").write_text(open(base).read().replace("isRestart: 0", "isRestart: 1"))
+    b = fracstep.Solver(str(rdir / "cav.inp"), "explicit")
+    Ua, Pa = a.ctx.fields()
+    Ub, Pb = b.ctx.fields()
+    assert np.allclose(Ub, Ua, rtol=2e-11, atol=1e-300) and np.allclose(Pb, Pa, rtol=2e-11, atol=1e-300)   # 11 digits in the file
+    o = orc.Oracle(str(rdir / "cav.inp"), "explicit")
+    o.read_restart(str(rdir / "cav_restart.dat"))
+    o.run(2)
+    b.ctx.time_loop(2)
+    Ub, Pb = b.ctx.fields()
+    assert rel(Ub, o.U) <= 1e-6 and rel(Pb, o.P) <= 1e-5
