@@ -31,16 +31,18 @@ WORKLOADS = {
     # configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (30^3 Q2/Q1, sinh clustering 2.0)
     "ne27000_explicit": dict(n=30, NENv=27, scheme="explicit", cluster=2.0, viscosity=0.01, dt=1e-3, inp=True),
     "ne27000_implicit": dict(n=30, NENv=27, scheme="implicit", cluster=2.0, viscosity=0.001, dt=1e-3, inp=True),
+    # configs[2]: stand-in for the missing bendingSquareDuct_49x33x33.inp (straight 48x32x32 channel, DESIGN.md / BASELINE.md C3)
+    "channel_48x32x32_implicit": dict(n=48, ny=32, nz=32, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3, inp=True, channel=True),
 }
 DEFAULT_WORKLOAD = "cavity256_q1_implicit"
 CPU_SAMPLE_N = 64   # mesh edge of the bounded CPU sample for workloads larger than this
 
 
 def sizes(w):
-    n, q2 = w["n"], w["NENv"] == 27
-    NN = (2 * n + 1) ** 3 if q2 else (n + 1) ** 3
-    NNp = (n + 1) ** 3
-    return dict(NE=n ** 3, NN=NN, NNp=NNp, DOF=3 * NN + NNp)
+    nx, ny, nz, q2 = w["n"], w.get("ny", w["n"]), w.get("nz", w["n"]), w["NENv"] == 27
+    NN = (2 * nx + 1) * (2 * ny + 1) * (2 * nz + 1) if q2 else (nx + 1) * (ny + 1) * (nz + 1)
+    NNp = (nx + 1) * (ny + 1) * (nz + 1)
+    return dict(NE=nx * ny * nz, NN=NN, NNp=NNp, DOF=3 * NN + NNp)
 
 
 class ClockSampler:
@@ -115,6 +117,11 @@ def ncu_traffic(workload, kernel_class):
 
 def make_inp(w, path, n=None):
     import meshgen
+    if w.get("channel"):
+        f = 1.0 if n is None else n / float(w["n"])
+        meshgen.channel(path, nx=max(2, int(w["n"] * f)), ny=max(2, int(w["ny"] * f)), nz=max(2, int(w["nz"] * f)), NENv=w["NENv"],
+                        viscosity=w["viscosity"], dt=w["dt"])
+        return
     meshgen.cube(path, n or w["n"], cluster=w["cluster"], NENv=w["NENv"], viscosity=w["viscosity"], dt=w["dt"],
                  full_precision=not w.get("inp", False))
 
@@ -146,7 +153,7 @@ def run_oracle(w, steps, warmup, n, threads=0):
 def cpu_sample(w, steps, warmup):
     n_s = min(w["n"], CPU_SAMPLE_N)
     sec, info = run_oracle(w, steps, warmup, n_s)
-    scale = (n_s ** 3) / float(w["n"] ** 3)   # per-step work ~ elements (Krylov iteration growth with n ignored: favours the CPU)
+    scale = (n_s / float(w["n"])) ** 3   # per-step work ~ elements (Krylov iteration growth with n ignored: favours the CPU)
     sample = ("oracle (C++/OpenMP restatement of the reference CPU path), %d^3 %s %s mesh, %d timed steps after %d warm-up"
               % (n_s, "Q2/Q1" if w["NENv"] == 27 else "Q1/Q1", w["scheme"], steps, warmup))
     if n_s != w["n"]:
@@ -169,7 +176,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = dict(workload=a.workload, scheme=w["scheme"], element="Q2/Q1" if w["NENv"] == 27 else "Q1/Q1", mesh="%d^3 hex cavity" % w["n"],
+    config = dict(workload=a.workload, scheme=w["scheme"], element="Q2/Q1" if w["NENv"] == 27 else "Q1/Q1",
+                  mesh=("%dx%dx%d hex channel" % (w["n"], w["ny"], w["nz"])) if w.get("channel") else "%d^3 hex cavity" % w["n"],
                   NE=sz["NE"], DOF=sz["DOF"], dt=w["dt"], viscosity=w["viscosity"],
                   krylov="Jacobi-PCG 1e-6/1000 (pressure)" + (", Jacobi-BiCGStab 1e-6/1000 x3 (momentum)" if w["scheme"] == "implicit" else ""))
 

@@ -37,7 +37,8 @@ int choose_T(int nrows, long long nnz) {
    if (nrows <= 0) return 1;
    const double avg = (double)nnz / nrows;
    int T = 1;
-   while ((long long)nrows * T < 120000 && T < 8 && avg / (2 * T) >= 8.0) T *= 2;
+   // enough (row, lane) pairs for >= 4 slices per resident warp of the persistent kernels, at least ~8 entries per lane
+   while ((long long)nrows * T < 2000000 && T < 8 && avg / (2 * T) >= 4.0) T *= 2;
    return T;
 }
 
@@ -430,12 +431,16 @@ __device__ __forceinline__ void ebe_gauss_b(const int (&nd)[NV], int NN, const d
 
 // R1 = -C(Uadv) * Ux   (calculateMatrixAGPU, BCH.cu:906-939; R1 must be zeroed first).  Scatter by
 // FP64 atomicAdd (RED.ADD.F64) instead of the reference's 8 coloured launches.
-template <int NV>
+// ATOMIC = false: the launch covers one colour (elist = its elements, no two share a node): plain read-modify-write,
+// bitwise reproducible -- the reference's scatter scheme with a valid colouring.
+template <int NV, bool ATOMIC>
 __global__ void __launch_bounds__(128) k_ebe_convect_apply(int NE, int NN, int ldE, const int* __restrict__ LtoGT,
                                                            const double* __restrict__ coord, const double* __restrict__ Uadv,
-                                                           const double* __restrict__ Ux, double* __restrict__ R1) {
-   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-   if (e >= NE) return;
+                                                           const double* __restrict__ Ux, double* __restrict__ R1,
+                                                           const int* __restrict__ elist) {
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= NE) return;
+   const int e = elist ? elist[t] : t;
    int nd[NV];
 #pragma unroll
    for (int i = 0; i < NV; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
@@ -464,19 +469,22 @@ __global__ void __launch_bounds__(128) k_ebe_convect_apply(int NE, int NN, int l
          double r = 0;
 #pragma unroll
          for (int k = 0; k < 8; k++) r += Tab<NV>::Sv(k, i) * t[k];
-         atomicAdd(R1 + (long long)c * NN + nd[i], -r);
+         if (ATOMIC) atomicAdd(R1 + (long long)c * NN + nd[i], -r);
+         else R1[(long long)c * NN + nd[i]] -= r;
       }
    }
 }
 
 // A += C(Uadv) assembled into the Sell value array through the element map
 // (calculateMatrixAGPU + calcAndAssembleMatrixA, GQ.cu:590-754).
-template <int NV>
+template <int NV, bool ATOMIC>
 __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, int ldE, const int* __restrict__ LtoGT,
                                                               const double* __restrict__ coord, const double* __restrict__ Uadv,
-                                                              const int* __restrict__ mapT, double* __restrict__ Aval) {
-   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-   if (e >= NE) return;
+                                                              const int* __restrict__ mapT, double* __restrict__ Aval,
+                                                              const int* __restrict__ elist) {
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= NE) return;
+   const int e = elist ? elist[t] : t;
    double b[8][3];
    {
       int nd[NV];
@@ -493,7 +501,10 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
 #pragma unroll
          for (int k = 0; k < 8; k++) a += Tab<NV>::Sv(k, i) * cj[k];
          const int pos = __ldg(mapT + (long long)(i * NV + j) * ldE + e);
-         if (pos >= 0) atomicAdd(Aval + pos, a);   // -1: row owned by another rank
+         if (pos >= 0) {   // -1: row owned by another rank
+            if (ATOMIC) atomicAdd(Aval + pos, a);
+            else Aval[pos] += a;
+         }
       }
    }
 }
@@ -1290,16 +1301,34 @@ int fetch_kinfo(cfd_ctx* c) {
 template <int NV>
 int launch_ebe_apply(cfd_ctx* c, const double* Uadv, const double* Ux, double* R1) {
    const int NE = c->NEa;   // elements touching an owned node
-   k_ebe_convect_apply<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, Ux, R1);
-   c->launches++;
+   if (c->opt.ebe_scatter == 1) {
+      for (size_t k = 0; k + 1 < c->colorStart.size(); k++) {
+         const int n = c->colorStart[k + 1] - c->colorStart[k];
+         k_ebe_convect_apply<NV, false><<<gridFor(n, 128), 128, 0, c->stream>>>(n, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, Ux, R1,
+                                                                                c->elemOfColor + c->colorStart[k]);
+         c->launches++;
+      }
+   } else {
+      k_ebe_convect_apply<NV, true><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, Ux, R1, nullptr);
+      c->launches++;
+   }
    CFD_CK(cudaGetLastError());
    return CFD_OK;
 }
 template <int NV>
 int launch_ebe_assemble(cfd_ctx* c, const double* Uadv, double* Aval) {
    const int NE = c->NEa;
-   k_ebe_convect_assemble<NV><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, c->mapT, Aval);
-   c->launches++;
+   if (c->opt.ebe_scatter == 1) {
+      for (size_t k = 0; k + 1 < c->colorStart.size(); k++) {
+         const int n = c->colorStart[k + 1] - c->colorStart[k];
+         k_ebe_convect_assemble<NV, false><<<gridFor(n, 128), 128, 0, c->stream>>>(n, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, c->mapT, Aval,
+                                                                                   c->elemOfColor + c->colorStart[k]);
+         c->launches++;
+      }
+   } else {
+      k_ebe_convect_assemble<NV, true><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->P.NN, c->ldE, c->LtoGT, c->coord, Uadv, c->mapT, Aval, nullptr);
+      c->launches++;
+   }
    CFD_CK(cudaGetLastError());
    return CFD_OK;
 }
@@ -1504,6 +1533,40 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       for (int e = 0; e < NE; e++)
          for (int i = 0; i < nv; i++) lt[(size_t)i * c->ldE + e] = P->LtoGnode[(size_t)e * nv + i];
       TRY(dupload(c, &c->LtoGT, lt.data(), lt.size()));
+      if (o.ebe_scatter == 1) {
+         // A VALID greedy colouring over corner-sharing neighbours (every shared node of two hexahedra lies on a shared
+         // face/edge/corner and so implies a shared corner).  Unlike setupMeshColoring (BCH.cpp:853-947) the scan restarts
+         // from the first neighbour after a clash, so no same-coloured neighbours can remain.
+         const int NEa = c->NEa;
+         std::vector<int> start((size_t)NN + 1, 0), items((size_t)NEa * 8), color(NEa, -1);
+         for (int e = 0; e < NEa; e++)
+            for (int i = 0; i < 8; i++) start[P->LtoGnode[(size_t)e * nv + i] + 1]++;
+         for (int i = 0; i < NN; i++) start[i + 1] += start[i];
+         {
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            for (int e = 0; e < NEa; e++)
+               for (int i = 0; i < 8; i++) items[fill[P->LtoGnode[(size_t)e * nv + i]]++] = e;
+         }
+         int ncol = 0;
+         for (int e = 0; e < NEa; e++) {
+            unsigned long long used = 0;
+            for (int i = 0; i < 8; i++) {
+               const int node = P->LtoGnode[(size_t)e * nv + i];
+               for (int t = start[node]; t < start[node + 1]; t++)
+                  if (color[items[t]] >= 0) used |= 1ull << color[items[t]];
+            }
+            int cc = 0;
+            while (cc < 63 && (used >> cc & 1ull)) cc++;
+            color[e] = cc;
+            ncol = std::max(ncol, cc + 1);
+         }
+         c->colorStart.assign((size_t)ncol + 1, 0);
+         for (int e = 0; e < NEa; e++) c->colorStart[color[e] + 1]++;
+         for (int k = 0; k < ncol; k++) c->colorStart[k + 1] += c->colorStart[k];
+         std::vector<int> eoc(NEa), fill(c->colorStart.begin(), c->colorStart.end() - 1);
+         for (int e = 0; e < NEa; e++) eoc[fill[color[e]]++] = e;
+         TRY(dupload(c, &c->elemOfColor, eoc.data(), eoc.size()));
+      }
       TRY(dupload(c, &c->coord, P->coord, (size_t)NN * 3));
       std::vector<int> bi(NN, -1), bn;
       for (int i = 0; i < P->BCnVelNodes; i++) {

@@ -84,6 +84,8 @@ struct cfd_ctx {
    double* coord = nullptr;     // [NN][3]
    int* mapT = nullptr;         // implicit: [NENv*NENv][ldE] SELL positions of A entries
    int* diagPosA = nullptr;     // implicit: [NN] SELL position of the diagonal
+   int* elemOfColor = nullptr;  // [NEa] elements grouped by colour (ebe_scatter = 1)
+   std::vector<int> colorStart; // [ncolors+1]
    int* bcIndex = nullptr;      // [NN] whichBC or -1
    int* bcNodes = nullptr;      // [BCnVelNodes]
    double* BCstr = nullptr;     // [nBC][3]

@@ -107,7 +107,9 @@ typedef struct cfd_options {
    int bicg_maxit;    /* default 1000 */
    int maxacc_rule;   /* 0 (default) = max|dU|/dt (BCH.cpp:3053); 1 = max|dU| (BCH.cu:107-117) */
    int device;        /* CUDA device ordinal; -1 = current device */
-   int reserved[8];
+   int ebe_scatter;   /* element-by-element scatter: 0 (default) = FP64 atomicAdd, one launch; 1 = element colouring, one launch
+                         per colour, plain stores, bitwise reproducible (the reference's scheme, BCH.cu:906-939) */
+   int reserved[7];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 
