@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
       xc.xstate[0] = epoch; xc.xstate[1] = hepoch;
-   }
+   }   // (xstate[3] = ticket counter, back to 0 after every reduction)
 }
 
 // Diagnostic: cost of the grid-wide primitives the persistent Krylov kernels are built from.

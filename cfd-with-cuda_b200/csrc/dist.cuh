@@ -394,31 +394,97 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* f, unsigned 
    }
 }
 
-// Sum N values over all blocks of all ranks; the result is bit-identical in every block of every rank
-// (local partials in block order, then ranks in rank order).
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+   unsigned long long v;
+   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+
+// Sum N (<= 4) values over all blocks of all ranks; the result is bit-identical in every block of every rank
+// (local partials in a fixed order, then ranks in rank order), so every block takes the same branches.
+// One fused barrier instead of "local grid reduction, then exchange":
+//   * every block publishes its partial and takes a ticket; the LAST block to arrive reduces the partials and
+//     delivers this rank's sums to every rank's mailbox (its own included)
+//   * delivery uses flag-in-data words (low / high half of the double + the 32-bit epoch in one 8-byte store, the
+//     scheme of NCCL's LL protocol): no fence and no separate flag, one NVLink traversal
+//   * every block polls its own mailbox; seeing all ranks' words of this epoch implies that every block of every
+//     rank has finished the phase before the reduction -> this IS the grid + cross-GPU barrier
 template <int N>
 __device__ __forceinline__ void xgrid_sum(cg::grid_group& grid, double (&v)[N], double* buf, double* sh, const XComm& xc,
                                           unsigned long long& epoch) {
-   grid_sum<N>(grid, v, buf, sh);
+   (void)grid;
+   __shared__ int s_last;
+   block_sum<N>(v, sh);
    epoch++;
+   const unsigned long long tag = (epoch & 0xffffffffull) << 32;
    const int slot = (int)(epoch % 3);
-   char* mine = xc.peerWin[xc.rank];
-   if (blockIdx.x == 0 && threadIdx.x < xc.world) {   // thread q delivers this rank's sums to rank q
-      char* w = xc.peerWin[threadIdx.x];
-      double* mb = win_mail(w, slot, xc.rank);
+   const int G = gridDim.x;
+   unsigned int* ticket = (unsigned int*)(xc.xstate + 3);
+   if (threadIdx.x == 0) {
 #pragma unroll
-      for (int i = 0; i < N; i++) st_sys_f64(mb + i, v[i]);
-      __threadfence_system();
-      st_rel_sys(win_arflag(w, slot, xc.rank), epoch);
+      for (int i = 0; i < N; i++) buf[(size_t)i * G + blockIdx.x] = v[i];
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == (unsigned)(G - 1)) ? 1 : 0;
    }
-   if (threadIdx.x < xc.world) wait_flag(win_arflag(mine, slot, threadIdx.x), epoch, xc.xstate + 2);
+   __syncthreads();
+   if (s_last && threadIdx.x < 32) {
+      __threadfence();
+      if (threadIdx.x == 0) *ticket = 0u;   // nobody takes a ticket again before this reduction has been delivered
+      double tot[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+         double s = 0.0;
+         for (int b = threadIdx.x; b < G; b += 32) s += __ldcg(buf + (size_t)i * G + b);
+         tot[i] = warp_sum(s);
+      }
+      if (threadIdx.x < xc.world) {   // lane q delivers to rank q
+         unsigned long long* mb = (unsigned long long*)win_mail(xc.peerWin[threadIdx.x], slot, xc.rank);
+#pragma unroll
+         for (int i = 0; i < N; i++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[i]);
+            st_sys_u64(mb + 2 * i, tag | (bits & 0xffffffffull));
+            st_sys_u64(mb + 2 * i + 1, tag | (bits >> 32));
+         }
+      }
+   }
+   if (threadIdx.x < 32) {
+      double mine[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) mine[i] = 0.0;
+      if (threadIdx.x < xc.world) {
+         const unsigned long long* mb = (const unsigned long long*)win_mail(xc.peerWin[xc.rank], slot, threadIdx.x);
+         const unsigned long long t0 = gtimer();
+         unsigned spins = 0;
+#pragma unroll
+         for (int i = 0; i < N; i++) {
+            unsigned long long lo, hi;
+            while (true) {
+               lo = ld_sys_u64(mb + 2 * i);
+               hi = ld_sys_u64(mb + 2 * i + 1);
+               if ((lo >> 32) == (tag >> 32) && (hi >> 32) == (tag >> 32)) break;
+               if ((++spins & 255u) == 0) {
+                  if (*(volatile unsigned long long*)(xc.xstate + 2)) break;
+                  if (gtimer() - t0 > 4000000000ull) { *(volatile unsigned long long*)(xc.xstate + 2) = 1; break; }
+               }
+            }
+            mine[i] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+         }
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+         double s = 0.0;
+         for (int q = 0; q < xc.world; q++) s += __shfl_sync(0xffffffffu, mine[i], q);   // rank order
+         if (threadIdx.x == 0) sh[i] = s;
+      }
+      if (threadIdx.x == 0) __threadfence();   // acquire side: drops this SM's L1 lines before the block reads other blocks' data
+   }
    __syncthreads();
 #pragma unroll
-   for (int i = 0; i < N; i++) {
-      double s = 0.0;
-      for (int q = 0; q < xc.world; q++) s += ld_sys_f64(win_mail(mine, slot, q) + i);
-      v[i] = s;
-   }
+   for (int i = 0; i < N; i++) v[i] = sh[i];
+   __syncthreads();
 }
 
 // p <- values (owned rows), pushed to the neighbours' ghost entries; then signal and wait for their pushes.
