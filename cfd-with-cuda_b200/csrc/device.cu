@@ -61,24 +61,65 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
    Sell& m = out.meta;
    m.nrows = nrows; m.ncols = ncols; m.T = T; m.R = R; m.nslices = ns; m.nnz = rs[nrows];
    out.sliceOff.assign((size_t)ns + 1, 0);
+   out.colOff.assign((size_t)ns, 0);
    std::vector<int> width(ns, 0);
-#pragma omp parallel for schedule(static)
-   for (int s = 0; s < ns; s++) {
-      int w = 0;
-      for (int rl = 0; rl < R; rl++) {
-         const int r = s * R + rl;
-         if (r < nrows) w = std::max(w, (rs[r + 1] - rs[r] + T - 1) / T);
+   std::vector<unsigned char> comp(ns, 0);
+   std::vector<std::vector<int> > uni(ns);   // offset list of the compressed slices
+   const bool allowComp = (T == 1) && getenv("CFD_NO_COLCOMP") == nullptr;
+#pragma omp parallel
+   {
+      std::vector<int> u;
+#pragma omp for schedule(static)
+      for (int s = 0; s < ns; s++) {
+         int w = 0;
+         for (int rl = 0; rl < R; rl++) {
+            const int r = s * R + rl;
+            if (r < nrows) w = std::max(w, (rs[r + 1] - rs[r] + T - 1) / T);
+         }
+         width[s] = (w + 1) & ~1;
+         if (!allowComp || w == 0) continue;
+         // union of the (col - row) offsets over the slice's rows
+         u.clear();
+         for (int rl = 0; rl < R; rl++) {
+            const int r = s * R + rl;
+            if (r >= nrows) break;
+            for (int k = rs[r]; k < rs[r + 1]; k++) u.push_back(col[k] - r);
+         }
+         std::sort(u.begin(), u.end());
+         u.erase(std::unique(u.begin(), u.end()), u.end());
+         const int wc = ((int)u.size() + 1) & ~1;
+         // worth it while the extra zero values (8 B each) cost less than the saved indices (4 B each)
+         if (4 * wc <= 5 * width[s]) { comp[s] = 1; width[s] = wc; uni[s] = u; }
       }
-      width[s] = (w + 1) & ~1;
    }
-   for (int s = 0; s < ns; s++) out.sliceOff[s + 1] = out.sliceOff[s] + (long long)width[s] * 32;
+   long long cpos = 0;
+   for (int s = 0; s < ns; s++) {
+      out.sliceOff[s + 1] = out.sliceOff[s] + (long long)width[s] * 32;
+      out.colOff[s] = cpos | (comp[s] ? 1 : 0);
+      cpos += comp[s] ? width[s] : (long long)width[s] * 32;
+      out.compressedSlices += comp[s];
+   }
    m.padded = out.sliceOff[ns];
-   out.cols.assign((size_t)m.padded, 0);
+   out.cols.assign((size_t)std::max<long long>(cpos, 2), 0);
    out.perm.assign((size_t)m.nnz, 0);
 #pragma omp parallel for schedule(static)
    for (int s = 0; s < ns; s++) {
       const long long off = out.sliceOff[s];
+      const long long co = out.colOff[s] & ~1LL;
       const int w = width[s];
+      if (comp[s]) {
+         const std::vector<int>& u = uni[s];
+         for (int j = 0; j < w; j++) out.cols[(size_t)co + j] = j < (int)u.size() ? u[j] : 0;   // offset 0 = the row itself (val 0)
+         for (int rl = 0; rl < R; rl++) {
+            const int r = s * R + rl;
+            if (r >= nrows) break;
+            for (int k = rs[r]; k < rs[r + 1]; k++) {
+               const int j = (int)(std::lower_bound(u.begin(), u.end(), col[k] - r) - u.begin());
+               out.perm[(size_t)k] = off + (long long)(j >> 1) * 64 + 2 * rl + (j & 1);
+            }
+         }
+         continue;
+      }
       for (int rl = 0; rl < R; rl++) {
          const int r = s * R + rl;
          const int len = (r < nrows) ? rs[r + 1] - rs[r] : 0;
@@ -86,13 +127,13 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
          for (int lane = 0; lane < T; lane++) {
             const int t = rl * T + lane;
             for (int j = 0; j < w; j++) {
-               const long long pos = off + (long long)(j >> 1) * 64 + 2 * t + (j & 1);
+               const long long rel = (long long)(j >> 1) * 64 + 2 * t + (j & 1);
                const int k = j * T + lane;
                if (k < len) {
-                  out.cols[pos] = col[rs[r] + k];
-                  out.perm[(size_t)rs[r] + k] = pos;
+                  out.cols[(size_t)(co + rel)] = col[rs[r] + k];
+                  out.perm[(size_t)rs[r] + k] = off + rel;
                } else {
-                  out.cols[pos] = padcol;
+                  out.cols[(size_t)(co + rel)] = padcol;
                }
             }
          }
@@ -105,6 +146,8 @@ int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell&
    d.nval = nval;
    CFD_CK(cudaMalloc(&d.sliceOff, sizeof(long long) * h.sliceOff.size()));
    CFD_CK(cudaMemcpy(d.sliceOff, h.sliceOff.data(), sizeof(long long) * h.sliceOff.size(), cudaMemcpyHostToDevice));
+   CFD_CK(cudaMalloc(&d.colOff, sizeof(long long) * std::max<size_t>(h.colOff.size(), 1)));
+   CFD_CK(cudaMemcpy(d.colOff, h.colOff.data(), sizeof(long long) * h.colOff.size(), cudaMemcpyHostToDevice));
    CFD_CK(cudaMalloc(&d.cols, sizeof(int) * std::max<size_t>(h.cols.size(), 2)));
    CFD_CK(cudaMemcpy(d.cols, h.cols.data(), sizeof(int) * h.cols.size(), cudaMemcpyHostToDevice));
    std::vector<double> tmp;
@@ -124,7 +167,7 @@ int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell&
 }
 
 void sell_free(Sell& s) {
-   cudaFree(s.sliceOff); cudaFree(s.cols);
+   cudaFree(s.sliceOff); cudaFree(s.colOff); cudaFree(s.cols);
    for (int v = 0; v < 3; v++) cudaFree(s.vals[v]);
    s = Sell();
 }
@@ -175,6 +218,29 @@ __device__ __forceinline__ const double* sell_vals(const Sell& A, int vidx) {
    return vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);   // no dynamic indexing of the by-value struct
 }
 
+// Column access of one lane inside one slice: explicit pairs, or the slice's shared offset list added to the row.
+struct ColCursor {
+   const int* base;
+   int cmp, row, hi;
+};
+__device__ __forceinline__ ColCursor col_cursor(const Sell& A, int slice, int lane) {
+   ColCursor cc;
+   const long long co = A.colOff[slice];
+   cc.cmp = (int)(co & 1);
+   cc.base = A.cols + (co & ~1LL) + (cc.cmp ? 0 : 2 * lane);
+   cc.row = slice * A.R + lane / A.T;
+   cc.hi = A.ncols - 1;
+   return cc;
+}
+__device__ __forceinline__ int2 col_pair(const ColCursor& cc, int jp) {
+   if (cc.cmp) {   // warp-uniform branch; the 8-byte offset pair is a broadcast load that stays in L1
+      const int2 o = __ldg(reinterpret_cast<const int2*>(cc.base) + jp);
+      // padded entries (value 0) of rows near the ends of the matrix may point outside: clamp
+      return make_int2(min(max(cc.row + o.x, 0), cc.hi), min(max(cc.row + o.y, 0), cc.hi));
+   }
+   return ldnc_i2(cc.base + ((long long)jp << 6));
+}
+
 // y_c = alpha * A x_c + beta * y_c for NV vectors sharing one Sell value array (vectors are
 // component-blocked with stride ldx / ldy).  Multi-RHS: the matrix stream is read once.
 template <int NV>
@@ -188,10 +254,11 @@ __global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const doub
    double acc[NV];
 #pragma unroll
    for (int c = 0; c < NV; c++) acc[c] = 0.0;
+   const ColCursor cc = col_cursor(A, m.slice, m.lane);
 #pragma unroll 4
    for (int jp = 0; jp < np; jp++) {
       const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = ldnc_i2(A.cols + e);
+      const int2 c2 = col_pair(cc, jp);
       const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
       for (int c = 0; c < NV; c++) acc[c] += v2.x * __ldg(x + c * ldx + c2.x) + v2.y * __ldg(x + c * ldx + c2.y);
@@ -213,10 +280,11 @@ __device__ __forceinline__ void lane_dot_k3(const Sell& K, const double* __restr
                                             long long NN, double& a0, double& a1, double& a2) {
    const long long off = K.sliceOff[m.slice];
    const int np = (int)((K.sliceOff[m.slice + 1] - off) >> 6);
+   const ColCursor cc = col_cursor(K, m.slice, m.lane);
 #pragma unroll 4
    for (int jp = 0; jp < np; jp++) {
       const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = ldnc_i2(K.cols + e);
+      const int2 c2 = col_pair(cc, jp);
       const double2 v2 = ldnc_d2(val + e);
       a0 += v2.x * __ldg(U + c2.x) + v2.y * __ldg(U + c2.y);
       a1 += v2.x * __ldg(U + NN + c2.x) + v2.y * __ldg(U + NN + c2.y);
@@ -229,10 +297,11 @@ template <typename PF>
 __device__ __forceinline__ void lane_dot_g3(const Sell& G, const RowMap& m, PF pf, double sign, double& a0, double& a1, double& a2) {
    const long long off = G.sliceOff[m.slice];
    const int np = (int)((G.sliceOff[m.slice + 1] - off) >> 6);
+   const ColCursor cc = col_cursor(G, m.slice, m.lane);
 #pragma unroll 2
    for (int jp = 0; jp < np; jp++) {
       const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = ldnc_i2(G.cols + e);
+      const int2 c2 = col_pair(cc, jp);
       const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
       const double px = sign * pf(c2.x), py = sign * pf(c2.y);
       a0 += g1.x * px + g1.y * py;
@@ -352,9 +421,10 @@ __global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const
    const long long off = GT.sliceOff[slice];
    const int np = (int)((GT.sliceOff[slice + 1] - off) >> 6);
    double acc = 0.0;
+   const ColCursor cc = col_cursor(GT, slice, lane);
    for (int jp = 0; jp < np; jp++) {
       const long long e = off + ((long long)jp << 6) + 2 * lane;
-      const int2 c2 = ldnc_i2(GT.cols + e);
+      const int2 c2 = col_pair(cc, jp);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
          const double2 g = ldnc_d2(GT.vals[c] + e);
@@ -510,7 +580,7 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
 }
 
 // Dirichlet rows of A -> identity rows (applyVelBC_LHS, GQ.cu:478-498), on the Sell layout.
-__global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restrict__ bcNodes) {
+__global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restrict__ bcNodes, const int* __restrict__ diagPos) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= nbc) return;
    const int row = bcNodes[i];
@@ -518,14 +588,12 @@ __global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restr
    const long long off = A.sliceOff[slice];
    const int w = (int)((A.sliceOff[slice + 1] - off) >> 5);
    double* val = vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);
-   bool diagDone = false;
+   const long long dpos = diagPos[row];
    for (int lane = 0; lane < A.T; lane++) {
       const int t = rl * A.T + lane;
       for (int j = 0; j < w; j++) {
          const long long pos = off + (long long)(j >> 1) * 64 + 2 * t + (j & 1);
-         const bool isDiag = (!diagDone && A.cols[pos] == row);
-         val[pos] = isDiag ? 1.0 : 0.0;
-         diagDone = diagDone || isDiag;
+         val[pos] = (pos == dpos) ? 1.0 : 0.0;
       }
    }
 }
@@ -614,10 +682,11 @@ __device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const int* part,
       const long long off = Z.sliceOff[s];
       const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
       double acc = 0.0;
+      const ColCursor cc = col_cursor(Z, s, lane);
 #pragma unroll 4
       for (int jp = 0; jp < np; jp++) {
          const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(Z.cols + e);
+         const int2 c2 = col_pair(cc, jp);
          const double2 v2 = ldnc_d2(val + e);
          acc += v2.x * p[c2.x] + v2.y * p[c2.y];
       }
@@ -634,7 +703,8 @@ __device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const int* part,
 // Jacobi-preconditioned CG, whole solve in one launch (replaces CUSP_CG_solver, BCH.cu:418-451 /
 // GQ.cu:302-362: cusp::krylov::cg + diagonal preconditioner + default_monitor(b, maxit, tol)).
 // 3 grid syncs per iteration; all reductions on the device; no host round trip.
-__global__ void __launch_bounds__(512, 3) k_pcg(PcgArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB) k_pcg_t(PcgArgs a) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[3 * 32];
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -707,6 +777,9 @@ __global__ void __launch_bounds__(512, 3) k_pcg(PcgArgs a) {
 #endif
    if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
 }
+
+// two register budgets of the same kernel: 3 CTAs/SM (40 registers) or 2 CTAs/SM (64 registers); chosen at init
+static void* pcg_kernel(int minb) { return minb == 2 ? (void*)k_pcg_t<2> : (void*)k_pcg_t<3>; }
 
 struct PcgP2PArgs {
    PcgArgs a;   // a.p lives in this rank's exchange window
@@ -838,10 +911,11 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
       double acc[NA];
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = 0.0;
+      const ColCursor cc = col_cursor(A, s, lane);
 #pragma unroll 4
       for (int jp = 0; jp < np; jp++) {
          const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = ldnc_i2(A.cols + e);
+         const int2 c2 = col_pair(cc, jp);
          const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
          for (int q = 0; q < NA; q++) acc[q] += v2.x * in[base[q] + c2.x] + v2.y * in[base[q] + c2.y];
@@ -1270,7 +1344,7 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    void* args[] = {&a};
    ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
    c->lastPcgRec = ps.idx;
-   CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
+   CFD_CK(cudaLaunchCooperativeKernel(pcg_kernel(c->pcg_minb), dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
    c->launches++;
    return CFD_OK;
 }
@@ -1650,7 +1724,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    // ---- cooperative launch geometry: persistent kernels, a whole number of CTAs per SM
    {
       int occ = 0;
-      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, c->pcg_threads, 0));
+      if (const char* e = getenv("CFD_PCG_OCC")) c->pcg_minb = atoi(e) == 2 ? 2 : 3;
+      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_kernel(c->pcg_minb), c->pcg_threads, 0));
       if (occ < 1) { set_error("k_pcg does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
       const long long wantWarps = std::max<long long>(c->Z.nslices, ((long long)NNp + 31) / 32);
       int blocks = c->numSMs * occ;
@@ -1958,7 +2033,7 @@ int gq_step1GPU(cfd_ctx* c) {
    {
       ProfScope ps(c, "assemble", 0.0);
       if (c->P.BCnVelNodes > 0) {
-         k_bc_rows_identity<<<gridFor(c->P.BCnVelNodes, 128), 128, 0, c->stream>>>(c->K, 2, c->P.BCnVelNodes, c->bcNodes);
+         k_bc_rows_identity<<<gridFor(c->P.BCnVelNodes, 128), 128, 0, c->stream>>>(c->K, 2, c->P.BCnVelNodes, c->bcNodes, c->diagPosA);
          c->launches++;
       }
       k_extract_dinv<<<gridFor(c->NNo, 256), 256, 0, c->stream>>>(c->NNo, c->K.vals[2], c->diagPosA, c->Adinv);
@@ -2245,7 +2320,7 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    int dev = 0, sms = 0, occ = 0;
    cudaGetDevice(&dev);
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg, 512, 0));
+   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_kernel(3), 512, 0));
    const int blocks = sms * std::max(1, occ);
    CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
    PcgArgs a;
@@ -2255,7 +2330,7 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    cudaEvent_t e0, e1;
    cudaEventCreate(&e0); cudaEventCreate(&e1);
    cudaEventRecord(e0);
-   CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(blocks), dim3(512), args, 0, 0));
+   CFD_CK(cudaLaunchCooperativeKernel(pcg_kernel(3), dim3(blocks), dim3(512), args, 0, 0));
    cudaEventRecord(e1);
    CFD_CK(cudaEventSynchronize(e1));
    float t = 0;

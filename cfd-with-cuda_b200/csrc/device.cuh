@@ -37,15 +37,20 @@ struct Sell {
    int nval = 0;
    long long nnz = 0;      // true non-zeros (algorithmic bytes use this)
    long long padded = 0;   // stored entries
-   long long* sliceOff = nullptr;   // [nslices+1] entry offsets (multiples of 64)
-   int* cols = nullptr;             // [padded]
+   long long* sliceOff = nullptr;   // [nslices+1] entry offsets of the value arrays (multiples of 64)
+   // Column indices.  colOff[s] = start of slice s inside `cols` (even), with bit 0 = 1 when the slice is
+   // OFFSET-COMPRESSED: all its rows share one list of W column offsets (col - row), stored once (W ints) instead
+   // of 32*W explicit columns -- lossless, detected per slice at build time (structured numbering), T = 1 only.
+   long long* colOff = nullptr;     // [nslices]
+   int* cols = nullptr;
    double* vals[3] = {nullptr, nullptr, nullptr};
 };
 
 struct SellHost {   // result of the host-side conversion
    Sell meta;       // device pointers unset
-   std::vector<long long> sliceOff;
+   std::vector<long long> sliceOff, colOff;
    std::vector<int> cols;
+   long long compressedSlices = 0;
    std::vector<long long> perm;   // CSR position -> SELL position
 };
 
@@ -108,6 +113,7 @@ struct cfd_ctx {
    double* scal = nullptr;      // device: [0..3] convergence sums, [4] maxAcc bits
    double* h_pinned = nullptr;  // pinned host mirror for read-backs (64 doubles)
    int pcg_blocks = 0, pcg_threads = 512, bicg_blocks = 0, bicg_threads = 512;
+   int pcg_minb = 3;
    int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping

@@ -116,10 +116,11 @@ __global__ void __launch_bounds__(256) k_dpcg_spmv(Sell Z, const DPcgState* __re
       const long long off = Z.sliceOff[m.slice];
       const int np = (int)((Z.sliceOff[m.slice + 1] - off) >> 6);
       double a = 0.0;
+      const ColCursor cc = col_cursor(Z, m.slice, m.lane);
 #pragma unroll 4
       for (int jp = 0; jp < np; jp++) {
          const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-         const int2 c2 = ldnc_i2(Z.cols + e);
+         const int2 c2 = col_pair(cc, jp);
          const double2 v2 = ldnc_d2(val + e);
          a += v2.x * __ldg(p + c2.x) + v2.y * __ldg(p + c2.y);
       }
@@ -211,10 +212,11 @@ __global__ void __launch_bounds__(256) k_dbicg_spmv(Sell A, int vidx, long long 
       const long long off = A.sliceOff[m.slice];
       const int np = (int)((A.sliceOff[m.slice + 1] - off) >> 6);
       double a0 = 0, a1 = 0, a2 = 0;
+      const ColCursor cc = col_cursor(A, m.slice, m.lane);
 #pragma unroll 2
       for (int jp = 0; jp < np; jp++) {
          const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-         const int2 c2 = ldnc_i2(A.cols + e);
+         const int2 c2 = col_pair(cc, jp);
          const double2 v2 = ldnc_d2(val + e);
          if (f0) a0 += v2.x * __ldg(in + c2.x) + v2.y * __ldg(in + c2.y);
          if (f1) a1 += v2.x * __ldg(in + ld + c2.x) + v2.y * __ldg(in + ld + c2.y);

