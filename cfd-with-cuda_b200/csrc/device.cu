@@ -640,7 +640,9 @@ __global__ void k_add(long long n, const double* __restrict__ a, const double* _
 // =================================================================================================
 struct PcgArgs {
    Sell Z;
-   const int* part;   // per-block slice ranges (may be NULL)
+   const int* part;   // per-block slice ranges of the static share (may be NULL)
+   int dynStart;      // first slice of the dynamically scheduled tail
+   int* dynCounter;   // NULL = everything static
    int n;
    const double* b;
    double* x;
@@ -673,28 +675,48 @@ __device__ __forceinline__ SliceRange slice_range(int nslices, const int* __rest
    return r;
 }
 
-__device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const int* part, const double* p, double* q, int gwarp, int nwarps, int lane) {
+// One slice of q = Z p by one warp; returns this lane's contribution to p.q.
+__device__ __forceinline__ double pcg_slice(const Sell& Z, const double* __restrict__ val, int s, const double* p, double* q, int lane) {
+   const int T = Z.T, sub = lane % T;
+   const long long off = Z.sliceOff[s];
+   const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
+   double acc = 0.0;
+   const ColCursor cc = col_cursor(Z, s, lane);
+#pragma unroll 4
+   for (int jp = 0; jp < np; jp++) {
+      const long long e = off + ((long long)jp << 6) + 2 * lane;
+      const int2 c2 = col_pair(cc, jp);
+      const double2 v2 = ldnc_d2(val + e);
+      acc += v2.x * p[c2.x] + v2.y * p[c2.y];
+   }
+   for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   const int row = s * Z.R + lane / T;
+   if (sub == 0 && row < Z.nrows) {
+      q[row] = acc;
+      return p[row] * acc;
+   }
+   return 0.0;
+}
+
+// q = Z p over the whole matrix.  Slices [0, dynStart) are dealt statically (slice_range); the tail
+// [dynStart, nslices) is handed out two slices at a time through an atomic counter, so that SMs which finish
+// their static share early (finish times differ by ~15 %) take the remaining work instead of idling at the
+// grid reduction that follows.  `dynCounter` must be 0 on entry; the caller resets it after the next grid sync.
+__device__ __forceinline__ double pcg_spmv_phase(const Sell& Z, const int* part, int dynStart, int* dynCounter, const double* p, double* q,
+                                                 int gwarp, int nwarps, int lane) {
    double pq = 0.0;
    const double* __restrict__ val = Z.vals[0];
-   const int T = Z.T, sub = lane % T;
-   const SliceRange sr = slice_range(Z.nslices, part, gwarp, nwarps);
-   for (int s = sr.begin; s < sr.end; s += sr.step) {
-      const long long off = Z.sliceOff[s];
-      const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
-      double acc = 0.0;
-      const ColCursor cc = col_cursor(Z, s, lane);
-#pragma unroll 4
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = col_pair(cc, jp);
-         const double2 v2 = ldnc_d2(val + e);
-         acc += v2.x * p[c2.x] + v2.y * p[c2.y];
-      }
-      for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const int row = s * Z.R + lane / T;
-      if (sub == 0 && row < Z.nrows) {
-         q[row] = acc;
-         pq += p[row] * acc;
+   const int nstatic = dynCounter ? dynStart : Z.nslices;
+   const SliceRange sr = slice_range(nstatic, part, gwarp, nwarps);
+   for (int s = sr.begin; s < sr.end; s += sr.step) pq += pcg_slice(Z, val, s, p, q, lane);
+   if (dynCounter) {
+      while (true) {
+         int base = 0;
+         if (lane == 0) base = atomicAdd(dynCounter, 2);
+         base = __shfl_sync(0xffffffffu, base, 0) + dynStart;
+         if (base >= Z.nslices) break;
+         pq += pcg_slice(Z, val, base, p, q, lane);
+         if (base + 1 < Z.nslices) pq += pcg_slice(Z, val, base + 1, p, q, lane);
       }
    }
    return pq;
@@ -716,8 +738,9 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_t(PcgArgs a) {
 
    if (!a.x0zero) {
       // r = b - Z x  (warm start, BCH.cu:418-451 keeps the previous Pdot)
-      pcg_spmv_phase(a.Z, a.part, a.x, a.q, gwarp, nwarps, lane);
+      pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.x, a.q, gwarp, nwarps, lane);
       grid.sync();
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
    }
    double v3[3] = {0, 0, 0};
    for (int i = tid; i < n; i += nthreads) {
@@ -746,9 +769,10 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_t(PcgArgs a) {
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       double v1[1];
-      v1[0] = pcg_spmv_phase(a.Z, a.part, a.p, a.q, gwarp, nwarps, lane);
+      v1[0] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.p, a.q, gwarp, nwarps, lane);
       PCG_TICK(0);
       grid_sum<1>(grid, v1, buf1, sh);
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the SpMV phase
       PCG_TICK(1);
       const double alpha = rz / v1[0];
       double v2[2] = {0, 0};
@@ -805,8 +829,9 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    unsigned long long epoch = xc.xstate[0], hepoch = xc.xstate[1];
 
    if (!a.x0zero) {   // ghost entries of x were refreshed by the caller
-      pcg_spmv_phase(a.Z, a.part, a.x, a.q, gwarp, nwarps, lane);
+      pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.x, a.q, gwarp, nwarps, lane);
       grid.sync();
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
    }
    double v3[3] = {0, 0, 0};
    for (int i = tid; i < n; i += nthreads) {
@@ -828,8 +853,9 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       double v1[1];
-      v1[0] = pcg_spmv_phase(a.Z, a.part, a.p, a.q, gwarp, nwarps, lane);
+      v1[0] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.p, a.q, gwarp, nwarps, lane);
       xgrid_sum<1>(grid, v1, buf1, sh, xc, epoch);
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
       const double alpha = rz / v1[0];
       double v2[2] = {0, 0};
       for (int i = tid; i < n; i += nthreads) {
@@ -1321,7 +1347,7 @@ int run_pcg_p2p(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (!x0zero && (rc = halo(c, x, false))) return rc;
    PcgP2PArgs pa;
    PcgArgs& a = pa.a;
-   a.Z = c->Z; a.part = c->pcgPart; a.n = c->NPo; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
+   a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->NPo; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
    XComm& xc = pa.xc;
    xc.world = c->P.world; xc.rank = c->P.rank; xc.npeers = (int)c->peerRank.size();
@@ -1339,7 +1365,7 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (parted(c) && c->p2p) return run_pcg_p2p(c, b, x, x0zero);
    if (parted(c)) return run_pcg_dist(c, b, x, x0zero);
    PcgArgs a;
-   a.Z = c->Z; a.part = c->pcgPart; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
+   a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
    void* args[] = {&a};
    ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
@@ -1754,8 +1780,24 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          part[0] = 0;
          return part;
       };
-      std::vector<int> pz = partition(c->hostOffZ, c->pcg_blocks);
-      TRY(dupload(c, &c->pcgPart, pz.data(), pz.size()));
+      {
+         // static share = the first ~88 % of the stored entries, balanced over the CTAs; the rest is the dynamic tail
+         const int nsZ = (int)c->hostOffZ.size() - 1;
+         int dynStart = nsZ;
+         const bool useDyn = getenv("CFD_NO_DYN") == nullptr && nsZ >= 4 * c->pcg_blocks * (c->pcg_threads / 32);
+         if (useDyn) {
+            double frac = 0.88;
+            if (const char* e = getenv("CFD_DYN_STATIC_FRAC")) frac = std::min(1.0, std::max(0.5, atof(e)));
+            const long long target = (long long)(frac * (double)c->hostOffZ[nsZ]);
+            dynStart = (int)(std::lower_bound(c->hostOffZ.begin(), c->hostOffZ.end(), target) - c->hostOffZ.begin());
+            dynStart = std::min(std::max(dynStart, 0), nsZ);
+         }
+         std::vector<long long> offStatic(c->hostOffZ.begin(), c->hostOffZ.begin() + dynStart + 1);
+         std::vector<int> pz = partition(offStatic, c->pcg_blocks);
+         TRY(dupload(c, &c->pcgPart, pz.data(), pz.size()));
+         c->pcgDynStart = dynStart;
+         if (useDyn) TRY(dalloc(c, &c->pcgDynCounter, 4));
+      }
       if (P->scheme == CFD_IMPLICIT) {
          std::vector<int> pk = partition(c->hostOffK, c->bicg_blocks);
          TRY(dupload(c, &c->bicgPart, pk.data(), pk.size()));
@@ -2324,7 +2366,7 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    const int blocks = sms * std::max(1, occ);
    CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
    PcgArgs a;
-   a.Z = Z; a.part = nullptr; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
+   a.Z = Z; a.part = nullptr; a.dynStart = Z.nslices; a.dynCounter = nullptr; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
    a.tol = tol; a.maxit = maxit; a.x0zero = 0;
    void* args[] = {&a};
    cudaEvent_t e0, e1;

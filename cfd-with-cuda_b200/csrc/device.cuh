@@ -114,6 +114,8 @@ struct cfd_ctx {
    double* h_pinned = nullptr;  // pinned host mirror for read-backs (64 doubles)
    int pcg_blocks = 0, pcg_threads = 512, bicg_blocks = 0, bicg_threads = 512;
    int pcg_minb = 3;
+   int pcgDynStart = 0;             // slices >= this are scheduled dynamically inside k_pcg
+   int* pcgDynCounter = nullptr;
    int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
