@@ -100,6 +100,7 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
       out.compressedSlices += comp[s];
    }
    m.padded = out.sliceOff[ns];
+   m.anyComp = out.compressedSlices > 0 ? 1 : 0;
    out.cols.assign((size_t)std::max<long long>(cpos, 2), 0);
    out.perm.assign((size_t)m.nnz, 0);
 #pragma omp parallel for schedule(static)
@@ -218,27 +219,36 @@ __device__ __forceinline__ const double* sell_vals(const Sell& A, int vidx) {
    return vidx == 0 ? A.vals[0] : (vidx == 1 ? A.vals[1] : A.vals[2]);   // no dynamic indexing of the by-value struct
 }
 
-// Column access of one lane inside one slice: explicit pairs, or the slice's shared offset list added to the row.
-struct ColCursor {
-   const int* base;
-   int cmp, row, hi;
-};
-__device__ __forceinline__ ColCursor col_cursor(const Sell& A, int slice, int lane) {
-   ColCursor cc;
-   const long long co = A.colOff[slice];
-   cc.cmp = (int)(co & 1);
-   cc.base = A.cols + (co & ~1LL) + (cc.cmp ? 0 : 2 * lane);
-   cc.row = slice * A.R + lane / A.T;
-   cc.hi = A.ncols - 1;
-   return cc;
-}
-__device__ __forceinline__ int2 col_pair(const ColCursor& cc, int jp) {
-   if (cc.cmp) {   // warp-uniform branch; the 8-byte offset pair is a broadcast load that stays in L1
-      const int2 o = __ldg(reinterpret_cast<const int2*>(cc.base) + jp);
-      // padded entries (value 0) of rows near the ends of the matrix may point outside: clamp
-      return make_int2(min(max(cc.row + o.x, 0), cc.hi), min(max(cc.row + o.y, 0), cc.hi));
+// Visit the (value index, column pair) of every entry pair this lane owns in `slice`:  f(e, c2) with e the index
+// of the pair inside the value arrays.  Three specialised loops: matrices without compressed slices (columns laid
+// out exactly like the values, no extra loads), offset-compressed slices (one broadcast 8-byte load per pair, added
+// to the row and clamped: padded zero entries near the ends of the matrix may point outside), explicit slices of a
+// matrix that also has compressed ones.
+template <int UNROLL, typename F>
+__device__ __forceinline__ void sell_pairs(const Sell& A, int slice, int lane, F&& f) {
+   const long long off = A.sliceOff[slice];
+   const int np = (int)((A.sliceOff[slice + 1] - off) >> 6);
+   const long long e0 = off + 2 * lane;
+   if (!A.anyComp) {
+      const int* __restrict__ cp = A.cols + e0;
+#pragma unroll(UNROLL)
+      for (int jp = 0; jp < np; jp++) f(e0 + ((long long)jp << 6), ldnc_i2(cp + ((long long)jp << 6)));
+      return;
    }
-   return ldnc_i2(cc.base + ((long long)jp << 6));
+   const long long co = A.colOff[slice];
+   if (co & 1) {
+      const int2* __restrict__ op = reinterpret_cast<const int2*>(A.cols + (co & ~1LL));
+      const int row = slice * A.R + lane / A.T, hi = A.ncols - 1;
+#pragma unroll(UNROLL)
+      for (int jp = 0; jp < np; jp++) {
+         const int2 o = __ldg(op + jp);
+         f(e0 + ((long long)jp << 6), make_int2(min(max(row + o.x, 0), hi), min(max(row + o.y, 0), hi)));
+      }
+   } else {
+      const int* __restrict__ cp = A.cols + co + 2 * lane;
+#pragma unroll(UNROLL)
+      for (int jp = 0; jp < np; jp++) f(e0 + ((long long)jp << 6), ldnc_i2(cp + ((long long)jp << 6)));
+   }
 }
 
 // y_c = alpha * A x_c + beta * y_c for NV vectors sharing one Sell value array (vectors are
@@ -249,20 +259,14 @@ __global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const doub
    RowMap m;
    if (!row_map(A, m)) return;
    const double* __restrict__ val = sell_vals(A, vidx);
-   const long long off = A.sliceOff[m.slice];
-   const int np = (int)((A.sliceOff[m.slice + 1] - off) >> 6);
    double acc[NV];
 #pragma unroll
    for (int c = 0; c < NV; c++) acc[c] = 0.0;
-   const ColCursor cc = col_cursor(A, m.slice, m.lane);
-#pragma unroll 4
-   for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = col_pair(cc, jp);
+   sell_pairs<4>(A, m.slice, m.lane, [&](long long e, int2 c2) {
       const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
       for (int c = 0; c < NV; c++) acc[c] += v2.x * __ldg(x + c * ldx + c2.x) + v2.y * __ldg(x + c * ldx + c2.y);
-   }
+   });
 #pragma unroll
    for (int c = 0; c < NV; c++) acc[c] = lanes_sum(acc[c], A.T);
    if (m.owner) {
@@ -278,36 +282,24 @@ __global__ void __launch_bounds__(256) k_spmv_multi(Sell A, int vidx, const doub
 // Accumulate a0..a2 += K * U_c (one value array, three component vectors) over this lane's entries.
 __device__ __forceinline__ void lane_dot_k3(const Sell& K, const double* __restrict__ val, const RowMap& m, const double* __restrict__ U,
                                             long long NN, double& a0, double& a1, double& a2) {
-   const long long off = K.sliceOff[m.slice];
-   const int np = (int)((K.sliceOff[m.slice + 1] - off) >> 6);
-   const ColCursor cc = col_cursor(K, m.slice, m.lane);
-#pragma unroll 4
-   for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = col_pair(cc, jp);
+   sell_pairs<4>(K, m.slice, m.lane, [&](long long e, int2 c2) {
       const double2 v2 = ldnc_d2(val + e);
       a0 += v2.x * __ldg(U + c2.x) + v2.y * __ldg(U + c2.y);
       a1 += v2.x * __ldg(U + NN + c2.x) + v2.y * __ldg(U + NN + c2.y);
       a2 += v2.x * __ldg(U + 2 * NN + c2.x) + v2.y * __ldg(U + 2 * NN + c2.y);
-   }
+   });
 }
 // Accumulate a_c += sign * G_c * p (three value arrays, one vector); p(col) is supplied by a functor so
 // that callers can form it on the fly (e.g. 2 Pk_prev - Pk_prevprev).
 template <typename PF>
 __device__ __forceinline__ void lane_dot_g3(const Sell& G, const RowMap& m, PF pf, double sign, double& a0, double& a1, double& a2) {
-   const long long off = G.sliceOff[m.slice];
-   const int np = (int)((G.sliceOff[m.slice + 1] - off) >> 6);
-   const ColCursor cc = col_cursor(G, m.slice, m.lane);
-#pragma unroll 2
-   for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-      const int2 c2 = col_pair(cc, jp);
+   sell_pairs<2>(G, m.slice, m.lane, [&](long long e, int2 c2) {
       const double2 g1 = ldnc_d2(G.vals[0] + e), g2 = ldnc_d2(G.vals[1] + e), g3 = ldnc_d2(G.vals[2] + e);
       const double px = sign * pf(c2.x), py = sign * pf(c2.y);
       a0 += g1.x * px + g1.y * py;
       a1 += g2.x * px + g2.y * py;
       a2 += g3.x * px + g3.y * py;
-   }
+   });
 }
 
 // step 1 of the explicit scheme, fused (replaces step1GPUpart, BCH.cu:946-973: 6 csrmv + applyVelBC +
@@ -418,13 +410,8 @@ __global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const
    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
    const int slice = gthread >> 5, lane = gthread & 31;
    if (slice >= GT.nslices) return;
-   const long long off = GT.sliceOff[slice];
-   const int np = (int)((GT.sliceOff[slice + 1] - off) >> 6);
    double acc = 0.0;
-   const ColCursor cc = col_cursor(GT, slice, lane);
-   for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * lane;
-      const int2 c2 = col_pair(cc, jp);
+   sell_pairs<1>(GT, slice, lane, [&](long long e, int2 c2) {
 #pragma unroll
       for (int c = 0; c < 3; c++) {
          const double2 g = ldnc_d2(GT.vals[c] + e);
@@ -436,7 +423,7 @@ __global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const
          }
          acc += g.x * dx + g.y * dy;
       }
-   }
+   });
    for (int o = GT.T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
    const int row = slice * GT.R + lane / GT.T;
    if ((lane % GT.T) == 0 && row < GT.nrows) R2[row] = (row == pinNode) ? 0.0 : acc;   // pinNode = -1: no pin
@@ -678,17 +665,11 @@ __device__ __forceinline__ SliceRange slice_range(int nslices, const int* __rest
 // One slice of q = Z p by one warp; returns this lane's contribution to p.q.
 __device__ __forceinline__ double pcg_slice(const Sell& Z, const double* __restrict__ val, int s, const double* p, double* q, int lane) {
    const int T = Z.T, sub = lane % T;
-   const long long off = Z.sliceOff[s];
-   const int np = (int)((Z.sliceOff[s + 1] - off) >> 6);
    double acc = 0.0;
-   const ColCursor cc = col_cursor(Z, s, lane);
-#pragma unroll 4
-   for (int jp = 0; jp < np; jp++) {
-      const long long e = off + ((long long)jp << 6) + 2 * lane;
-      const int2 c2 = col_pair(cc, jp);
+   sell_pairs<4>(Z, s, lane, [&](long long e, int2 c2) {
       const double2 v2 = ldnc_d2(val + e);
       acc += v2.x * p[c2.x] + v2.y * p[c2.y];
-   }
+   });
    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
    const int row = s * Z.R + lane / T;
    if (sub == 0 && row < Z.nrows) {
@@ -932,20 +913,14 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
 #pragma unroll
    for (int q = 0; q < NA; q++) { base[q] = (size_t)sys[q] * n; s0[q] = 0.0; s1[q] = 0.0; }
    for (int s = sr.begin; s < sr.end; s += sr.step) {
-      const long long off = A.sliceOff[s];
-      const int np = (int)((A.sliceOff[s + 1] - off) >> 6);
       double acc[NA];
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = 0.0;
-      const ColCursor cc = col_cursor(A, s, lane);
-#pragma unroll 4
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * lane;
-         const int2 c2 = col_pair(cc, jp);
+      sell_pairs<4>(A, s, lane, [&](long long e, int2 c2) {
          const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
          for (int q = 0; q < NA; q++) acc[q] += v2.x * in[base[q] + c2.x] + v2.y * in[base[q] + c2.y];
-      }
+      });
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = lanes_sum(acc[q], T);
       const int row = s * A.R + lane / T;

@@ -42,6 +42,7 @@ struct Sell {
    // OFFSET-COMPRESSED: all its rows share one list of W column offsets (col - row), stored once (W ints) instead
    // of 32*W explicit columns -- lossless, detected per slice at build time (structured numbering), T = 1 only.
    long long* colOff = nullptr;     // [nslices]
+   int anyComp = 0;                 // 0: no compressed slice -> cols are laid out exactly like the values (colOff unused)
    int* cols = nullptr;
    double* vals[3] = {nullptr, nullptr, nullptr};
 };

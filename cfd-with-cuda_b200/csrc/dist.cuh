@@ -113,17 +113,11 @@ __global__ void __launch_bounds__(256) k_dpcg_spmv(Sell Z, const DPcgState* __re
    double v[1] = {0.0};
    if (row_map(Z, m)) {
       const double* __restrict__ val = Z.vals[0];
-      const long long off = Z.sliceOff[m.slice];
-      const int np = (int)((Z.sliceOff[m.slice + 1] - off) >> 6);
       double a = 0.0;
-      const ColCursor cc = col_cursor(Z, m.slice, m.lane);
-#pragma unroll 4
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-         const int2 c2 = col_pair(cc, jp);
+      sell_pairs<4>(Z, m.slice, m.lane, [&](long long e, int2 c2) {
          const double2 v2 = ldnc_d2(val + e);
          a += v2.x * __ldg(p + c2.x) + v2.y * __ldg(p + c2.y);
-      }
+      });
       a = lanes_sum(a, Z.T);
       if (m.owner) { q[m.row] = a; v[0] = p[m.row] * a; }
    }
@@ -209,19 +203,13 @@ __global__ void __launch_bounds__(256) k_dbicg_spmv(Sell A, int vidx, long long 
    double v[6] = {0, 0, 0, 0, 0, 0};
    if (row_map(A, m)) {
       const double* __restrict__ val = sell_vals(A, vidx);
-      const long long off = A.sliceOff[m.slice];
-      const int np = (int)((A.sliceOff[m.slice + 1] - off) >> 6);
       double a0 = 0, a1 = 0, a2 = 0;
-      const ColCursor cc = col_cursor(A, m.slice, m.lane);
-#pragma unroll 2
-      for (int jp = 0; jp < np; jp++) {
-         const long long e = off + ((long long)jp << 6) + 2 * m.lane;
-         const int2 c2 = col_pair(cc, jp);
+      sell_pairs<2>(A, m.slice, m.lane, [&](long long e, int2 c2) {
          const double2 v2 = ldnc_d2(val + e);
          if (f0) a0 += v2.x * __ldg(in + c2.x) + v2.y * __ldg(in + c2.y);
          if (f1) a1 += v2.x * __ldg(in + ld + c2.x) + v2.y * __ldg(in + ld + c2.y);
          if (f2) a2 += v2.x * __ldg(in + 2 * ld + c2.x) + v2.y * __ldg(in + 2 * ld + c2.y);
-      }
+      });
       a0 = lanes_sum(a0, A.T); a1 = lanes_sum(a1, A.T); a2 = lanes_sum(a2, A.T);
       if (m.owner) {
          const double a[3] = {a0, a1, a2};
