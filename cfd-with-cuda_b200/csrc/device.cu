@@ -1355,6 +1355,11 @@ int fetch_kinfo(cfd_ctx* c) {
    CFD_CK(cudaStreamSynchronize(c->stream));
    c->last_cg = (int)c->h_pinned[16];
    for (int d = 0; d < 3; d++) c->last_bicg[d] = (int)c->h_pinned[16 + 3 + d];
+   if (c->p2p && c->xstate) {   // a peer that never arrived: the spin-waits of k_pcg_p2p give up after 4 s and raise this word
+      unsigned long long err = 0;
+      CFD_CK(cudaMemcpy(&err, c->xstate + 2, sizeof err, cudaMemcpyDeviceToHost));
+      if (err) { set_error("peer-memory exchange timed out (a rank stopped participating)"); return CFD_ERR_STATE; }
+   }
    // algorithmic bytes of the Krylov launches are known only now (iteration counts): DESIGN.md byte model
    if (c->lastPcgRec >= 0) {
       const double N = c->P.NNp;
@@ -2287,6 +2292,55 @@ int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, con
    cudaFree(dx); cudaFree(dy);
    sell_free(A);
    return CFD_OK;
+}
+
+long long cfd_sell_layout_check(int nrows, int ncols, const int* rs, const int* col, const double* val, int T, long long* slices,
+                                long long* compressed_slices, double* stored_over_nnz) {
+   if (T <= 0) T = choose_T(nrows, rs[nrows]);
+   SellHost h;
+   sell_build_host(nrows, ncols, rs, col, T, h);
+   const Sell& m = h.meta;
+   std::vector<double> v((size_t)m.padded, 0.0);
+   for (long long k = 0; k < m.nnz; k++) v[(size_t)h.perm[(size_t)k]] = val[k];
+   if (slices) *slices = m.nslices;
+   if (compressed_slices) *compressed_slices = h.compressedSlices;
+   if (stored_over_nnz) *stored_over_nnz = m.nnz ? (double)m.padded / (double)m.nnz : 1.0;
+   long long bad = 0;
+   std::vector<double> dense;   // one decoded row at a time: accumulate by column, compare with the CSR row
+   std::vector<std::pair<int, double> > ent;
+   for (int s = 0; s < m.nslices; s++) {
+      const long long off = h.sliceOff[s];
+      const int w = (int)((h.sliceOff[s + 1] - off) >> 5);
+      const long long co = h.colOff[s] & ~1LL;
+      const bool cmp = h.colOff[s] & 1;
+      for (int rl = 0; rl < m.R; rl++) {
+         const int r = s * m.R + rl;
+         ent.clear();
+         for (int lane = 0; lane < T; lane++) {
+            const int t = rl * T + lane;
+            for (int j = 0; j < w; j++) {
+               const long long rel = (long long)(j >> 1) * 64 + 2 * t + (j & 1);
+               int c;
+               if (cmp) c = std::min(std::max(r + h.cols[(size_t)co + j], 0), ncols - 1);
+               else c = h.cols[(size_t)(co + rel)];
+               const double x = v[(size_t)(off + rel)];
+               if (r >= nrows) { if (x != 0.0) bad++; continue; }
+               if (c < 0 || c >= ncols) { bad++; continue; }
+               if (x != 0.0) ent.push_back(std::make_pair(c, x));
+            }
+         }
+         if (r >= nrows) continue;
+         std::sort(ent.begin(), ent.end());
+         size_t q = 0;
+         for (int k = rs[r]; k < rs[r + 1]; k++) {
+            if (val[k] == 0.0) continue;   // explicit zeros of the CSR matrix are indistinguishable from padding
+            if (q < ent.size() && ent[q].first == col[k] && ent[q].second == val[k]) q++;
+            else bad++;
+         }
+         if (q != ent.size()) bad += (long long)(ent.size() - q);
+      }
+   }
+   return bad;
 }
 
 int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_op) {

@@ -139,6 +139,8 @@ def lib():
     L.cfd_solver_write_tecplot_fields.argtypes = [vp, C.c_char_p, C.c_char_p, _dp, _dp]
     L.cfd_solver_read_restart_fields.argtypes = [vp, C.c_char_p, _dp, _dp]
     L.cfd_diag_sync.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+    L.cfd_sell_layout_check.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _dp]
+    L.cfd_sell_layout_check.restype = C.c_longlong
     L.cfd_solver_main.argtypes = [C.c_char_p, C.c_int, C.c_int]
     _lib = L
     return L
@@ -465,6 +467,16 @@ def csr_spmv(rowStarts, col, val, x, y=None, alpha=1.0, beta=0.0, ncols=None, re
     ms = C.c_double()
     _check(lib().cfd_csr_spmv(nrows, ncols, _i(rs), _i(cl), _d(vl), x.shape[0], _d(x), _d(yy), alpha, beta, repeat, C.byref(ms)))
     return yy, ms.value
+
+
+def sell_layout_check(rowStarts, col, val, ncols, T=0):
+    """Host-side round trip CSR -> device layout -> CSR.  Returns (mismatches, slices, compressed slices, stored/nnz)."""
+    rs = np.ascontiguousarray(rowStarts, np.int32)
+    cl = np.ascontiguousarray(col, np.int32)
+    vl = np.ascontiguousarray(val, np.float64)
+    ns, nc, ratio = C.c_longlong(), C.c_longlong(), C.c_double()
+    bad = lib().cfd_sell_layout_check(len(rs) - 1, ncols, _i(rs), _i(cl), _d(vl), T, C.byref(ns), C.byref(nc), C.byref(ratio))
+    return int(bad), int(ns.value), int(nc.value), float(ratio.value)
 
 
 def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000):

@@ -207,6 +207,12 @@ long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context
 /* y = alpha*A*x + beta*y for `nvec` vectors sharing one CSR matrix; x is [nvec][ncols], y [nvec][nrows] host arrays */
 int cfd_csr_spmv(int nrows, int ncols, const int* rowStarts, const int* col, const double* val, int nvec,
                  const double* x, double* y, double alpha, double beta, int repeat, double* ms_per_call);
+/* Host-side self-check of the device matrix layout (no GPU needed): converts the CSR matrix to the sliced layout with T
+ * lanes per row (T = 0: the library's own choice), decodes it again -- explicit and offset-compressed slices -- and
+ * returns the number of (row, col, value) triples that differ (0 = exact); *compressed_slices / *slices report how many
+ * slices store a shared column-offset list instead of explicit columns. */
+long long cfd_sell_layout_check(int nrows, int ncols, const int* rowStarts, const int* col, const double* val, int T,
+                                long long* slices, long long* compressed_slices, double* stored_over_nnz);
 /* diagnostic: microseconds per grid-wide sync (mode 0) / deterministic grid reduction of 1 (mode 1) or 3 (mode 2) values */
 int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_op);
 /* Jacobi-PCG on a CSR matrix: returns iterations in *its */

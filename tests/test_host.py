@@ -95,3 +95,30 @@ def test_tecplot_and_restart_formats(mesh, tmp_path, name):
     o2 = orc.Oracle(path, "explicit")
     o2.read_restart(f_o)
     assert np.array_equal(o2.U, U) and np.array_equal(o2.P, P)
+
+
+def test_device_matrix_layout_round_trip(mesh):
+    """CSR -> sliced layout -> CSR on the host (no GPU): every lane-per-row setting, explicit slices (Q2 numbering) and
+    offset-compressed slices (structured Q1 numbering: most slices must compress, boundary rows zero-padded onto the
+    shared offset list)."""
+    import fracstep
+    s = fracstep.Solver(mesh("h_q2_c6", **MESHES["h_q2_c6"]), "implicit", init_gpu=False)
+    NN, NNp = s.i("NN"), s.i("NNp")
+    for (rs, cl, v, ncols) in ((s.arr("sparseMrowStarts"), s.arr("sparseMcol"), s.arr("sparseKvalue"), NN),
+                               (s.arr("sparseGrowStarts"), s.arr("sparseGcol"), s.arr("sparseG2value"), NNp),
+                               (s.arr("sparseZrowStarts"), s.arr("sparseZcol"), s.arr("sparseZvalue"), NNp)):
+        for T in (0, 1, 2, 4, 8):
+            bad, ns, nc, ratio = fracstep.sell_layout_check(rs, cl, v, ncols, T)
+            assert bad == 0 and 1.0 <= ratio < 2.0   # (T = 8 on 15-entry rows of a 6^3 mesh pads heavily; never chosen by the library)
+    q1 = fracstep.Solver(scheme="implicit", cavity=dict(nx=40, NENv=8), init_gpu=False)
+    n = q1.i("NN")
+    bad, ns, nc, ratio = fracstep.sell_layout_check(q1.arr("sparseZrowStarts"), q1.arr("sparseZcol"), q1.arr("sparseZvalue"), n, 1)
+    assert bad == 0 and nc >= 0.95 * ns and ratio < 1.12        # structured numbering: (nearly) every slice shares its offsets
+    bad, ns, nc, ratio = fracstep.sell_layout_check(q1.arr("sparseZrowStarts"), q1.arr("sparseZcol"), q1.arr("sparseZvalue"), n, 2)
+    assert bad == 0 and nc == 0                                   # compression is a T = 1 feature
+    # a random unstructured matrix never compresses and still round-trips
+    import scipy.sparse as sp
+    A = sp.random(500, 300, density=0.03, format="csr", random_state=1)
+    A.sort_indices()
+    bad, ns, nc, ratio = fracstep.sell_layout_check(A.indptr, A.indices, A.data, 300, 1)
+    assert bad == 0 and nc == 0
