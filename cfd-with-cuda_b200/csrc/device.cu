@@ -65,7 +65,7 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
    std::vector<int> width(ns, 0);
    std::vector<unsigned char> comp(ns, 0);
    std::vector<std::vector<int> > uni(ns);   // offset list of the compressed slices
-   const bool allowComp = (T == 1) && getenv("CFD_NO_COLCOMP") == nullptr;
+   const bool allowComp = getenv("CFD_NO_COLCOMP") == nullptr;
 #pragma omp parallel
    {
       std::vector<int> u;
@@ -87,7 +87,8 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
          }
          std::sort(u.begin(), u.end());
          u.erase(std::unique(u.begin(), u.end()), u.end());
-         const int wc = ((int)u.size() + 1) & ~1;
+         // offset u of the sorted union goes to lane u % T, slot u / T (the same dealing as the explicit layout)
+         const int wc = (((int)u.size() + T - 1) / T + 1) & ~1;
          // worth it while the extra zero values (8 B each) cost less than the saved indices (4 B each)
          if (4 * wc <= 5 * width[s]) { comp[s] = 1; width[s] = wc; uni[s] = u; }
       }
@@ -96,7 +97,7 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
    for (int s = 0; s < ns; s++) {
       out.sliceOff[s + 1] = out.sliceOff[s] + (long long)width[s] * 32;
       out.colOff[s] = cpos | (comp[s] ? 1 : 0);
-      cpos += comp[s] ? width[s] : (long long)width[s] * 32;
+      cpos += comp[s] ? (long long)width[s] * T : (long long)width[s] * 32;
       out.compressedSlices += comp[s];
    }
    m.padded = out.sliceOff[ns];
@@ -110,13 +111,15 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
       const int w = width[s];
       if (comp[s]) {
          const std::vector<int>& u = uni[s];
-         for (int j = 0; j < w; j++) out.cols[(size_t)co + j] = j < (int)u.size() ? u[j] : 0;   // offset 0 = the row itself (val 0)
+         // offset list stored as [slot j][lane-in-row t]; missing tail = offset 0 (the row itself, value 0)
+         for (int q = 0; q < w * T; q++) out.cols[(size_t)co + q] = q < (int)u.size() ? u[q] : 0;
          for (int rl = 0; rl < R; rl++) {
             const int r = s * R + rl;
             if (r >= nrows) break;
             for (int k = rs[r]; k < rs[r + 1]; k++) {
-               const int j = (int)(std::lower_bound(u.begin(), u.end(), col[k] - r) - u.begin());
-               out.perm[(size_t)k] = off + (long long)(j >> 1) * 64 + 2 * rl + (j & 1);
+               const int q = (int)(std::lower_bound(u.begin(), u.end(), col[k] - r) - u.begin());
+               const int j = q / T, t = rl * T + q % T;
+               out.perm[(size_t)k] = off + (long long)(j >> 1) * 64 + 2 * t + (j & 1);
             }
          }
          continue;
@@ -237,12 +240,22 @@ __device__ __forceinline__ void sell_pairs(const Sell& A, int slice, int lane, F
    }
    const long long co = A.colOff[slice];
    if (co & 1) {
-      const int2* __restrict__ op = reinterpret_cast<const int2*>(A.cols + (co & ~1LL));
       const int row = slice * A.R + lane / A.T, hi = A.ncols - 1;
+      if (A.T == 1) {
+         const int2* __restrict__ op = reinterpret_cast<const int2*>(A.cols + (co & ~1LL));
 #pragma unroll(UNROLL)
-      for (int jp = 0; jp < np; jp++) {
-         const int2 o = __ldg(op + jp);
-         f(e0 + ((long long)jp << 6), make_int2(min(max(row + o.x, 0), hi), min(max(row + o.y, 0), hi)));
+         for (int jp = 0; jp < np; jp++) {
+            const int2 o = __ldg(op + jp);
+            f(e0 + ((long long)jp << 6), make_int2(min(max(row + o.x, 0), hi), min(max(row + o.y, 0), hi)));
+         }
+      } else {   // T lanes per row: slot j of lane-in-row t holds offset [j][t]
+         const int T = A.T;
+         const int* __restrict__ op = A.cols + (co & ~1LL) + lane % T;
+#pragma unroll(UNROLL)
+         for (int jp = 0; jp < np; jp++) {
+            const int ox = __ldg(op + (2 * jp) * T), oy = __ldg(op + (2 * jp + 1) * T);
+            f(e0 + ((long long)jp << 6), make_int2(min(max(row + ox, 0), hi), min(max(row + oy, 0), hi)));
+         }
       }
    } else {
       const int* __restrict__ cp = A.cols + co + 2 * lane;
@@ -2321,7 +2334,7 @@ long long cfd_sell_layout_check(int nrows, int ncols, const int* rs, const int* 
             for (int j = 0; j < w; j++) {
                const long long rel = (long long)(j >> 1) * 64 + 2 * t + (j & 1);
                int c;
-               if (cmp) c = std::min(std::max(r + h.cols[(size_t)co + j], 0), ncols - 1);
+               if (cmp) c = std::min(std::max(r + h.cols[(size_t)co + (size_t)j * T + lane], 0), ncols - 1);
                else c = h.cols[(size_t)(co + rel)];
                const double x = v[(size_t)(off + rel)];
                if (r >= nrows) { if (x != 0.0) bad++; continue; }

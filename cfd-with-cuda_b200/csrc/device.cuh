@@ -40,7 +40,8 @@ struct Sell {
    long long* sliceOff = nullptr;   // [nslices+1] entry offsets of the value arrays (multiples of 64)
    // Column indices.  colOff[s] = start of slice s inside `cols` (even), with bit 0 = 1 when the slice is
    // OFFSET-COMPRESSED: all its rows share one list of W column offsets (col - row), stored once (W ints) instead
-   // of 32*W explicit columns -- lossless, detected per slice at build time (structured numbering), T = 1 only.
+   // of 32*W explicit columns -- lossless, detected per slice at build time (structured numbering).  With T lanes
+   // per row the list holds W*T offsets, [slot][lane-in-row].
    long long* colOff = nullptr;     // [nslices]
    int anyComp = 0;                 // 0: no compressed slice -> cols are laid out exactly like the values (colOff unused)
    int* cols = nullptr;
