@@ -36,9 +36,15 @@ int choose_T(int nrows, long long nnz) {
    }
    if (nrows <= 0) return 1;
    const double avg = (double)nnz / nrows;
+   int Tmax = 1;   // keep at least ~8 entries per lane
+   while (Tmax < 8 && avg / (4 * Tmax) >= 4.0) Tmax *= 2;
+   // mid-size and large matrices: >= 4 slices per resident warp of the persistent kernels (blocked + dynamic-tail
+   // scheduling needs that); small L2-resident ones: about one slice per warp at 2 CTAs/SM -- more lanes would only
+   // add CTAs to every grid-wide sync, which is what bounds those solves
+   const long long big = 909000, small = 100000;
    int T = 1;
-   // enough (row, lane) pairs for >= 4 slices per resident warp of the persistent kernels, at least ~8 entries per lane
-   while ((long long)nrows * T < 2000000 && T < 8 && avg / (2 * T) >= 4.0) T *= 2;
+   if ((long long)nrows * Tmax >= big) { while ((long long)nrows * T < big) T *= 2; }
+   else { while ((long long)nrows * T < small && T < Tmax) T *= 2; }
    return T;
 }
 
