@@ -273,8 +273,16 @@ def main():
     dom = max((k for k in prof if k != "halo"), key=lambda k: prof[k]["ms"])
     d = prof[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-    traffic = ncu_traffic(a.workload, dom)
     cg_its = sum(r["cg_iterations"] for r in reps)
+    cg_its_local = cg_its
+    traffic = ncu_traffic(a.workload, dom)
+    # the same event time expressed in the bytes the device layout actually stores (padding in, compressed indices out)
+    layout = None
+    if dom == "pcg" and d["ms"] > 0:
+        zs = c.matrix_stats("Z")
+        n_loc = c.NNp
+        per_it = 8.0 * zs["stored_values"] + 4.0 * zs["stored_indices"] + 4.0 * (n_loc + 1) + 104.0 * n_loc
+        layout = dict(gbs=round(per_it * cg_its_local / (d["ms"] * 1e-3) / 1e9, 1), matrix=zs)
     cg_ms = prof["pcg"]["ms"]
     kernels = {k: dict(ms=round(v["ms"], 3), launches=v["launches"], gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
                        share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
@@ -292,7 +300,9 @@ def main():
                               traffic=traffic, peak_source=peak_src, share_of_step=round(d["ms"] / total_ms, 4) if total_ms else None,
                               note="achieved = ALGORITHMIC bytes (CSR model: 12 B per non-zero + vectors) / event time; slices with a shared "
                                    "column-offset pattern store their indices once (lossless), so on structured meshes the kernel moves fewer DRAM "
-                                   "bytes than the model and frac can exceed 1; `traffic` is the DRAM byte count ncu measured for one launch"),
+                                   "bytes than the model and frac can exceed 1; `traffic` is the DRAM byte count ncu measured for one launch; "
+                                   "`layout` re-expresses the same time in the bytes the device layout stores",
+                              layout=layout),
                 cg_gdof_iter_per_s=(sz["NNp"] * cg_its / (cg_ms * 1e-3) / 1e9) if cg_ms > 0 else None,
                 kernels=kernels)
     if world == 1 and not a.no_cpu_baseline:

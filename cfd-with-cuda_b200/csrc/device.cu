@@ -108,6 +108,7 @@ void sell_build_host(int nrows, int ncols, const int* rs, const int* col, int T,
    }
    m.padded = out.sliceOff[ns];
    m.anyComp = out.compressedSlices > 0 ? 1 : 0;
+   m.nindex = cpos;
    out.cols.assign((size_t)std::max<long long>(cpos, 2), 0);
    out.perm.assign((size_t)m.nnz, 0);
 #pragma omp parallel for schedule(static)
@@ -2268,6 +2269,18 @@ int cfd_profile_get(cfd_ctx* c, const char* name, double* ms, long long* launche
    return CFD_OK;
 }
 long long cfd_kernel_launches(cfd_ctx* c) { return c->launches; }
+
+int cfd_matrix_stats(cfd_ctx* c, const char* name, long long* nnz, long long* stored_values, long long* stored_indices, int* lanes_per_row) {
+   if (!c || !name) return CFD_ERR_ARG;
+   const std::string n(name);
+   const Sell* m = n == "K" ? &c->K : n == "G" ? &c->G : n == "GT" ? &c->GT : n == "Z" ? &c->Z : nullptr;
+   if (!m) { set_error("unknown matrix %s", name); return CFD_ERR_ARG; }
+   if (nnz) *nnz = m->nnz;
+   if (stored_values) *stored_values = m->padded;
+   if (stored_indices) *stored_indices = m->nindex;
+   if (lanes_per_row) *lanes_per_row = m->T;
+   return CFD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // stand-alone kernels on caller data

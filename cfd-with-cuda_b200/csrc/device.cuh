@@ -43,6 +43,7 @@ struct Sell {
    // of 32*W explicit columns -- lossless, detected per slice at build time (structured numbering).  With T lanes
    // per row the list holds W*T offsets, [slot][lane-in-row].
    long long* colOff = nullptr;     // [nslices]
+   long long nindex = 0;            // ints stored in `cols`
    int anyComp = 0;                 // 0: no compressed slice -> cols are laid out exactly like the values (colOff unused)
    int* cols = nullptr;
    double* vals[3] = {nullptr, nullptr, nullptr};

@@ -112,6 +112,7 @@ def lib():
     L.cfd_profile_get.argtypes = [vp, C.c_char_p, _dp, C.POINTER(C.c_longlong), _dp]
     L.cfd_kernel_launches.argtypes = [vp]
     L.cfd_kernel_launches.restype = C.c_longlong
+    L.cfd_matrix_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]
     L.cfd_csr_spmv.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.cfd_csr_pcg.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, _ip, _dp]
     L.cfd_solver_create_from_inp.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
@@ -329,6 +330,11 @@ class Context:
         b = C.c_double()
         self.L.cfd_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n), C.byref(b))
         return dict(ms=ms.value, launches=n.value, bytes=b.value)
+
+    def matrix_stats(self, name):
+        a, b, c_, t = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int()
+        _check(self.L.cfd_matrix_stats(self.h, name.encode(), C.byref(a), C.byref(b), C.byref(c_), C.byref(t)))
+        return dict(nnz=a.value, stored_values=b.value, stored_indices=c_.value, lanes_per_row=t.value)
 
     def kernel_launches(self):
         return int(self.L.cfd_kernel_launches(self.h))

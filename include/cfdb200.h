@@ -202,6 +202,9 @@ int cfd_timeStep_host(cfd_ctx* ctx, double* U, double* P, cfd_step_report* repor
 int cfd_profile(cfd_ctx* ctx, int enable);
 int cfd_profile_get(cfd_ctx* ctx, const char* name, double* ms, long long* launches, double* bytes);
 long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context so far */
+/* layout statistics of a device matrix ("K", "G", "GT", "Z"): true non-zeros, stored value slots (padding included),
+ * stored index integers (after per-slice offset compression), lanes per row */
+int cfd_matrix_stats(cfd_ctx* ctx, const char* name, long long* nnz, long long* stored_values, long long* stored_indices, int* lanes_per_row);
 
 /* ---- stand-alone kernels on caller data (micro-benchmarks and parity tests) ------------------- */
 /* y = alpha*A*x + beta*y for `nvec` vectors sharing one CSR matrix; x is [nvec][ncols], y [nvec][nrows] host arrays */
