@@ -417,3 +417,36 @@ def test_coloured_scatter_is_reproducible(mesh, name):
         U, P = cc.fields()
         bar = 1e-6 if (scheme == "explicit" or name.startswith("q1")) else 5e-3
         assert rel(U, oo.U) <= bar and rel(P, oo.P) <= bar
+
+
+def test_pcg_against_library_solver(mesh):
+    """Independent cross-check of the persistent PCG kernel: the same system solved by a plain cuSPARSE + cuBLAS CG
+    (baseline/lib_pcg.cu, the reference's GPU call sequence on current APIs) -- same iteration count, same solution."""
+    import ctypes as C
+    import os
+    import subprocess
+    import fracstep
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(root, "baseline")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        LB = C.CDLL(os.path.join(root, "baseline", "liblibpcg.so"))
+    except Exception as e:   # cuSPARSE / cuBLAS not available
+        pytest.skip("library baseline not buildable: %s" % e)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    LB.lib_pcg.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, C.c_double, C.c_int, ip, dp]
+    s = fracstep.Solver(mesh("q2_c6_lib", n=6, cluster=2.0), "explicit")
+    s.ctx.time_loop(2)
+    R2, x_ours, its_ours = np.ascontiguousarray(s.ctx.download("R2")), s.ctx.download("Pdot"), s.ctx.last_cg()
+    rs = np.ascontiguousarray(s.arr("sparseZrowStarts"), np.int32)
+    cl = np.ascontiguousarray(s.arr("sparseZcol"), np.int32)
+    v = np.ascontiguousarray(s.arr("sparseZvalue"), np.float64)
+    n = len(rs) - 1
+    rows = np.repeat(np.arange(n), np.diff(rs))
+    dinv = np.ones(n)
+    dinv[rows[rows == cl]] = 1.0 / v[rows == cl]
+    x = np.zeros(n)
+    its, ms = C.c_int(), C.c_double()
+    assert LB.lib_pcg(n, len(cl), rs.ctypes.data_as(ip), cl.ctypes.data_as(ip), v.ctypes.data_as(dp), dinv.ctypes.data_as(dp),
+                      R2.ctypes.data_as(dp), x.ctypes.data_as(dp), 1e-6, 1000, C.byref(its), C.byref(ms)) == 0
+    assert abs(its.value - its_ours) <= 1
+    assert rel(x_ours, x) <= 1e-9
