@@ -1620,7 +1620,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       std::vector<double> dinv(NPo, 1.0);
 #pragma omp parallel for schedule(static)
       for (int r = 0; r < NPo; r++)
-         for (int k = P->sparseZrowStarts[r]; k < P->sparseZrowStarts[r + 1]; k++)
+         for (int k = P->sparseZrowStarts[r]; !o.cg_no_precond && k < P->sparseZrowStarts[r + 1]; k++)
             if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
       TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
    }

@@ -54,7 +54,7 @@ class cfd_options(C.Structure):
     _fields_ = [
         ("cg_tol", C.c_double), ("cg_maxit", C.c_int), ("cg_warm_start", C.c_int),
         ("bicg_tol", C.c_double), ("bicg_maxit", C.c_int), ("maxacc_rule", C.c_int),
-        ("device", C.c_int), ("ebe_scatter", C.c_int), ("reserved", C.c_int * 7), ("cuda_stream", C.c_void_p),
+        ("device", C.c_int), ("ebe_scatter", C.c_int), ("cg_no_precond", C.c_int), ("reserved", C.c_int * 6), ("cuda_stream", C.c_void_p),
     ]
 
 

@@ -109,7 +109,9 @@ typedef struct cfd_options {
    int device;        /* CUDA device ordinal; -1 = current device */
    int ebe_scatter;   /* element-by-element scatter: 0 (default) = FP64 atomicAdd, one launch; 1 = element colouring, one launch
                          per colour, plain stores, bitwise reproducible (the reference's scheme, BCH.cu:906-939) */
-   int reserved[7];
+   int cg_no_precond; /* 0 (default) = Jacobi-preconditioned CG (BCH.cpp:4017, BCH.cu:437, GQ.cu:348); 1 = plain CG, what the
+                         reference's implicit CPU build runs (its Jacobi line is commented out, GQ.cpp:4514) */
+   int reserved[6];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 

@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_*.npz from the REFERENCE ITSELF.
+
+`make -C oracle ref` compiles the unmodified reference sources
+  /root/reference/fractionalStep/explicit/Cpp/blascoCodinaHuerta.cpp   -> oracle/_ref/bch_cpu
+  /root/reference/fractionalStep/implicit/Cpp/guermondQuartapelle.cpp  -> oracle/_ref/gq_cpu
+against the stand-ins for MKL / CSparse / PARALUTION in oracle/shim (those libraries are not in the image).  This
+script runs the two programs exactly as a user of the reference would -- ProblemName.txt + <name>.inp in the working
+directory, no arguments -- and stores what they write: the nodal fields of <name>.dat, the monitor table on stdout,
+and the Krylov iteration counts the stand-ins log.
+
+Two kinds of run per scheme:
+  as-is : the reference's own solver settings (explicit: Jacobi-CG, squared-norm test 1e-12; implicit: CG without
+          preconditioner, squared-norm test 1e-6, BiCGStab rel 1e-6);
+  tight : the stand-ins are told (REF_SHIM_* environment) to iterate to 1e-13, which takes the third-party solver's
+          stopping rule out of the comparison and leaves the reference's own arithmetic (reader, node generation,
+          element integrals, step0, right-hand sides, BC handling, updates).
+`converge` is set negative for the implicit runs: the implicit CPU time loop keeps the SIGNED value of the largest
+|acceleration| (guermondQuartapelle.cpp:3336-3341: `if (abs(a) > maxAcc) maxAcc = a`), so a negative largest entry reads
+as "steady state reached" and ends the run after a step or two.
+
+Needs /root/reference (through the prebuilt binaries only) -- run it in the build container:
+   make -C oracle ref && python tests/golden/make_ref_golden.py
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "cfd-with-cuda_b200"))
+import meshgen  # noqa: E402
+
+BIN = {"explicit": os.path.join(ROOT, "oracle", "_ref", "bch_cpu"), "implicit": os.path.join(ROOT, "oracle", "_ref", "gq_cpu")}
+TIGHT = {"REF_SHIM_CG_TOL": "1e-13", "REF_SHIM_CG_PRECOND": "1", "REF_SHIM_BICG_TOL": "1e-13"}
+NEVER_STEADY = -1e30
+
+# name -> (scheme, mesh generator, generator keywords, time steps, stand-in environment, node stride of the stored fields)
+CASES = {
+    "ref_bch_cav4": ("explicit", "cube", dict(n=4, cluster=0.0), 5, {}, 1),
+    "ref_bch_cav6c": ("explicit", "cube", dict(n=6, cluster=2.0), 4, {}, 1),
+    "ref_bch_chan644": ("explicit", "channel", dict(nx=6, ny=4, nz=4), 4, {}, 1),
+    "ref_gq_cav4": ("implicit", "cube", dict(n=4, cluster=0.0, converge=NEVER_STEADY), 3, {}, 1),
+    "ref_gq_cav4_tight": ("implicit", "cube", dict(n=4, cluster=0.0, converge=NEVER_STEADY), 3, TIGHT, 1),
+    "ref_gq_cav6c_tight": ("implicit", "cube", dict(n=6, cluster=2.0, viscosity=0.001, converge=NEVER_STEADY), 3, TIGHT, 1),
+    "ref_gq_chan644_tight": ("implicit", "channel", dict(nx=6, ny=4, nz=4, converge=NEVER_STEADY), 3, TIGHT, 1),
+    # BASELINE.json configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (meshgen.cube(30, cluster=2.0) is that
+    # file byte for byte, tests/test_oracle.py), only t_final shortened; every 61st node stored
+    "ref_bch_ne27000": ("explicit", "cube", dict(n=30, cluster=2.0), 3, {}, 61),
+    # implicit, Re = 1000, reference settings.  No "tight" twin: on this mesh the under-integrated Q2 momentum matrix (27-node
+    # mass matrix, 8 Gauss points, GQ.cpp:3490-3500) lets BiCGStab stagnate -- two correct implementations that both report
+    # 1e-10 differ by 4e-4 in the free velocities -- so forcing the tolerance down pins nothing.
+    "ref_gq_ne27000": ("implicit", "cube", dict(n=30, cluster=2.0, viscosity=0.001, converge=NEVER_STEADY), 2, {}, 61),
+}
+
+
+def write_inp(path, kind, kw, steps):
+    kw = dict(kw)
+    dt = kw.setdefault("dt", 0.001)
+    getattr(meshgen, kind)(path, t_final=(steps - 0.5) * dt, **kw)
+
+
+def run_reference(scheme, inp_kind, kw, steps, env, workdir):
+    name = "case"
+    write_inp(os.path.join(workdir, name + ".inp"), inp_kind, kw, steps)
+    with open(os.path.join(workdir, "ProblemName.txt"), "w") as f:
+        f.write(name + "\n")
+    log = os.path.join(workdir, "shim.log")
+    e = dict(os.environ, REF_SHIM_LOG=log, **env)
+    out = subprocess.run([BIN[scheme]], cwd=workdir, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         stdin=subprocess.DEVNULL, check=True).stdout
+    # monitor table: explicit "timeN iter time u v w p timeSpent maxAcc", implicit "timeN time u v w p timeSpent maxAcc"
+    ncol = 9 if scheme == "explicit" else 8
+    rows = [ln.split() for ln in out.splitlines() if re.match(r"^\s*\d+\s+[\d.]+\s+-?\d", ln)]
+    rows = [r for r in rows if len(r) == ncol]
+    mon = np.array([[float(v) for v in r] for r in rows])
+    dat = os.path.join(workdir, name + ".dat")
+    with open(dat) as f:
+        lines = [f.readline() for _ in range(3)]
+    NN = int(lines[2].split("N=")[1].split(",")[0])
+    NEsub = int(lines[2].split("E=")[1].split(",")[0])
+    d = np.loadtxt(dat, skiprows=3, max_rows=NN)
+    cg, bicg = [], []
+    for ln in open(log):
+        w = ln.split()
+        (cg if w[0] == "cg" else bicg).append((int(w[1]), int(w[2])))
+    return dict(dat_path=dat, NN=NN, NEsub=NEsub, table=d, monitor=mon, cg=np.array(cg).reshape(-1, 2),
+                bicg=np.array(bicg).reshape(-1, 2), header=lines)
+
+
+def main(only=None):
+    for b in BIN.values():
+        if not os.path.exists(b):
+            raise SystemExit("missing %s: run `make -C oracle ref` where /root/reference is mounted" % b)
+    for name, (scheme, kind, kw, steps, env, stride) in CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            r = run_reference(scheme, kind, kw, steps, env, d)
+            t = r["table"]
+            NN = r["NN"]
+            NNp = (kw["n"] + 1) ** 3 if kind == "cube" else (kw["nx"] + 1) * (kw["ny"] + 1) * (kw["nz"] + 1)
+            U = np.concatenate([t[:, 3], t[:, 4], t[:, 5]])
+            P = t[:NNp, 6]              # corner nodes come first (BCH.cpp:1352-1368); the rest of the column is interpolated
+            done = int(r["monitor"][-1, 0])
+            assert done == steps, (name, done, steps)
+            out = dict(scheme=scheme, mesh_kind=kind, mesh_kw=repr(kw), steps=steps, shim_env=repr(env), NN=NN, NNp=NNp,
+                       monitor=r["monitor"], cg=r["cg"], bicg=r["bicg"], normU=np.linalg.norm(U), normP=np.linalg.norm(P),
+                       stride=stride, dat_header="".join(r["header"]))
+            if stride == 1:
+                out.update(U=U, P=P, P_all_nodes=t[:, 6], coord=t[:, :3])
+                # first / last connectivity rows of the Tecplot file (format pin for the writer)
+                with open(r["dat_path"]) as f:
+                    tail = f.readlines()[3 + NN:]
+                out.update(conn=np.array([[int(v) for v in ln.split()] for ln in tail], dtype=np.int32))
+            else:
+                idx = np.arange(0, NN, stride)
+                pidx = np.arange(0, NNp, stride)
+                out.update(node_idx=idx, U_sub=np.stack([t[idx, 3], t[idx, 4], t[idx, 5]]), pres_idx=pidx, P_sub=P[pidx])
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+            print("%-22s %s %d steps  NN %d  cg %s  bicg %s" % (name, scheme, done, NN, list(r["cg"][:, 0]), list(r["bicg"][:, 0])))
+
+
+if __name__ == "__main__":
+    main(set(sys.argv[1:]))
