@@ -115,15 +115,39 @@ def ncu_traffic(workload, kernel_class):
     return None
 
 
-def make_inp(w, path, n=None):
+def make_inp(w, path, n=None, **extra):
     import meshgen
     if w.get("channel"):
         f = 1.0 if n is None else n / float(w["n"])
         meshgen.channel(path, nx=max(2, int(w["n"] * f)), ny=max(2, int(w["ny"] * f)), nz=max(2, int(w["nz"] * f)), NENv=w["NENv"],
-                        viscosity=w["viscosity"], dt=w["dt"])
+                        viscosity=w["viscosity"], dt=w["dt"], **extra)
         return
     meshgen.cube(path, n or w["n"], cluster=w["cluster"], NENv=w["NENv"], viscosity=w["viscosity"], dt=w["dt"],
-                 full_precision=not w.get("inp", False))
+                 full_precision=not w.get("inp", False), **extra)
+
+
+REF_BIN = {"explicit": os.path.join(ROOT, "oracle", "_ref", "bch_cpu"), "implicit": os.path.join(ROOT, "oracle", "_ref", "gq_cpu")}
+REF_SAMPLE_N = 30   # the reference's own preprocessing and the serial symmetric SpMV of its CG are slow beyond the shipped mesh size
+
+
+def run_reference_binary(w, steps, warmup, n):
+    """The UNMODIFIED reference program (oracle/_ref: its source compiled against the MKL / CSparse / PARALUTION stand-ins of
+    oracle/shim, see oracle/Makefile) run the way its users run it: ProblemName.txt + <name>.inp in the working directory.
+    Times come from the `TimeSpend` column of its own monitor table.  It sets its thread count itself
+    (N_OPENMP_THREADS = 8, BCH.cpp:86).  Returns seconds per step of the last `steps` steps."""
+    with tempfile.TemporaryDirectory() as d:
+        total = steps + warmup
+        make_inp(w, os.path.join(d, "case.inp"), n, t_final=(total - 0.5) * w["dt"], converge=-1e30)
+        with open(os.path.join(d, "ProblemName.txt"), "w") as f:
+            f.write("case\n")
+        out = subprocess.run([REF_BIN[w["scheme"]]], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, stdin=subprocess.DEVNULL,
+                             text=True, check=True).stdout
+    ncol, tcol = (9, 7) if w["scheme"] == "explicit" else (8, 6)
+    rows = [ln.split() for ln in out.splitlines()]
+    rows = [r for r in rows if len(r) == ncol and r[0].isdigit()]
+    if len(rows) != total:
+        raise RuntimeError("reference binary printed %d monitor rows, expected %d" % (len(rows), total))
+    return sum(float(r[tcol]) for r in rows[warmup:]) / steps
 
 
 def run_oracle(w, steps, warmup, n, threads=0):
@@ -151,6 +175,19 @@ def run_oracle(w, steps, warmup, n, threads=0):
 
 
 def cpu_sample(w, steps, warmup):
+    if w["NENv"] == 27 and all(os.path.exists(b) for b in REF_BIN.values()):
+        # Q2/Q1 workloads: the reference itself (it has no Q1/Q1 element: its NENv == 8 branch is commented out, BCH.cpp:2303-2305)
+        n_s = min(w["n"], REF_SAMPLE_N)
+        sec = run_reference_binary(w, steps, warmup, n_s)
+        scale = (n_s / float(w["n"])) ** 3
+        sample = ("the reference program itself (%s compiled against oracle/shim stand-ins for MKL/CSparse/PARALUTION), %s Q2/Q1 %s mesh, "
+                  "%d timed steps after %d warm-up, per-step times from its own monitor table"
+                  % ("blascoCodinaHuerta.cpp" if w["scheme"] == "explicit" else "guermondQuartapelle.cpp",
+                     ("%d^3" % n_s) if not w.get("channel") else "%d/%d-scale channel" % (n_s, w["n"]), w["scheme"], steps, warmup))
+        if n_s != w["n"]:
+            sample += "; steps/s scaled by element count %d^3/%d^3 to the workload mesh" % (n_s, w["n"])
+        return dict(value=scale / sec, unit="steps/s", cores=min(8, os.cpu_count() or 8), kind="reference", sample=sample,
+                    sample_steps_per_s=1.0 / sec)
     n_s = min(w["n"], CPU_SAMPLE_N)
     sec, info = run_oracle(w, steps, warmup, n_s)
     scale = (n_s / float(w["n"])) ** 3   # per-step work ~ elements (Krylov iteration growth with n ignored: favours the CPU)

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace {
 
@@ -40,6 +41,16 @@ void shim_log(const char* what, int its, int converged) {
    fprintf(stderr, "mkl_shim: %s is not provided (the reference never calls it on the fractional-step path)\n", name);
    abort();
 }
+
+struct SymCache {
+   const double* a = nullptr;
+   const int *ia = nullptr, *ja = nullptr;
+   int n = 0, nnz = 0;
+   double chk = 0.0;
+   char uplo = 0;
+   std::vector<int> rs, col;
+   std::vector<double> val;
+};
 
 // private slots of ipar / dpar (the interface reserves everything past ipar[10] / dpar[7] for the solver)
 enum { PHASE = 100 };
@@ -76,18 +87,41 @@ void mkl_dcsrmv(const char* transa, const MKL_INT* m, const MKL_INT* k, const do
    }
 }
 
+// The stored triangle is expanded once into a full row-wise copy (kept for as long as the caller keeps passing the same
+// arrays; a sampled checksum guards against in-place edits) so that every call is one row-parallel sweep -- the role MKL's
+// threaded kernels play in the reference's `-mkl=parallel` build.  The reference calls this once per CG iteration with a
+// matrix that never changes (BCH.cpp:4036, GQ.cpp:4533).
 void mkl_dcsrsymv(const char* uplo, const MKL_INT* m, const double* a, const MKL_INT* ia, const MKL_INT* ja, const double* x, double* y) {
+   static SymCache C;
    const int n = *m;
-   const bool upper = (*uplo == 'u' || *uplo == 'U');
-   for (int i = 0; i < n; i++) y[i] = 0.0;
+   const int nnz = ia[n] - 1;
+   double chk = 0.0;
+   for (int p = 0; p < nnz; p += 61) chk += a[p];
+   if (C.a != a || C.ia != ia || C.ja != ja || C.n != n || C.nnz != nnz || C.chk != chk || C.uplo != *uplo) {
+      const bool upper = (*uplo == 'u' || *uplo == 'U');
+      C.a = a; C.ia = ia; C.ja = ja; C.n = n; C.nnz = nnz; C.chk = chk; C.uplo = *uplo;
+      C.rs.assign(n + 1, 0);
+      for (int i = 0; i < n; i++)
+         for (int p = ia[i] - 1; p < ia[i + 1] - 1; p++) {
+            const int j = ja[p] - 1;
+            if (j == i) C.rs[i + 1]++;
+            else if (upper ? (j > i) : (j < i)) { C.rs[i + 1]++; C.rs[j + 1]++; }
+         }
+      for (int i = 0; i < n; i++) C.rs[i + 1] += C.rs[i];
+      C.col.resize(C.rs[n]); C.val.resize(C.rs[n]);
+      std::vector<int> fill(C.rs.begin(), C.rs.end() - 1);
+      for (int i = 0; i < n; i++)
+         for (int p = ia[i] - 1; p < ia[i + 1] - 1; p++) {
+            const int j = ja[p] - 1;
+            if (j == i || (upper ? (j > i) : (j < i))) { C.col[fill[i]] = j; C.val[fill[i]++] = a[p]; }
+            if (j != i && (upper ? (j > i) : (j < i))) { C.col[fill[j]] = i; C.val[fill[j]++] = a[p]; }
+         }
+   }
+#pragma omp parallel for schedule(static)
    for (int i = 0; i < n; i++) {
       double s = 0.0;
-      for (int p = ia[i] - 1; p < ia[i + 1] - 1; p++) {
-         const int j = ja[p] - 1;
-         if (j == i) s += a[p] * x[j];
-         else if (upper ? (j > i) : (j < i)) { s += a[p] * x[j]; y[j] += a[p] * x[i]; }
-      }
-      y[i] += s;
+      for (int p = C.rs[i]; p < C.rs[i + 1]; p++) s += C.val[p] * x[C.col[p]];
+      y[i] = s;
    }
 }
 

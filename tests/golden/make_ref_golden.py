@@ -12,7 +12,7 @@ and the Krylov iteration counts the stand-ins log.
 Two kinds of run per scheme:
   as-is : the reference's own solver settings (explicit: Jacobi-CG, squared-norm test 1e-12; implicit: CG without
           preconditioner, squared-norm test 1e-6, BiCGStab rel 1e-6);
-  tight : the stand-ins are told (REF_SHIM_* environment) to iterate to 1e-13, which takes the third-party solver's
+  tight : the stand-ins are told (REF_SHIM_* environment) to iterate to 1e-12, which takes the third-party solver's
           stopping rule out of the comparison and leaves the reference's own arithmetic (reader, node generation,
           element integrals, step0, right-hand sides, BC handling, updates).
 `converge` is set negative for the implicit runs: the implicit CPU time loop keeps the SIGNED value of the largest
@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "cfd-with-cuda_b200"))
 import meshgen  # noqa: E402
 
 BIN = {"explicit": os.path.join(ROOT, "oracle", "_ref", "bch_cpu"), "implicit": os.path.join(ROOT, "oracle", "_ref", "gq_cpu")}
-TIGHT = {"REF_SHIM_CG_TOL": "1e-13", "REF_SHIM_CG_PRECOND": "1", "REF_SHIM_BICG_TOL": "1e-13"}
+TIGHT = {"REF_SHIM_CG_TOL": "1e-12", "REF_SHIM_CG_PRECOND": "1", "REF_SHIM_BICG_TOL": "1e-12"}
 NEVER_STEADY = -1e30
 
 # name -> (scheme, mesh generator, generator keywords, time steps, stand-in environment, node stride of the stored fields)
@@ -58,18 +58,29 @@ CASES = {
 }
 
 
-def write_inp(path, kind, kw, steps):
-    kw = dict(kw)
+# restart runs (readRestartFile, BCH.cpp:4214-4242 / isRestart 1): the reference runs `first` steps, its case.dat becomes
+# case_restart.dat, and a second run of the program continues from it for `steps` more steps.
+# name -> (scheme, generator, keywords, first, steps, environment)
+RESTART_CASES = {
+    "ref_bch_cav4_restart": ("explicit", "cube", dict(n=4, cluster=0.0), 3, 2, {}),
+    "ref_gq_cav4_restart_tight": ("implicit", "cube", dict(n=4, cluster=0.0, converge=NEVER_STEADY), 2, 2, TIGHT),
+}
+
+
+def write_inp(path, kind, kw, steps, **extra):
+    kw = dict(kw, **extra)
     dt = kw.setdefault("dt", 0.001)
     getattr(meshgen, kind)(path, t_final=(steps - 0.5) * dt, **kw)
 
 
-def run_reference(scheme, inp_kind, kw, steps, env, workdir):
+def run_reference(scheme, inp_kind, kw, steps, env, workdir, **extra):
     name = "case"
-    write_inp(os.path.join(workdir, name + ".inp"), inp_kind, kw, steps)
+    write_inp(os.path.join(workdir, name + ".inp"), inp_kind, kw, steps, **extra)
     with open(os.path.join(workdir, "ProblemName.txt"), "w") as f:
         f.write(name + "\n")
     log = os.path.join(workdir, "shim.log")
+    if os.path.exists(log):
+        os.remove(log)
     e = dict(os.environ, REF_SHIM_LOG=log, **env)
     out = subprocess.run([BIN[scheme]], cwd=workdir, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          stdin=subprocess.DEVNULL, check=True).stdout
@@ -125,5 +136,24 @@ def main(only=None):
             print("%-22s %s %d steps  NN %d  cg %s  bicg %s" % (name, scheme, done, NN, list(r["cg"][:, 0]), list(r["bicg"][:, 0])))
 
 
+def main_restart(only=None):
+    for name, (scheme, kind, kw, first, steps, env) in RESTART_CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            r1 = run_reference(scheme, kind, kw, first, env, d)
+            os.replace(r1["dat_path"], os.path.join(d, "case_restart.dat"))
+            r = run_reference(scheme, kind, kw, steps, env, d, is_restart=1)
+            t, NN = r["table"], r["NN"]
+            NNp = (kw["n"] + 1) ** 3
+            assert int(r["monitor"][-1, 0]) == steps
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), scheme=scheme, mesh_kind=kind, mesh_kw=repr(kw), steps=steps,
+                                first=first, shim_env=repr(env), NN=NN, NNp=NNp, stride=1, restart_table=r1["table"],
+                                dat_header="".join(r1["header"]), U=np.concatenate([t[:, 3], t[:, 4], t[:, 5]]), P=t[:NNp, 6],
+                                monitor=r["monitor"], cg=r["cg"], bicg=r["bicg"])
+            print("%-26s %s %d + %d steps  cg %s" % (name, scheme, first, steps, list(r["cg"][:, 0])))
+
+
 if __name__ == "__main__":
+    main_restart(set(sys.argv[1:]))
     main(set(sys.argv[1:]))

@@ -9,7 +9,7 @@ and run the way a user runs them; tests/golden/make_ref_golden.py is the generat
                   Implicit (plain CG to 1e-3, BiCGStab to 1e-6 on an under-integrated momentum matrix) is compared with the
                   same settings but a loose bar: where in the iteration the residual is tested differs between BiCGStab
                   implementations and moves the fields by ~1e-5.
-  tight fixtures  Krylov tolerances forced to 1e-13 on both sides: isolates everything that is the reference's own code.
+  tight fixtures  Krylov tolerances forced to 1e-12 on both sides: isolates everything that is the reference's own code.
 """
 import ast
 import os
@@ -150,7 +150,52 @@ def test_tecplot_writer_against_reference_file(mesh, name, tmp_path):
     assert np.array_equal(conn, g["conn"])
 
 
+RESTART = ["ref_bch_cav4_restart", "ref_gq_cav4_restart_tight"]
+
+
+def restart_dir(tmp_path, g, meta):
+    """case.inp with isRestart 1 and case_restart.dat rebuilt from the rows the reference's FIRST run wrote
+    (`scientific, precision(11)`, BCH.cpp:4288-4292 == "%.11e")."""
+    import meshgen
+    getattr(meshgen, meta["kind"])(str(tmp_path / "case.inp"), is_restart=1, **meta["kw"])
+    with open(str(tmp_path / "case_restart.dat"), "w") as f:
+        f.write(str(g["dat_header"]))
+        for row in g["restart_table"]:
+            f.write(" ".join("%.11e" % v for v in row) + "\n")
+    return str(tmp_path / "case.inp"), str(tmp_path / "case_restart.dat")
+
+
+@pytest.mark.parametrize("name", RESTART)
+def test_oracle_reproduces_reference_restart(name, tmp_path):
+    """readRestartFile (BCH.cpp:4214-4242, GQ.cpp likewise): the reference continued from its own .dat file."""
+    import orc
+    g, meta = load(name)
+    inp, dat = restart_dir(tmp_path, g, meta)
+    o = orc.Oracle(inp, meta["scheme"], **settings(meta)[0])
+    o.read_restart(dat)
+    o.run(meta["steps"])
+    eu, ep = errors(o.U, o.P, g, meta, o.i("NN"))
+    assert eu <= 1e-7 and ep <= 1e-7, (eu, ep)
+    assert all(abs(a - b) <= 2 for a, b in zip(o.arr("cgIters"), g["cg"][:, 0]))
+
+
 # ---------------------------------------------------------------------------------------------------- GPU: the product
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", RESTART)
+def test_cuda_path_reproduces_reference_restart(name, tmp_path):
+    import fracstep
+    g, meta = load(name)
+    inp, _ = restart_dir(tmp_path, g, meta)
+    popt = settings(meta)[1]
+    s = fracstep.Solver(inp, meta["scheme"], opts=fracstep.options(**popt) if popt else None)   # reads case_restart.dat itself
+    reps = s.ctx.time_loop(meta["steps"])
+    U, P = s.ctx.fields()
+    eu, ep = errors(U, P, g, meta, s.i("NN"))
+    assert eu <= 1e-6 and ep <= 1e-6, (eu, ep)
+    assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cg"][:, 0].sum())) <= 2 * len(g["cg"])
+    s.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SMALL + FULL)
 def test_cuda_path_reproduces_reference_run(mesh, name):
