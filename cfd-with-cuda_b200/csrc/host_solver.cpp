@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 
@@ -578,7 +579,19 @@ int cfd_solver_main(const char* workdir, int scheme, int max_steps) {
    printf("\n*********************************************************\n\n");
    double t0 = now_s();
    cfd_solver* s = nullptr;
-   int rc = cfd_solver_create_from_inp((dir + name + ".inp").c_str(), scheme, nullptr, 1, &s);
+   // the reference hard-codes its solver settings, differently in each of its four builds: the program
+   // takes the GPU builds' (the defaults) and lets the environment select the others
+   cfd_options opt;
+   cfd_default_options(&opt);
+   if (const char* v = getenv("CFD_CG_TOL")) opt.cg_tol = atof(v);
+   if (const char* v = getenv("CFD_CG_MAXIT")) opt.cg_maxit = atoi(v);
+   if (const char* v = getenv("CFD_CG_WARM_START")) opt.cg_warm_start = atoi(v);
+   if (const char* v = getenv("CFD_CG_NO_PRECOND")) opt.cg_no_precond = atoi(v);
+   if (const char* v = getenv("CFD_BICG_TOL")) opt.bicg_tol = atof(v);
+   if (const char* v = getenv("CFD_BICG_MAXIT")) opt.bicg_maxit = atoi(v);
+   if (const char* v = getenv("CFD_MAXACC_RULE")) opt.maxacc_rule = atoi(v);
+   if (const char* v = getenv("CFD_DEVICE")) opt.device = atoi(v);
+   int rc = cfd_solver_create_from_inp((dir + name + ".inp").c_str(), scheme, &opt, 1, &s);
    if (rc) return rc;
    const Mesh& m = s->mesh;
    printf("readInputFile() .. step0() took  %8.3f seconds.\n", now_s() - t0);

@@ -264,7 +264,11 @@ int cfd_solver_write_tecplot_fields(cfd_solver* s, const char* dat_path, const c
 int cfd_solver_read_restart_fields(cfd_solver* s, const char* dat_path, double* U, double* P);
 int cfd_solver_read_restart(cfd_solver* s, const char* dat_path);
 /* the reference's main(): reads ./ProblemName.txt, runs to t_final, prints the monitor table,
- * writes <name>.dat.  max_steps > 0 bounds the run. */
+ * writes <name>.dat.  max_steps > 0 bounds the run.  Solver settings: cfd_default_options (= the reference's GPU builds),
+ * overridden by the environment variables CFD_CG_TOL, CFD_CG_MAXIT, CFD_CG_WARM_START, CFD_CG_NO_PRECOND, CFD_BICG_TOL,
+ * CFD_BICG_MAXIT, CFD_MAXACC_RULE, CFD_DEVICE (same meaning as the cfd_options fields).
+ * csrc/solver_main.cpp wraps this into the executables bin/solverGPU_explicit and bin/solverGPU_implicit, which -- like the
+ * reference's solverGPU (makeBCH:16-18) -- take no arguments and work on the current directory. */
 int cfd_solver_main(const char* workdir, int scheme, int max_steps);
 
 #ifdef __cplusplus

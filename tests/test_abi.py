@@ -61,6 +61,27 @@ def test_no_cpu_fallback_without_device(mesh):
         s.ctx
 
 
+def test_solverGPU_executables_fail_loudly_without_device(mesh, tmp_path):
+    """bin/solverGPU_explicit / _implicit (the reference's executables, no arguments) are built with the library; without a
+    GPU they must stop with an error code and a message instead of computing anything on the CPU."""
+    import shutil
+    import subprocess
+    import torch
+    for scheme in ("explicit", "implicit"):
+        exe = os.path.join(ROOT, "cfd-with-cuda_b200", "bin", "solverGPU_" + scheme)
+        assert os.access(exe, os.X_OK), exe
+        # no ProblemName.txt: an I/O error, not a crash
+        out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, stdin=subprocess.DEVNULL, timeout=120)
+        assert out.returncode == 1 and "ProblemName.txt" in out.stderr
+    if torch.cuda.is_available():
+        return
+    shutil.copy(mesh("abi_q2", n=2), str(tmp_path / "c.inp"))
+    (tmp_path / "ProblemName.txt").write_text("c\n")
+    out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, stdin=subprocess.DEVNULL, timeout=120)
+    assert out.returncode == 1 and "solverGPU: error -2" in out.stderr
+    assert not os.path.exists(str(tmp_path / "c.dat"))
+
+
 def test_product_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "cfd-with-cuda_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -217,3 +217,43 @@ def test_cuda_path_reproduces_reference_run(mesh, name):
     elif dcg is not None:
         assert all(abs(r["cg_iterations"] - k) <= 2 for r, k in zip(reps, g["cg"][:, 0]))
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,env", [("ref_bch_cav4", {}), ("ref_bch_chan644", {}),
+                                      ("ref_gq_cav4_tight", {"CFD_CG_TOL": "1e-12", "CFD_BICG_TOL": "1e-12"})])
+def test_solverGPU_program_against_reference_files(name, env, tmp_path):
+    """Process-level drop-in: bin/solverGPU_<scheme> run like the reference's executable -- no arguments,
+    ProblemName.txt + case.inp in the working directory -- must write the case.dat the reference wrote and print the same
+    monitor table (all columns but the wall-clock one)."""
+    import meshgen
+    g, meta = load(name)
+    exe = os.path.join(ROOT, "cfd-with-cuda_b200", "bin", "solverGPU_" + meta["scheme"])
+    kw = dict(meta["kw"])
+    getattr(meshgen, meta["kind"])(str(tmp_path / "case.inp"), t_final=(meta["steps"] - 0.5) * kw.get("dt", 0.001), **kw)
+    (tmp_path / "ProblemName.txt").write_text("case\n")
+    out = subprocess.run([exe], cwd=str(tmp_path), env=dict(os.environ, **env), capture_output=True, text=True, stdin=subprocess.DEVNULL,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    NN = int(g["NN"])
+    lines = open(str(tmp_path / "case.dat")).read().split("\n")
+    assert "\n".join(lines[:3]) + "\n" == str(g["dat_header"])
+    t = np.array([[float(v) for v in ln.split()] for ln in lines[3:3 + NN]])
+    assert np.array_equal(t[:, :3], g["coord"])
+    eu, ep = errors(t[:, 3:6].T.ravel(), t[:int(g["NNp"]), 6], g, meta, NN)
+    assert eu <= 1e-6 and ep <= 1e-6, (eu, ep)
+    assert np.allclose(t[:, 6], g["P_all_nodes"], rtol=0, atol=1e-6 * np.abs(g["P_all_nodes"]).max())
+    conn = np.array([[int(v) for v in ln.split()] for ln in lines[3 + NN:] if ln.strip()], dtype=np.int32)
+    assert np.array_equal(conn, g["conn"])
+    # monitor table: explicit "timeN iter time u v w p TimeSpend maxAcc", implicit "timeN time u v w p TimeSpend maxAcc"
+    ncol, skip = (9, 7) if meta["scheme"] == "explicit" else (8, 6)
+    rows = [ln.split() for ln in out.stdout.split("\n")]
+    rows = np.array([[float(v) for v in r] for r in rows if len(r) == ncol and r[0].isdigit()])
+    ref = g["monitor"]
+    assert rows.shape == ref.shape
+    keep = [c for c in range(ncol) if c != skip]
+    if meta["scheme"] == "implicit":
+        # the implicit CPU loop's maxAcc is not a maximum: `if (abs(a) > maxAcc) maxAcc = a` keeps SIGNED values, so later
+        # entries are compared against a possibly negative running value (GQ.cpp:3336-3341); the GPU builds take max|a|
+        keep.remove(ncol - 1)
+    assert np.allclose(rows[:, keep], ref[:, keep], rtol=1e-4, atol=2e-5), (rows, ref)
