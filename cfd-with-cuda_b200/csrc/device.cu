@@ -905,7 +905,9 @@ __global__ void __launch_bounds__(1024) k_diag_sync(int iters, int mode, double*
 
 struct BicgArgs {
    Sell A;
-   const int* part;
+   const int* part;   // per-block slice ranges of the static share
+   int dynStart;      // first slice handed out through dynCounter (0 = everything dynamic)
+   int* dynCounter;   // NULL = everything static
    int vidx;
    int n;
    const double* b;   // [3][n]
@@ -923,16 +925,30 @@ struct BicgArgs {
 // Specialised on NA so that the common late phase (one slow system left) runs a lean single-vector loop
 // with four matrix pairs in flight per lane.
 template <int NA>
-__device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, const double* __restrict__ val, int n, const double* in,
-                                             double* out, const int (&sys)[3], const double* l1, double (&d0)[3], double (&d1)[3],
+__device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int dynStart, int* dynCounter, const double* __restrict__ val, int n,
+                                             const double* in, double* out, const int (&sys)[3], const double* l1, double (&d0)[3], double (&d1)[3],
                                              int gwarp, int nwarps, int lane) {
    const int T = A.T, sub = lane % T;
-   const SliceRange sr = slice_range(A.nslices, part, gwarp, nwarps);
+   // Static share [0, nstatic) dealt as in slice_range; the rest is taken one slice at a time from a shared counter, so that
+   // warps whose slices were cheap (rows of a Q2 mesh differ 4.6x in length, and in how well their gathers hit L1) keep
+   // working instead of waiting at the grid reduction: measured on the 30^3 Taylor-Hood cavity, block 0 used to wait 22 us
+   // after a 29 us SpMV share.  `dynCounter` must be 0 on entry; the kernel resets it after the reduction that follows.
+   const int nstatic = dynCounter ? dynStart : A.nslices;
+   const SliceRange sr = slice_range(nstatic, part, gwarp, nwarps);
    size_t base[NA];
    double s0[NA], s1[NA];   // dot-product partials stay in registers (no dynamically indexed local arrays in the loop)
 #pragma unroll
    for (int q = 0; q < NA; q++) { base[q] = (size_t)sys[q] * n; s0[q] = 0.0; s1[q] = 0.0; }
-   for (int s = sr.begin; s < sr.end; s += sr.step) {
+   int next = sr.begin;
+   while (true) {
+      int s;
+      if (next < sr.end) { s = next; next += sr.step; }
+      else if (dynCounter) {
+         int g = 0;
+         if (lane == 0) g = atomicAdd(dynCounter, 1);
+         s = __shfl_sync(0xffffffffu, g, 0) + dynStart;
+         if (s >= A.nslices) break;
+      } else break;
       double acc[NA];
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = 0.0;
@@ -962,15 +978,15 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, con
       else { d0[2] += s0[q]; d1[2] += s1[q]; }
    }
 }
-__device__ __forceinline__ void bicg_spmv_phase(const Sell& A, const int* part, int vidx, int n, const double* in, double* out, const bool (&act)[3],
-                                                const double* l1, double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
-   const double* __restrict__ val = sell_vals(A, vidx);
+__device__ __forceinline__ void bicg_spmv_phase(const BicgArgs& a, const double* in, double* out, const bool (&act)[3], const double* l1,
+                                                double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
+   const double* __restrict__ val = sell_vals(a.A, a.vidx);
    int sys[3] = {0, 0, 0}, na = 0;
    for (int c = 0; c < 3; c++)
       if (act[c]) sys[na++] = c;
-   if (na == 1) bicg_spmv_na<1>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 2) bicg_spmv_na<2>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 3) bicg_spmv_na<3>(A, part, val, n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   if (na == 1) bicg_spmv_na<1>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 2) bicg_spmv_na<2>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 3) bicg_spmv_na<3>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
 }
 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
@@ -1001,7 +1017,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    double* shv = a.w + 5 * N3;   // M s
    double* AMs = a.w + 6 * N3;
 
-   double v6[6] = {0, 0, 0, 0, 0, 0};
+   double v6[6] = {0, 0, 0, 0, 0, 0}, v3[3];
    for (int c = 0; c < 3; c++) {
       double acc = 0.0;
       for (int i = tid; i < n; i += nthreads) {
@@ -1022,6 +1038,15 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          S.its[c] = 0; S.act[c] = 1; S.half[c] = 0; S.act2[c] = 0; S.alpha[c] = 0.0; S.omega[c] = 0.0;
       }
    __syncthreads();
+   // phase clock of block 0 (diagnostics build only: info[16..24] = ns in spmv1 / reduce / s-update / reduce / spmv2 / reduce /
+   // x,r-update / reduce / p-update + grid sync, info[25] = lock-step iterations)
+#ifdef CFD_BICG_PHASE_TIMERS
+   unsigned long long tph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1, nit = 0;
+#define BICG_TICK(k) do { if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define BICG_TICK(k)
+#endif
    while (true) {
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++)
@@ -1032,12 +1057,15 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       {
          double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
          const bool act[3] = {S.act[0] != 0, S.act[1] != 0, S.act[2] != 0};
-         bicg_spmv_phase(a.A, a.part, a.vidx, n, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
-         v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = 0; v6[4] = 0; v6[5] = 0;
+         bicg_spmv_phase(a, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
+         v3[0] = d0[0]; v3[1] = d0[1]; v3[2] = d0[2];
       }
-      grid_sum<6>(grid, v6, buf1, sh);
+      BICG_TICK(0);
+      grid_sum<3>(grid, v3, buf1, sh);
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the SpMV phase
+      BICG_TICK(1);
       if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++) S.alpha[c] = S.act[c] ? S.rrs[c] / v6[c] : 0.0;
+         for (int c = 0; c < 3; c++) S.alpha[c] = S.act[c] ? S.rrs[c] / v3[c] : 0.0;
       __syncthreads();
       // ---- s = r - alpha AMp (stored in r), sh = M s, |s|^2
       for (int c = 0; c < 3; c++) {
@@ -1052,12 +1080,14 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
                acc += si * si;
             }
          }
-         v6[c] = acc; v6[3 + c] = 0.0;
+         v3[c] = acc;
       }
-      grid_sum<6>(grid, v6, buf0, sh);
+      BICG_TICK(2);
+      grid_sum<3>(grid, v3, buf0, sh);
+      BICG_TICK(3);
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) {   // converged at the half step: x += alpha M p and stop
-            S.half[c] = (S.act[c] && sqrt(v6[c]) <= S.thresh[c]) ? 1 : 0;
+            S.half[c] = (S.act[c] && sqrt(v3[c]) <= S.thresh[c]) ? 1 : 0;
             S.act2[c] = (S.act[c] && !S.half[c]) ? 1 : 0;
          }
       __syncthreads();
@@ -1065,10 +1095,13 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       {
          double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
          const bool act2[3] = {S.act2[0] != 0, S.act2[1] != 0, S.act2[2] != 0};
-         bicg_spmv_phase(a.A, a.part, a.vidx, n, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
+         bicg_spmv_phase(a, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
          v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = d1[0]; v6[4] = d1[1]; v6[5] = d1[2];
       }
+      BICG_TICK(4);
       grid_sum<6>(grid, v6, buf1, sh);
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+      BICG_TICK(5);
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) S.omega[c] = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
       __syncthreads();
@@ -1093,7 +1126,9 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          }
          v6[c] = a0; v6[3 + c] = a1;
       }
+      BICG_TICK(6);
       grid_sum<6>(grid, v6, buf0, sh);
+      BICG_TICK(7);
       // ---- p = r + beta (p - omega AMp) ; ph = M p
       for (int c = 0; c < 3; c++) {
          if (!S.act2[c]) continue;
@@ -1113,7 +1148,18 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
             else if (S.act2[c]) { S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++; }
          }
       grid.sync();
+      BICG_TICK(8);
+#ifdef CFD_BICG_PHASE_TIMERS
+      nit++;
+#endif
    }
+#undef BICG_TICK
+#ifdef CFD_BICG_PHASE_TIMERS
+   if (tid == 0) {
+      for (int k = 0; k < 9; k++) a.info[16 + k] = (double)tph[k];
+      a.info[25] = (double)nit;
+   }
+#endif
    if (tid == 0)
       for (int c = 0; c < 3; c++) { a.info[3 + c] = (double)S.its[c]; a.info[6 + c] = S.rr[c]; }
 }
@@ -1698,7 +1744,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       TRY(dalloc(c, &c->bw, (size_t)(7 * N3)));
    }
    TRY(dalloc(c, &c->cg_r, (size_t)NNp)); TRY(dalloc(c, &c->cg_p, (size_t)NNp)); TRY(dalloc(c, &c->cg_q, (size_t)NNp));
-   TRY(dalloc(c, &c->kinfo, 16)); TRY(dalloc(c, &c->scal, 16));
+   TRY(dalloc(c, &c->kinfo, 32)); TRY(dalloc(c, &c->scal, 16));
    // initial state (applyBC_initial, BCH.cpp:4062-4110 / GQ.cpp:4559-4607)
    {
       std::vector<double> u0((size_t)N3, 0.0);
@@ -1799,8 +1845,27 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          if (useDyn) TRY(dalloc(c, &c->pcgDynCounter, 4));
       }
       if (P->scheme == CFD_IMPLICIT) {
-         std::vector<int> pk = partition(c->hostOffK, c->bicg_blocks);
+         // large matrices: static share (contiguous chunk per CTA, its gathered window stays in L1) + dynamic tail as for Z;
+         // fewer than 4 slices per warp: everything through the counter (slice order = node order, long corner rows first)
+         const int nsK = (int)c->hostOffK.size() - 1;
+         const int nwarps = c->bicg_blocks * (c->bicg_threads / 32);
+         int dynStart = nsK;
+         const bool useDyn = getenv("CFD_NO_DYN") == nullptr && nsK > nwarps;
+         if (useDyn) {
+            dynStart = 0;
+            if (nsK >= 4 * nwarps) {
+               double frac = 0.88;
+               if (const char* e = getenv("CFD_DYN_STATIC_FRAC")) frac = std::min(1.0, std::max(0.0, atof(e)));
+               const long long target = (long long)(frac * (double)c->hostOffK[nsK]);
+               dynStart = (int)(std::lower_bound(c->hostOffK.begin(), c->hostOffK.end(), target) - c->hostOffK.begin());
+               dynStart = std::min(std::max(dynStart, 0), nsK);
+            }
+         }
+         std::vector<long long> offStatic(c->hostOffK.begin(), c->hostOffK.begin() + dynStart + 1);
+         std::vector<int> pk = partition(offStatic, c->bicg_blocks);
          TRY(dupload(c, &c->bicgPart, pk.data(), pk.size()));
+         c->bicgDynStart = dynStart;
+         if (useDyn) TRY(dalloc(c, &c->bicgDynCounter, 4));
       }
    }
 #undef TRY
@@ -2096,13 +2161,24 @@ int gq_step1GPU(cfd_ctx* c) {
    }
    {
       BicgArgs a;
-      a.A = c->K; a.part = c->bicgPart; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
+      a.A = c->K; a.part = c->bicgPart; a.dynStart = c->bicgDynStart; a.dynCounter = c->bicgDynCounter; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
       a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
       void* args[] = {&a};
       ProfScope ps(c, "bicgstab", 0.0);
       c->lastBicgRec = ps.idx;
       CFD_CK(cudaLaunchCooperativeKernel((void*)k_bicgstab3, dim3(c->bicg_blocks), dim3(c->bicg_threads), args, 0, c->stream));
       c->launches++;
+#ifdef CFD_BICG_PHASE_TIMERS
+      {
+         double h[10];
+         CFD_CK(cudaStreamSynchronize(c->stream));
+         CFD_CK(cudaMemcpy(h, c->kinfo + 16, sizeof h, cudaMemcpyDeviceToHost));
+         if (h[9] > 0)
+            fprintf(stderr, "bicgstab phases (us / lock-step iteration, block 0; %d iterations): spmv1 %.2f red %.2f | s-upd %.2f red %.2f | spmv2 %.2f red %.2f | "
+                            "xr-upd %.2f red %.2f | p-upd+sync %.2f\n", (int)h[9], h[0] / h[9] * 1e-3, h[1] / h[9] * 1e-3, h[2] / h[9] * 1e-3, h[3] / h[9] * 1e-3,
+                    h[4] / h[9] * 1e-3, h[5] / h[9] * 1e-3, h[6] / h[9] * 1e-3, h[7] / h[9] * 1e-3, h[8] / h[9] * 1e-3);
+      }
+#endif
    }
    return CFD_OK;
 }

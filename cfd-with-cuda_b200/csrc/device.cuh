@@ -119,6 +119,8 @@ struct cfd_ctx {
    int pcg_minb = 3;
    int pcgDynStart = 0;             // slices >= this are scheduled dynamically inside k_pcg
    int* pcgDynCounter = nullptr;
+   int bicgDynStart = 0;            // same for the momentum matrix inside k_bicgstab3
+   int* bicgDynCounter = nullptr;
    int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping

@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libcfdb200.so")
+_LIBPATH = os.environ.get("CFD_LIBPATH") or os.path.join(_HERE, "libcfdb200.so")   # CFD_LIBPATH: an instrumented build (diagnostics)
 _lib = None
 
 EXPLICIT, IMPLICIT = 0, 1

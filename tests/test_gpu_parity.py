@@ -282,20 +282,22 @@ def test_two_gpu_partitioned_run(peer_memory, tmp_path):
 
 def test_channel_standin_implicit(mesh):
     """BASELINE configs[2] stand-in (straight channel, uniform inlet, free outlet, pin at the outlet): implicit scheme
-    against the oracle, Krylov tolerances tightened on both sides (see TIGHT above)."""
+    against the oracle.  The anisotropic channel is the hardest case for Jacobi-BiCGStab on the reference's under-integrated
+    Q2 momentum matrix: 1e-12 is not attainable (measured: the solver stagnates for thousands of iterations, the count varies
+    by +-50 % from run to run with the summation order -- in the OpenMP oracle too -- and can end in the rho = 0 breakdown),
+    so the momentum tolerance here is 1e-9, which both sides reach."""
     import fracstep
     import orc
     path = mesh("chan_gpu", kind="channel", nx=12, ny=8, nz=8, full_precision=True)
-    o = orc.Oracle(path, "implicit", **TIGHT)
-    s = fracstep.Solver(path, "implicit", opts=fracstep.options(**TIGHT))
+    opt = dict(cg_tol=1e-12, bicg_tol=1e-9, cg_maxit=5000, bicg_maxit=5000)
+    o = orc.Oracle(path, "implicit", **opt)
+    s = fracstep.Solver(path, "implicit", opts=fracstep.options(**opt))
     o.run(3)
     reps = s.ctx.time_loop(3)
     U, P = s.ctx.fields()
-    # the anisotropic channel is the hardest case for Jacobi-BiCGStab (the oracle itself needs hundreds of iterations and
-    # can stall short of 1e-12): the 1e-6 bar holds whenever both sides converged, otherwise agreement to the level reached
-    converged = all(max(r["bicg_iterations"]) < 5000 for r in reps) and o.arr("bicgIters").max() < 5000
-    bar = 1e-6 if converged else 1e-3
-    assert rel(U, o.U) <= bar and rel_free(U, o.U, o) <= 20 * bar and rel(P, o.P) <= 10 * bar
+    assert np.isfinite(U).all() and np.isfinite(P).all() and np.isfinite(o.U).all()
+    assert all(max(r["bicg_iterations"]) < 5000 for r in reps) and o.arr("bicgIters").max() < 5000
+    assert rel(U, o.U) <= 1e-6 and rel_free(U, o.U, o) <= 2e-5 and rel(P, o.P) <= 1e-5
 
 
 def test_solver_main_drop_in(mesh, tmp_path):
