@@ -124,8 +124,9 @@ def _write(path, title, nx, ny, nz, xs, ys, zs, vel_faces, pin_node, monitor, NE
 
 def cube(path, n, cluster=0.0, NENv=27, viscosity=0.01, dt=0.001, t_final=1.0, max_iter=4, tolerance=0.001,
          converge=0.000001, full_precision=False, title="3D Lid-driven cavity problem", ny=None, nz=None,
-         is_restart=0):
-    """Unit-cube lid-driven cavity: no-slip BC 1 on 5 walls, lid BC 2 u=(1,0,0) on the top (face 6)."""
+         is_restart=0, pin=None, lid=("1.0", "0.0", "0.0")):
+    """Unit-cube lid-driven cavity: no-slip BC 1 on 5 walls, lid BC 2 u=(1,0,0) on the top (face 6).
+    `pin` overrides the pressure-pin node (1-based; negative = none), `lid` the lid velocity strings."""
     nx = n
     ny = ny or n
     nz = nz or n
@@ -139,9 +140,10 @@ def cube(path, n, cluster=0.0, NENv=27, viscosity=0.01, dt=0.001, t_final=1.0, m
     faces += [(el(i, ny, k), 4, 1) for k in range(1, nz + 1) for i in range(1, nx + 1)]      # back
     faces += [(el(i, j, nz), 6, 2) for j in range(1, ny + 1) for i in range(1, nx + 1)]      # top (lid)
     nxc = nx + 1
-    pin = (ny // 2) * nxc + (nxc + 1) // 2
+    if pin is None:
+        pin = (ny // 2) * nxc + (nxc + 1) // 2
     return _write(path, title, nx, ny, nz, xs, ys, zs, faces, pin, ("0.5", "0.5", "0.5"), NENv, dt, t_final,
-                  max_iter, tolerance, converge, viscosity, [("0.0", "0.0", "0.0"), ("1.0", "0.0", "0.0")],
+                  max_iter, tolerance, converge, viscosity, [("0.0", "0.0", "0.0"), tuple(lid)],
                   full_precision, is_restart=is_restart)
 
 

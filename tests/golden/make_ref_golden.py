@@ -48,6 +48,13 @@ CASES = {
     "ref_gq_cav4_tight": ("implicit", "cube", dict(n=4, cluster=0.0, converge=NEVER_STEADY), 3, TIGHT, 1),
     "ref_gq_cav6c_tight": ("implicit", "cube", dict(n=6, cluster=2.0, viscosity=0.001, converge=NEVER_STEADY), 3, TIGHT, 1),
     "ref_gq_chan644_tight": ("implicit", "channel", dict(nx=6, ny=4, nz=4, converge=NEVER_STEADY), 3, TIGHT, 1),
+    # edge cases of the input grammar: a 3x4x5 box with an oblique lid velocity, no pressure pin (negative node, BCH.cpp:701-705);
+    # pin node 1 = 0-based 0, which the `> 0` test never pins (BCH.cpp:4172); one inner iteration per step and another dt
+    "ref_bch_box345_nopin": ("explicit", "cube", dict(n=3, ny=4, nz=5, pin=-1, lid=("0.8", "0.3", "0.0")), 4, {}, 1),
+    "ref_bch_cav4_pin1_it1": ("explicit", "cube", dict(n=4, cluster=2.0, pin=1, max_iter=1, dt=0.002, viscosity=0.02), 4, {}, 1),
+    # (without a pin Z is singular and CG stagnates near 1e-11: pressure tolerance 1e-9 here)
+    "ref_gq_box345_nopin_tight": ("implicit", "cube", dict(n=3, ny=4, nz=5, pin=-1, lid=("0.8", "0.3", "0.0"), converge=NEVER_STEADY), 3,
+                                  dict(TIGHT, REF_SHIM_CG_TOL="1e-9"), 1),
     # BASELINE.json configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (meshgen.cube(30, cluster=2.0) is that
     # file byte for byte, tests/test_oracle.py), only t_final shortened; every 61st node stored
     "ref_bch_ne27000": ("explicit", "cube", dict(n=30, cluster=2.0), 3, {}, 61),
@@ -114,7 +121,8 @@ def main(only=None):
             r = run_reference(scheme, kind, kw, steps, env, d)
             t = r["table"]
             NN = r["NN"]
-            NNp = (kw["n"] + 1) ** 3 if kind == "cube" else (kw["nx"] + 1) * (kw["ny"] + 1) * (kw["nz"] + 1)
+            NNp = ((kw["n"] + 1) * (kw.get("ny", kw["n"]) + 1) * (kw.get("nz", kw["n"]) + 1) if kind == "cube"
+                   else (kw["nx"] + 1) * (kw["ny"] + 1) * (kw["nz"] + 1))
             U = np.concatenate([t[:, 3], t[:, 4], t[:, 5]])
             P = t[:NNp, 6]              # corner nodes come first (BCH.cpp:1352-1368); the rest of the column is interpolated
             done = int(r["monitor"][-1, 0])

