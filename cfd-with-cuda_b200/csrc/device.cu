@@ -1064,8 +1064,16 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       grid_sum<3>(grid, v3, buf1, sh);
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the SpMV phase
       BICG_TICK(1);
+      // Breakdown guards (the reference's libraries have none and hand back NaN fields when BiCGStab stagnates on the rounding
+      // floor, e.g. at an unattainable tolerance on the under-integrated Q2 matrix): a non-finite alpha stops the system with the
+      // iterate it has; a non-finite omega accepts the half step; a non-finite beta stops it after the full step.  All blocks
+      // see bit-identical reduced values, so they decide alike.
       if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++) S.alpha[c] = S.act[c] ? S.rrs[c] / v3[c] : 0.0;
+         for (int c = 0; c < 3; c++) {
+            const double al = S.act[c] ? S.rrs[c] / v3[c] : 0.0;
+            if (!isfinite(al)) { S.act[c] = 0; S.alpha[c] = 0.0; }
+            else S.alpha[c] = al;
+         }
       __syncthreads();
       // ---- s = r - alpha AMp (stored in r), sh = M s, |s|^2
       for (int c = 0; c < 3; c++) {
@@ -1103,7 +1111,11 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
       BICG_TICK(5);
       if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++) S.omega[c] = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
+         for (int c = 0; c < 3; c++) {
+            const double om = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
+            if (S.act2[c] && (!isfinite(om) || om == 0.0)) { S.act2[c] = 0; S.half[c] = 1; S.omega[c] = 0.0; }   // keep x + alpha M p
+            else S.omega[c] = om;
+         }
       __syncthreads();
       // ---- x += alpha M p + omega M s ; r = s - omega AMs ; rs.r , r.r
       for (int c = 0; c < 3; c++) {
@@ -1134,6 +1146,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          if (!S.act2[c]) continue;
          const double omega = S.omega[c];
          const double beta = (v6[c] / S.rrs[c]) * (S.alpha[c] / omega);
+         if (!isfinite(beta)) continue;   // rho = 0: the system is stopped below
          for (int i = tid; i < n; i += nthreads) {
             const size_t k = (size_t)c * n + i;
             const double pi = r[k] + beta * (p[k] - omega * AMp[k]);
@@ -1145,7 +1158,10 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) {
             if (S.half[c]) { S.its[c]++; S.act[c] = 0; }
-            else if (S.act2[c]) { S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++; }
+            else if (S.act2[c]) {
+               if (!isfinite((v6[c] / S.rrs[c]) * (S.alpha[c] / S.omega[c]))) S.act[c] = 0;
+               S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++;
+            }
          }
       grid.sync();
       BICG_TICK(8);

@@ -1102,7 +1102,10 @@ void* orc_create(const char* inpPath, int scheme, int nthreads) {
    Orc* o = new Orc();
    o->scheme = scheme;
 #ifdef _OPENMP
-   if (nthreads > 0) omp_set_num_threads(nthreads);
+   // the thread count is process-wide: nthreads = 0 means "the default again" (OMP_NUM_THREADS or all cores), so that a
+   // single-threaded (deterministic) instance does not slow down the ones created after it
+   static const int kDefaultThreads = omp_get_max_threads();
+   omp_set_num_threads(nthreads > 0 ? nthreads : kDefaultThreads);
 #endif
    if (!readInputFile(*o, inpPath)) return o;
    findNeighbors(*o);

@@ -39,7 +39,11 @@ def settings(meta):
     env = meta["env"]
     if env:   # tight: REF_SHIM_* told the stand-ins what to do
         ct, bt = float(env["REF_SHIM_CG_TOL"]), float(env["REF_SHIM_BICG_TOL"])
-        return dict(cg_tol=ct, bicg_tol=bt, cg_precond=1), dict(cg_tol=ct, bicg_tol=bt)
+        # GPU side: the reproducible (coloured) element scatter, so that -- these meshes being too small for the dynamic slice
+        # scheduling -- the run is bitwise repeatable.  BiCGStab sits on the rounding floor of the under-integrated Q2 matrix
+        # for hundreds of iterations at 1e-12; with atomics the path it takes there changes from run to run and it
+        # occasionally stagnates (1 run in ~5 on the Re = 1000 fixture); 1e-10 instead moves the fields by ~1e-6 (measured).
+        return dict(cg_tol=ct, bicg_tol=bt, cg_precond=1), dict(cg_tol=ct, bicg_tol=bt, ebe_scatter=1)
     if meta["scheme"] == "implicit":   # GQ.cpp:4510-4515: no Jacobi, dpar[0] = 1e-6 on SQUARED norms
         return dict(cg_precond=0, cg_tol=1e-3), dict(cg_no_precond=1, cg_tol=1e-3)
     return {}, {}
@@ -79,7 +83,9 @@ def inp_for(mesh, name, meta):
 def test_oracle_reproduces_reference_run(mesh, name):
     import orc
     g, meta = load(name)
-    o = orc.Oracle(inp_for(mesh, name, meta), meta["scheme"], **settings(meta)[0])
+    # tight fixtures: one thread, so that the summation order -- and with it the path BiCGStab takes along the rounding
+    # floor -- is the same in every run of this test
+    o = orc.Oracle(inp_for(mesh, name, meta), meta["scheme"], 1 if meta["env"] else 0, **settings(meta)[0])
     o.run(meta["steps"])
     eu, ep = errors(o.U, o.P, g, meta, o.i("NN"))
     bu, bp, dcg = bars(name, meta)
@@ -175,7 +181,7 @@ def test_oracle_reproduces_reference_restart(name, tmp_path):
     import orc
     g, meta = load(name)
     inp, dat = restart_dir(tmp_path, g, meta)
-    o = orc.Oracle(inp, meta["scheme"], **settings(meta)[0])
+    o = orc.Oracle(inp, meta["scheme"], 1 if meta["env"] else 0, **settings(meta)[0])
     o.read_restart(dat)
     o.run(meta["steps"])
     eu, ep = errors(o.U, o.P, g, meta, o.i("NN"))
