@@ -69,6 +69,38 @@ def test_reader_rejects_bad_input(tmp_path, mesh):
         fracstep.Solver(str(trunc), "explicit", init_gpu=False)
 
 
+def test_restart_reader_rejects_bad_files(tmp_path, mesh):
+    """readRestartFile's input checked row by row (the rows are parsed in parallel: the FIRST bad row is reported)."""
+    import fracstep
+    s = fracstep.Solver(mesh("h_q2_c6", **MESHES["h_q2_c6"]), "explicit", init_gpu=False)
+    NN, NNp = s.i("NN"), s.i("NNp")
+    rng = np.random.default_rng(1)
+    U, P = rng.standard_normal(3 * NN), rng.standard_normal(NNp)
+    good = str(tmp_path / "good.dat")
+    s.write_tecplot_fields(good, "t", U, P)
+    lines = open(good).read().split("\n")
+    U2, P2 = s.read_restart_fields(good)
+    assert np.allclose(U2, U, rtol=2e-11, atol=0) and np.allclose(P2, P, rtol=2e-11, atol=0)
+    with pytest.raises(fracstep.CfdError, match="cannot open"):
+        s.read_restart_fields(str(tmp_path / "missing.dat"))
+    (tmp_path / "short.dat").write_text("\n".join(lines[:3 + NN // 2]) + "\n")
+    with pytest.raises(fracstep.CfdError, match="malformed row %d" % (NN // 2)):
+        s.read_restart_fields(str(tmp_path / "short.dat"))
+    broken = list(lines)
+    broken[3 + 1234] = "1.0 2.0 three 4.0 5.0 6.0 7.0"
+    broken[3 + 2000] = "1.0 2.0"
+    (tmp_path / "broken.dat").write_text("\n".join(broken))
+    with pytest.raises(fracstep.CfdError, match="malformed row 1234"):
+        s.read_restart_fields(str(tmp_path / "broken.dat"))
+    (tmp_path / "hdr.dat").write_text("TITLE = t\n")
+    with pytest.raises(fracstep.CfdError, match="truncated header"):
+        s.read_restart_fields(str(tmp_path / "hdr.dat"))
+    # no final newline, Windows line ends: still readable (operator>> in the reference skips any white space)
+    (tmp_path / "crlf.dat").write_text("\r\n".join(lines[:3 + NN]))
+    U3, P3 = s.read_restart_fields(str(tmp_path / "crlf.dat"))
+    assert np.array_equal(U3, U2) and np.array_equal(P3, P2)
+
+
 @pytest.mark.parametrize("name", ["h_q2_c6", "h_q1_u7"])
 def test_tecplot_and_restart_formats(mesh, tmp_path, name):
     """createTecplot bytes (BCH.cpp:4249-4482) and readRestartFile (BCH.cpp:4214-4242): product == oracle."""

@@ -189,6 +189,18 @@ def test_oracle_reproduces_reference_restart(name, tmp_path):
     assert all(abs(a - b) <= (5 if meta["env"] else 0) for a, b in zip(o.arr("cgIters"), g["cg"][:, 0]))
 
 
+@pytest.mark.parametrize("name", RESTART)
+def test_product_reads_the_reference_restart_file(name, tmp_path):
+    """The product's (parallel) restart reader on the .dat the reference wrote: u, v, w of every node, p of the corner nodes."""
+    import fracstep
+    g, meta = load(name)
+    inp, dat = restart_dir(tmp_path, g, meta)
+    s = fracstep.Solver(inp, meta["scheme"], init_gpu=False)
+    U, P = s.read_restart_fields(dat)
+    t = g["restart_table"]
+    assert np.array_equal(U, np.concatenate([t[:, 3], t[:, 4], t[:, 5]])) and np.array_equal(P, t[:int(g["NNp"]), 6])
+
+
 # ---------------------------------------------------------------------------------------------------- GPU: the product
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", RESTART)
