@@ -62,8 +62,17 @@ struct CsrPattern {
 };
 
 struct Assembled {
-   CsrPattern Mp, Gp, Zp;
-   std::vector<int> mapM, mapG, mapZ;   // [e][i][j] CSR positions
+   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z have one and the same pattern and element map; they are then built
+   // once and shared (at 256^3 one pattern + map is 6 GB of host memory and seconds of copying)
+   CsrPattern Mp, GpOwn, ZpOwn;
+   std::vector<int> mapM, mapGOwn, mapZOwn;   // [e][i][j] CSR positions
+   bool sharedG = false, sharedZ = false;
+   CsrPattern& Gp() { return sharedG ? Mp : GpOwn; }
+   CsrPattern& Zp() { return sharedZ ? Mp : ZpOwn; }
+   const CsrPattern& Gp() const { return sharedG ? Mp : GpOwn; }
+   const CsrPattern& Zp() const { return sharedZ ? Mp : ZpOwn; }
+   const std::vector<int>& mapG() const { return sharedG ? mapM : mapGOwn; }
+   const std::vector<int>& mapZ() const { return sharedZ ? mapM : mapZOwn; }
    big_dvec Mval, Kval, G1, G2, G3, Zval;
    std::vector<double> MdInv, MdOrigInv;
 };

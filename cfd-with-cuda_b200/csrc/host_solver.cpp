@@ -101,18 +101,18 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
    const std::vector<int>* pidx = m.presIndex.empty() ? nullptr : &m.presIndex;
    build_pattern(m, nv, nv, NN, NN, A.Mp, &A.mapM);
    const bool samePattern = (nv == 8 && !pidx);   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z share one pattern
-   if (samePattern) { A.Gp = A.Mp; A.mapG = A.mapM; }
-   else build_pattern(m, nv, 8, NN, NNp, A.Gp, &A.mapG, nullptr, pidx);
+   A.sharedG = samePattern;
+   if (!samePattern) build_pattern(m, nv, 8, NN, NNp, A.GpOwn, &A.mapGOwn, nullptr, pidx);
    PHASE("patterns M, G");
-   const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp.nnz();
+   const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp().nnz();
    par_zero(A.Mval, nnzM); par_zero(A.Kval, nnzM);
    par_zero(A.G1, nnzG); par_zero(A.G2, nnzG); par_zero(A.G3, nnzG);
    const double invDens = 1.0 / m.density;
    const double mscale = scheme == CFD_IMPLICIT ? 1.0 / m.dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
    if (scheme == CFD_IMPLICIT) {
-      if (samePattern) { A.Zp = A.Mp; A.mapZ = A.mapM; }
-      else build_pattern(m, 8, 8, NNp, NNp, A.Zp, &A.mapZ, pidx, pidx);
-      par_zero(A.Zval, (size_t)A.Zp.nnz());
+      A.sharedZ = samePattern;
+      if (!samePattern) build_pattern(m, 8, 8, NNp, NNp, A.ZpOwn, &A.mapZOwn, pidx, pidx);
+      par_zero(A.Zval, (size_t)A.Zp().nnz());
       PHASE("pattern Z");
    }
    // Elements are dealt to threads in contiguous chunks.  A node touched only by elements of one chunk is
@@ -157,7 +157,7 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                add(A.Mval[mm[i * nv + j]], mscale * me);
                add(A.Kval[mm[i * nv + j]], m.viscosity * ke);
             }
-         const int* mg = &A.mapG[(size_t)e * nv * 8];
+         const int* mg = &A.mapG()[(size_t)e * nv * 8];
          for (int i = 0; i < nv; i++)
             for (int j = 0; j < 8; j++) {
                double g1 = 0, g2 = 0, g3 = 0;
@@ -170,7 +170,7 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                add(A.G3[mg[i * 8 + j]], -invDens * g3);
             }
          if (scheme == CFD_IMPLICIT) {
-            const int* mz = &A.mapZ[(size_t)e * 64];
+            const int* mz = &A.mapZ()[(size_t)e * 64];
             for (int i = 0; i < 8; i++)
                for (int j = 0; j < 8; j++) {
                   double z = 0;
@@ -199,18 +199,18 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
          for (int c = 0; c < 3; c++) A.MdInv[(size_t)c * NN + m.BCvelNodes[2 * i]] = 1.0;
       // Z = sum_c G_c^T diag(MdOrigInv) G_c : row-wise sparse product through the transposed pattern
       std::vector<int> ts((size_t)NNp + 1, 0), trow(nnzG), tpos(nnzG);
-      for (size_t k = 0; k < nnzG; k++) ts[A.Gp.col[k] + 1]++;
+      for (size_t k = 0; k < nnzG; k++) ts[A.Gp().col[k] + 1]++;
       for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
       {
          std::vector<int> fill(ts.begin(), ts.end() - 1);
          for (int r = 0; r < NN; r++)
-            for (int k = A.Gp.rowStarts[r]; k < A.Gp.rowStarts[r + 1]; k++) {
-               const int p = fill[A.Gp.col[k]]++;
+            for (int k = A.Gp().rowStarts[r]; k < A.Gp().rowStarts[r + 1]; k++) {
+               const int p = fill[A.Gp().col[k]]++;
                trow[p] = r; tpos[p] = k;
             }
       }
-      A.Zp.nrows = A.Zp.ncols = NNp;
-      A.Zp.rowStarts.assign((size_t)NNp + 1, 0);
+      A.Zp().nrows = A.Zp().ncols = NNp;
+      A.Zp().rowStarts.assign((size_t)NNp + 1, 0);
       std::vector<std::vector<int> > zc(NNp);
       std::vector<std::vector<double> > zv(NNp);
 #pragma omp parallel
@@ -224,8 +224,8 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
                const int r = trow[t];
                const double d = md[r];
                const double w1 = A.G1[tpos[t]] / d, w2 = A.G2[tpos[t]] / d, w3 = A.G3[tpos[t]] / d;
-               for (int k = A.Gp.rowStarts[r]; k < A.Gp.rowStarts[r + 1]; k++) {
-                  const int j = A.Gp.col[k];
+               for (int k = A.Gp().rowStarts[r]; k < A.Gp().rowStarts[r + 1]; k++) {
+                  const int j = A.Gp().col[k];
                   if (mark[j] != i) { mark[j] = i; acc[j] = 0.0; list.push_back(j); }
                   acc[j] += w1 * A.G1[k] + w2 * A.G2[k] + w3 * A.G3[k];
                }
@@ -236,13 +236,13 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
             for (size_t q = 0; q < list.size(); q++) zv[i][q] = acc[list[q]];
          }
       }
-      for (int i = 0; i < NNp; i++) A.Zp.rowStarts[i + 1] = A.Zp.rowStarts[i] + (int)zc[i].size();
-      A.Zp.col.resize((size_t)A.Zp.rowStarts[NNp]);
-      A.Zval.resize((size_t)A.Zp.rowStarts[NNp]);
+      for (int i = 0; i < NNp; i++) A.Zp().rowStarts[i + 1] = A.Zp().rowStarts[i] + (int)zc[i].size();
+      A.Zp().col.resize((size_t)A.Zp().rowStarts[NNp]);
+      A.Zval.resize((size_t)A.Zp().rowStarts[NNp]);
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < NNp; i++) {
-         std::copy(zc[i].begin(), zc[i].end(), A.Zp.col.begin() + A.Zp.rowStarts[i]);
-         std::copy(zv[i].begin(), zv[i].end(), A.Zval.begin() + A.Zp.rowStarts[i]);
+         std::copy(zc[i].begin(), zc[i].end(), A.Zp().col.begin() + A.Zp().rowStarts[i]);
+         std::copy(zv[i].begin(), zv[i].end(), A.Zval.begin() + A.Zp().rowStarts[i]);
       }
    }
    PHASE("Z");
@@ -250,8 +250,8 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
    // (a partitioned sub-mesh carries the rule already applied: local DOF or -1)
    const int pin = m.presIndex.empty() ? (m.zeroPressureNode > 0 ? m.zeroPressureNode : -1) : m.zeroPressureNode;
    if (pin >= 0)
-      for (int k = A.Zp.rowStarts[pin]; k < A.Zp.rowStarts[pin + 1]; k++)
-         if (A.Zp.col[k] == pin) { A.Zval[k] *= 1000.0; break; }
+      for (int k = A.Zp().rowStarts[pin]; k < A.Zp().rowStarts[pin + 1]; k++)
+         if (A.Zp().col[k] == pin) { A.Zval[k] *= 1000.0; break; }
 }
 
 // createTecplot (BCH.cpp:4249-4482): same bytes (TITLE / VARIABLES / ZONE lines, `scientific`
@@ -474,9 +474,9 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    P.coord = m.coord.data(); P.LtoGnode = m.LtoGnode.data();
    P.sparseM_nnz = (int)s->A.Mp.nnz(); P.sparseMrowStarts = s->A.Mp.rowStarts.data(); P.sparseMcol = s->A.Mp.col.data();
    P.sparseKvalue = s->A.Kval.data(); P.sparseMvalue = s->A.Mval.data();
-   P.sparseG_nnz = (int)s->A.Gp.nnz(); P.sparseGrowStarts = s->A.Gp.rowStarts.data(); P.sparseGcol = s->A.Gp.col.data();
+   P.sparseG_nnz = (int)s->A.Gp().nnz(); P.sparseGrowStarts = s->A.Gp().rowStarts.data(); P.sparseGcol = s->A.Gp().col.data();
    P.sparseG1value = s->A.G1.data(); P.sparseG2value = s->A.G2.data(); P.sparseG3value = s->A.G3.data();
-   P.sparseZ_nnz = (int)s->A.Zp.nnz(); P.sparseZrowStarts = s->A.Zp.rowStarts.data(); P.sparseZcol = s->A.Zp.col.data();
+   P.sparseZ_nnz = (int)s->A.Zp().nnz(); P.sparseZrowStarts = s->A.Zp().rowStarts.data(); P.sparseZcol = s->A.Zp().col.data();
    P.sparseZvalue = s->A.Zval.data();
    P.sparseMapM_1d = s->A.mapM.data();
    P.MdInv = s->A.MdInv.empty() ? nullptr : s->A.MdInv.data();
@@ -597,8 +597,8 @@ long long cfd_solver_int(cfd_solver* s, const char* name) {
    if (n == "NE_apply") return s->partitioned ? s->part.NEa : m.NE; if (n == "nPeers") return (long long)s->part.peers.size();
    if (n == "pinLocal") return s->partitioned ? s->part.pinLocal : (m.zeroPressureNode > 0 ? m.zeroPressureNode : -1);
    if (n == "monLocal") return s->partitioned ? s->part.monLocal : m.monPoint;
-   if (n == "NENv") return m.NENv; if (n == "nnzM") return s->A.Mp.nnz(); if (n == "nnzG") return s->A.Gp.nnz();
-   if (n == "nnzZ") return s->A.Zp.nnz(); if (n == "BCnVelNodes") return m.BCnVelNodes; if (n == "monPoint") return m.monPoint;
+   if (n == "NENv") return m.NENv; if (n == "nnzM") return s->A.Mp.nnz(); if (n == "nnzG") return s->A.Gp().nnz();
+   if (n == "nnzZ") return s->A.Zp().nnz(); if (n == "BCnVelNodes") return m.BCnVelNodes; if (n == "monPoint") return m.monPoint;
    if (n == "zeroPressureNode") return m.zeroPressureNode; if (n == "maxIter") return m.maxIter; if (n == "isRestart") return m.isRestart;
    if (n == "nActiveColors") { if (m.meshColors.empty()) color_mesh(s->mesh); return s->mesh.nActiveColors; }
    return -999999;
@@ -614,8 +614,8 @@ const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, 
    IV("peerRank", s->peerRank) IV("sendVptr", s->sendVptr) IV("sendVidx", s->sendVidx) IV("recvVoff", s->recvVoff) IV("recvVcnt", s->recvVcnt)
    IV("remoteVoff", s->remoteVoff) IV("remotePoff", s->remotePoff) IV("sendPptr", s->sendPptr) IV("sendPidx", s->sendPidx) IV("recvPoff", s->recvPoff) IV("recvPcnt", s->recvPcnt)
    DV("coord", m.coord) IV("LtoGnode", m.LtoGnode) IV("BCvelNodes", m.BCvelNodes) DV("BCstr", m.BCstr)
-   IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp.rowStarts) IV("sparseGcol", A.Gp.col)
-   IV("sparseZrowStarts", A.Zp.rowStarts) IV("sparseZcol", A.Zp.col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG)
+   IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp().rowStarts) IV("sparseGcol", A.Gp().col)
+   IV("sparseZrowStarts", A.Zp().rowStarts) IV("sparseZcol", A.Zp().col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG())
    DV("sparseMvalue", A.Mval) DV("sparseKvalue", A.Kval) DV("sparseG1value", A.G1) DV("sparseG2value", A.G2) DV("sparseG3value", A.G3)
    DV("sparseZvalue", A.Zval) DV("MdInv", A.MdInv) DV("MdOrigInv", A.MdOrigInv)
    if (n == "meshColors" || n == "NmeshColors" || n == "elementsOfColor") {
@@ -684,7 +684,7 @@ int cfd_solver_main(const char* workdir, int scheme, int max_steps) {
    if (rc) return rc;
    const Mesh& m = s->mesh;
    printf("readInputFile() .. step0() took  %8.3f seconds.\n", now_s() - t0);
-   printf("\n NN = %d\n NNp = %d\n sparseM_NNZ = %lld\n sparseG_NNZ = %lld\n", m.NN, m.NNp, 3 * s->A.Mp.nnz(), 3 * s->A.Gp.nnz());
+   printf("\n NN = %d\n NNp = %d\n sparseM_NNZ = %lld\n sparseG_NNZ = %lld\n", m.NN, m.NNp, 3 * s->A.Mp.nnz(), 3 * s->A.Gp().nnz());
    printf("\n\nMonitoring node is %d, with coordinates [%f, %f, %f]\n\n\n", m.monPoint, m.coord[3 * (size_t)m.monPoint],
           m.coord[3 * (size_t)m.monPoint + 1], m.coord[3 * (size_t)m.monPoint + 2]);
    const std::string dat = dir + name + ".dat";
