@@ -55,6 +55,8 @@ CASES = {
     # (without a pin Z is singular and CG stagnates near 1e-11: pressure tolerance 1e-9 here)
     "ref_gq_box345_nopin_tight": ("implicit", "cube", dict(n=3, ny=4, nz=5, pin=-1, lid=("0.8", "0.3", "0.0"), converge=NEVER_STEADY), 3,
                                   dict(TIGHT, REF_SHIM_CG_TOL="1e-9"), 1),
+    # a longer run: 20 time steps (73 pressure solves) on an 8^3 clustered mesh, every 7th node stored
+    "ref_bch_cav8c_20steps": ("explicit", "cube", dict(n=8, cluster=2.0), 20, {}, 7),
     # BASELINE.json configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (meshgen.cube(30, cluster=2.0) is that
     # file byte for byte, tests/test_oracle.py), only t_final shortened; every 61st node stored
     "ref_bch_ne27000": ("explicit", "cube", dict(n=30, cluster=2.0), 3, {}, 61),
