@@ -1992,6 +1992,12 @@ int cfd_download(cfd_ctx* c, const char* name, double* host, long long count) {
    CFD_CK(cudaMemcpy(host, *it->second.first, sizeof(double) * count, cudaMemcpyDeviceToHost));
    return CFD_OK;
 }
+void* cfd_device_pointer(cfd_ctx* c, const char* name) {
+   if (!c || !name) return nullptr;
+   auto it = c->vecs.find(name);
+   return it == c->vecs.end() ? nullptr : (void*)*it->second.first;
+}
+
 int cfd_upload(cfd_ctx* c, const char* name, const double* host, long long count) {
    if (!c) return CFD_ERR_ARG;
    auto it = c->vecs.find(name);

@@ -144,6 +144,14 @@ int cfd_p2p_attach(cfd_ctx* ctx, const char* all_desc /* [world][96] */);
  * "Uk","Uk_prev","Pk","Pk_prev","Pk_prevprev","Pdiff","R1","R2","sparseAvalue" (implicit). */
 int cfd_download(cfd_ctx* ctx, const char* name, double* host, long long count);
 int cfd_upload(cfd_ctx* ctx, const char* name, const double* host, long long count);
+/* Raw device address of a named vector (names as above; NULL if unknown).  For host programs that -- like the reference's
+ * own timeLoop under USECUDA (BCH.cpp:2866-2869, 2929-2932, 3070-3071, 3099-3100; GQ.cpp:3366-3368) -- move data between
+ * iterates with their own cudaMemcpy calls on the `*_d` globals: integration/cfdb200_shim_*.cpp points those globals here.
+ * Buffers are never re-allocated.  The seam functions the reference calls leave the addresses alone; gq_endTimeStep and
+ * cfd_timeLoop (implicit) rotate Uk/Uk_prev and Pk/Pk_prev/Pk_prevprev by swapping buffers -- a caller that uses those
+ * must fetch the pointers again afterwards.  Launch on the same stream (cfd_options.cuda_stream) or synchronise the device
+ * between such copies and the seam calls, as the reference does (cudaThreadSynchronize). */
+void* cfd_device_pointer(cfd_ctx* ctx, const char* name);
 /* current velocity [3NN] and pressure [NNp] (Un/Pn or Uk_prev/Pk_prev after a completed step) */
 int cfd_get_fields(cfd_ctx* ctx, double* U, double* P);
 

@@ -1,0 +1,74 @@
+"""The reference's own HOST programs driving libcfdb200.so through the seam.
+
+`make -C oracle refhost` compiles blascoCodinaHuerta.cpp / guermondQuartapelle.cpp unmodified with -DUSECUDA and links them
+with integration/cfdb200_shim_bch.cpp / cfdb200_shim_gq.cpp in place of their CUDAcodes.cu (the binding INTEGRATION.md
+describes, as real code).  Everything outside the eleven / six seam functions is then the reference: main(), reader,
+preprocessing, step0(), timeLoop() with its own cudaMemcpy rotations on the `*_d` globals, createTecplot().
+
+CPU part: the programs exist (where the reference tree was mounted at build time) and stop with an error code without a GPU.
+GPU part: they must write the .dat the reference's CPU build wrote for the same input deck (tests/golden/ref_*.npz).
+The file sorts last on purpose: the GPU part was written after round 1's GPU budget was spent and has not run on
+hardware yet, so it is marked xfail(strict=False) -- an XPASS in the log is the first evidence, a failure does not mask
+the validated suites."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_reference_pin import ROOT, errors, load
+
+EXE = {"explicit": os.path.join(ROOT, "oracle", "_ref", "bch_gpu_cfdb200"), "implicit": os.path.join(ROOT, "oracle", "_ref", "gq_gpu_cfdb200")}
+
+
+def deck(tmp_path, meta):
+    import meshgen
+    kw = dict(meta["kw"])
+    getattr(meshgen, meta["kind"])(str(tmp_path / "case.inp"), t_final=(meta["steps"] - 0.5) * kw.get("dt", 0.001), **kw)
+    (tmp_path / "ProblemName.txt").write_text("case\n")
+
+
+@pytest.mark.parametrize("scheme", ["explicit", "implicit"])
+def test_reference_host_program_links_against_the_library(scheme, tmp_path):
+    if not os.path.exists(EXE[scheme]):
+        pytest.skip("oracle/_ref/*_gpu_cfdb200 not built (needs the reference tree: make -C oracle refhost)")
+    out = subprocess.run(["ldd", EXE[scheme]], capture_output=True, text=True).stdout
+    assert "libcfdb200.so" in out and "not found" not in out
+    assert "cusparse" not in out and "cublas" not in out        # CUDAcodes.cu's libraries are gone from the link line
+    import torch
+    if torch.cuda.is_available():
+        return
+    _, meta = load("ref_bch_cav4" if scheme == "explicit" else "ref_gq_cav4")
+    deck(tmp_path, meta)
+    r = subprocess.run([EXE[scheme]], cwd=str(tmp_path), capture_output=True, text=True, stdin=subprocess.DEVNULL, timeout=120)
+    assert r.returncode == 1 and "cfdb200: error -2" in r.stderr   # selectCUDAdevice(): no device, no CPU fallback, no `cin >>`
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: first hardware run is this one")
+@pytest.mark.parametrize("name,env", [("ref_bch_cav4", {"CFDB200_CPU_SEMANTICS": "1"}), ("ref_bch_cav6c", {"CFDB200_CPU_SEMANTICS": "1"}),
+                                      ("ref_gq_cav4", {})])
+def test_reference_host_program_on_the_gpu_library(name, env, tmp_path):
+    g, meta = load(name)
+    exe = EXE[meta["scheme"]]
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/*_gpu_cfdb200 not built")
+    deck(tmp_path, meta)
+    r = subprocess.run([exe], cwd=str(tmp_path), env=dict(os.environ, **env), capture_output=True, text=True, stdin=subprocess.DEVNULL,
+                       timeout=300)
+    assert r.returncode == 0, (r.stderr[-1500:], r.stdout[-1500:])
+    NN = int(g["NN"])
+    t = np.loadtxt(str(tmp_path / "case.dat"), skiprows=3, max_rows=NN)
+    assert np.array_equal(t[:, :3], g["coord"])
+    eu, ep = errors(np.concatenate([t[:, 3], t[:, 4], t[:, 5]]), t[:int(g["NNp"]), 6], g, meta, NN)
+    # explicit: the CPU build's settings were selected, so the bar is the parity bar; implicit: the GPU build's Jacobi-CG at
+    # 1e-6 against the CPU build's plain CG at 1e-3 on the under-integrated Q2 matrix -> loose
+    bar = 1e-6 if meta["scheme"] == "explicit" else 5e-3
+    assert eu <= bar and ep <= bar, (eu, ep)
+    ncol = 9 if meta["scheme"] == "explicit" else 8
+    rows = [ln.split() for ln in r.stdout.split("\n")]
+    rows = [x for x in rows if len(x) == ncol and x[0].isdigit()]
+    assert len(rows) == meta["steps"]
+    if meta["scheme"] == "explicit":
+        assert [int(x[1]) for x in rows] == [int(v) for v in g["monitor"][:, 1]]   # inner iterations per step
