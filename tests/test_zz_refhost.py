@@ -56,7 +56,7 @@ def test_reference_host_program_on_the_gpu_library(name, env, tmp_path):
         pytest.skip("oracle/_ref/*_gpu_cfdb200 not built")
     deck(tmp_path, meta)
     r = subprocess.run([exe], cwd=str(tmp_path), env=dict(os.environ, **env), capture_output=True, text=True, stdin=subprocess.DEVNULL,
-                       timeout=300)
+                       timeout=60)
     assert r.returncode == 0, (r.stderr[-1500:], r.stdout[-1500:])
     NN = int(g["NN"])
     t = np.loadtxt(str(tmp_path / "case.dat"), skiprows=3, max_rows=NN)
