@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "cfdb200.h"
+#include "cfdb200_explicit_z.hpp"
 
 // ---- the reference's globals (defined in blascoCodinaHuerta.cpp) ------------------------------------------------------
 extern int NE, NN, NNp, NENv, NENp, NGP, sparseM_NNZ, sparseG_NNZ, BCnVelNodes, nBC, zeroPressureNode, monPoint, maxIter, timeN;
@@ -49,60 +50,10 @@ double* dev(const char* name) {
 void selectCUDAdevice() { die(cfd_selectCUDAdevice(0)); }   // BCH.cu:126-154 picks the LAST device of the box; here: device 0
 
 // Called by step0() in place of the CPU/CSparse calculateZ() (BCH.cpp:3301-3306).  CUDAcodes.cu forms Z with CUSP on the
-// host and converts it for the device (BCH.cu:281-411); any CSR product does: row i of Z gathers, over the velocity rows r
-// that hold pressure column i, G_c(r,i) * MdOrigInv_c(r) * G_c(r,:).
+// host and converts it for the device (BCH.cu:281-411); cfdb200_explicit_z.hpp is a plain CSR product doing the same.
 void calculateZ_CUSP() {
-   const int nnzG = sparseG_NNZ / 3;
-   // transpose pattern of G: for every pressure node the (velocity row, position) pairs that reference it
-   std::vector<int> ts(NNp + 1, 0), trow(nnzG), tpos(nnzG);
-   for (int k = 0; k < nnzG; k++) ts[sparseGcol[k] + 1]++;
-   for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
-   {
-      std::vector<int> fill(ts.begin(), ts.end() - 1);
-      for (int r = 0; r < NN; r++)
-         for (int k = sparseGrowStarts[r]; k < sparseGrowStarts[r + 1]; k++) {
-            const int q = fill[sparseGcol[k]]++;
-            trow[q] = r; tpos[q] = k;
-         }
-   }
-   const double* G[3] = {sparseG1value, sparseG2value, sparseG3value};
-   zrs.assign(NNp + 1, 0);
-   std::vector<std::vector<int> > cols(NNp);
-   std::vector<std::vector<double> > vals(NNp);
-#pragma omp parallel
-   {
-      std::vector<double> acc(NNp, 0.0);
-      std::vector<int> mark(NNp, -1), list;
-#pragma omp for schedule(dynamic, 64)
-      for (int i = 0; i < NNp; i++) {
-         list.clear();
-         for (int q = ts[i]; q < ts[i + 1]; q++) {
-            const int r = trow[q];
-            for (int c = 0; c < 3; c++) {
-               const double w = G[c][tpos[q]] * MdOrigInv[c * NN + r];
-               for (int k = sparseGrowStarts[r]; k < sparseGrowStarts[r + 1]; k++) {
-                  const int j = sparseGcol[k];
-                  if (mark[j] != i) { mark[j] = i; acc[j] = 0.0; list.push_back(j); }
-                  acc[j] += w * G[c][k];
-               }
-            }
-         }
-         std::sort(list.begin(), list.end());
-         cols[i] = list;
-         vals[i].resize(list.size());
-         for (size_t t = 0; t < list.size(); t++) vals[i][t] = acc[list[t]];
-      }
-   }
-   for (int i = 0; i < NNp; i++) zrs[i + 1] = zrs[i] + (int)cols[i].size();
-   zcol.resize(zrs[NNp]); zval.resize(zrs[NNp]);
-   for (int i = 0; i < NNp; i++) {
-      std::copy(cols[i].begin(), cols[i].end(), zcol.begin() + zrs[i]);
-      std::copy(vals[i].begin(), vals[i].end(), zval.begin() + zrs[i]);
-   }
-   // applyBC_Step2(1): the pinned node's diagonal times 1000, only for a node id > 0 (BCH.cu:357, BCH.cpp:4172)
-   if (zeroPressureNode > 0)
-      for (int k = zrs[zeroPressureNode]; k < zrs[zeroPressureNode + 1]; k++)
-         if (zcol[k] == zeroPressureNode) zval[k] *= 1000.0;
+   cfdb200_form_explicit_Z(NN, NNp, sparseGrowStarts, sparseGcol, sparseG1value, sparseG2value, sparseG3value, MdOrigInv, zeroPressureNode,
+                           zrs, zcol, zval);
 }
 
 void initializeAndAllocateGPU() {   // BCH.cu:161-273

@@ -29,3 +29,17 @@ extern "C" int shim_paralution_bicgstab(int n, int nnz, int* rowStarts, int* col
    ls.Clear();
    return (rs == rowStarts && c == col && v == val && b == rhs && sol == x) ? 0 : -2;   // ... and LeaveDataPtr hands them back
 }
+
+// ---- the explicit-Z product of integration/cfdb200_explicit_z.hpp, for tests/test_shim.py ---------------------------------
+#include "../../integration/cfdb200_explicit_z.hpp"
+extern "C" int shim_form_explicit_Z(int NN, int NNp, const int* growStarts, const int* gcol, const double* G1, const double* G2, const double* G3,
+                                    const double* MdOrigInv, int pin, int* zrs, int* zcol, double* zval, int cap) {
+   std::vector<int> rs, col;
+   std::vector<double> val;
+   cfdb200_form_explicit_Z(NN, NNp, growStarts, gcol, G1, G2, G3, MdOrigInv, pin, rs, col, val);
+   if ((int)col.size() > cap) return -(int)col.size();
+   std::copy(rs.begin(), rs.end(), zrs);
+   std::copy(col.begin(), col.end(), zcol);
+   std::copy(val.begin(), val.end(), zval);
+   return (int)col.size();
+}

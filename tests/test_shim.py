@@ -205,3 +205,24 @@ def test_paralution_bicgstab_standin(L, tmp_path, monkeypatch):
     monkeypatch.setenv("REF_SHIM_BICG_TOL", "1e-300")
     assert L.shim_paralution_bicgstab(n, len(val), ip(rs), ip(col), dp(val), dp(b), dp(x), 0.0, 1e-6, 1e8, 5) == 0
     assert log.read_text().strip().split("\n")[-1] == "bicgstab 5 0"
+
+
+@pytest.mark.parametrize("mk", [dict(n=4, cluster=2.0), dict(n=3, ny=4, nz=5, pin=1)])
+def test_integration_shim_explicit_Z(L, mesh, mk):
+    """integration/cfdb200_explicit_z.hpp (what calculateZ_CUSP() of the replacement shim runs) against the product's own step0
+    on the same G, MdOrigInv: same pattern, same values, same pin rule (node id > 0)."""
+    import fracstep
+    s = fracstep.Solver(mesh("shimz_%d_%s" % (mk["n"], mk.get("pin", "d")), **mk), "explicit", init_gpu=False)
+    NN, NNp = s.i("NN"), s.i("NNp")
+    grs, gcol = s.arr("sparseGrowStarts"), s.arr("sparseGcol")
+    G = [np.ascontiguousarray(s.arr("sparseG%dvalue" % c)) for c in (1, 2, 3)]
+    mdo = np.ascontiguousarray(s.arr("MdOrigInv"))
+    zrs_p, zcol_p, zval_p = s.arr("sparseZrowStarts"), s.arr("sparseZcol"), s.arr("sparseZvalue")
+    cap = len(zcol_p) + 16
+    zrs, zcol, zval = np.zeros(NNp + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    L.shim_form_explicit_Z.argtypes = [C.c_int, C.c_int, I, I, D, D, D, D, C.c_int, I, I, D, C.c_int]
+    n = L.shim_form_explicit_Z(NN, NNp, ip(np.ascontiguousarray(grs, np.int32)), ip(np.ascontiguousarray(gcol, np.int32)), dp(G[0]), dp(G[1]),
+                               dp(G[2]), dp(mdo), s.i("zeroPressureNode"), ip(zrs), ip(zcol), dp(zval), cap)
+    assert n == len(zcol_p)
+    assert np.array_equal(zrs, zrs_p) and np.array_equal(zcol[:n], zcol_p)
+    assert np.allclose(zval[:n], zval_p, rtol=1e-12, atol=1e-14 * np.abs(zval_p).max())
