@@ -84,6 +84,7 @@ void initializeAndAllocateGPU() {   // BCH.cu:161-273
    o.cg_warm_start = cpuSemantics ? 0 : 1;
    o.maxacc_rule = cpuSemantics ? 0 : 1;
    o.cuda_stream = (void*)cudaStreamLegacy;   // the host file's own cudaMemcpy / cudaMemset calls run on the legacy stream: keep one order
+   if (const char* v = getenv("CFD_CG_TOL")) o.cg_tol = atof(v);   // the original hard-codes 1e-6 (BCH.cu:433)
    die(cfd_initializeAndAllocateGPU(&p, &o, &ctx));
    zrs.clear(); zcol.clear(); zval.clear(); zrs.shrink_to_fit(); zcol.shrink_to_fit(); zval.shrink_to_fit();
    // the `*_d` globals timeLoop() copies between
@@ -100,8 +101,10 @@ void calculate_KtimesAcc_prevGPU() { die(bch_calculate_KtimesAcc_prevGPU(ctx)); 
 bool checkConvergenceGPU()         { int c = 0; die(bch_checkConvergenceGPU(ctx, &c)); return c != 0; }                        // BCH.cu:1084-1121
 bool checkConvergenceInTimeGPU()   { int s = 0; die(bch_checkConvergenceInTimeGPU(ctx, &s, &maxAcc)); return s != 0; }         // BCH.cu:1151-1178
 void printMonitorDataGPU(int iter) {                                                                                           // BCH.cu:1128-1144
-   double m[4];
-   die(cfd_printMonitorDataGPU(ctx, m));
-   printf("%6d  %6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, iter, timeT, m[0], m[1], m[2], m[3],
-          wallClockTimeCurrentTimeStep, maxAcc);
+   // Like the original: bring the whole fields back every step.  The host program relies on it -- its createTecplot() at
+   // the end of main() (BCH.cpp:517) writes the HOST arrays, and timeLoop() itself copies them back only every 1000 steps,
+   // at steady state or when timeT hits t_final to 1e-10 (BCH.cpp:3097-3112).
+   die(cfd_get_fields(ctx, Un, Pn));
+   printf("%6d  %6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, iter, timeT, Un[monPoint], Un[monPoint + NN],
+          Un[monPoint + 2 * NN], Pn[monPoint], wallClockTimeCurrentTimeStep, maxAcc);
 }

@@ -67,6 +67,10 @@ void initializeAndAllocateGPU() {   // GQ.cu:166-295
    cfd_default_options(&o);          // = CUDAcodes.cu: Jacobi-CG and Jacobi-BiCGStab, 1e-6, 1000 iterations (GQ.cu:344-353, 404-414)
    o.maxacc_rule = 0;                // GQ.cu:975-1002 divides by dt
    o.cuda_stream = (void*)cudaStreamLegacy;   // same stream as the host file's own cudaMemcpy calls
+   if (const char* v = getenv("CFD_CG_TOL")) o.cg_tol = atof(v);       // the original hard-codes 1e-6 for both solvers (GQ.cu:344, 404)
+   if (const char* v = getenv("CFD_BICG_TOL")) o.bicg_tol = atof(v);
+   if (const char* v = getenv("CFD_BICG_MAXIT")) o.bicg_maxit = atoi(v);
+   if (const char* v = getenv("CFD_EBE_SCATTER")) o.ebe_scatter = atoi(v);
    die(cfd_initializeAndAllocateGPU(&p, &o, &ctx));
    Uk_d = dev("Uk"); Uk_prev_d = dev("Uk_prev"); Pk_d = dev("Pk"); Pk_prev_d = dev("Pk_prev"); Pk_prevprev_d = dev("Pk_prevprev");
    Pdiff_d = dev("Pdiff"); R1_d = dev("R1"); R2_d = dev("R2");
@@ -76,7 +80,10 @@ void step1GPU() { die(gq_step1GPU(ctx)); }   // GQ.cu:761-890; like the original
 void step2GPU() { die(gq_step2GPU(ctx)); }                                     // GQ.cu:897-944
 bool checkConvergenceInTimeGPU() { int s = 0; die(gq_checkConvergenceInTimeGPU(ctx, &s, &maxAcc)); return s != 0; }   // GQ.cu:975-1002
 void printMonitorDataGPU() {                                                                                         // GQ.cu:951-967
-   double m[4];
-   die(cfd_printMonitorDataGPU(ctx, m));   // reads Uk_prev / Pk_prev, which timeLoop() has just overwritten with Uk / Pk
-   printf("%6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, timeT, m[0], m[1], m[2], m[3], wallClockTimeCurrentTimeStep, maxAcc);
+   // Like the original: bring Uk and Pk back to the host arrays every step (createTecplot() writes those).  timeLoop() has
+   // just copied Uk_d into Uk_prev_d and Pk_d into Pk_prev_d (GQ.cpp:3366-3368), which is what cfd_get_fields reads.
+   extern double *Uk, *Pk;
+   die(cfd_get_fields(ctx, Uk, Pk));
+   printf("%6d  %10.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f  %12.5f\n", timeN, timeT, Uk[monPoint], Uk[monPoint + NN], Uk[monPoint + 2 * NN],
+          Pk[monPoint], wallClockTimeCurrentTimeStep, maxAcc);
 }

@@ -7,9 +7,13 @@ preprocessing, step0(), timeLoop() with its own cudaMemcpy rotations on the `*_d
 
 CPU part: the programs exist (where the reference tree was mounted at build time) and stop with an error code without a GPU.
 GPU part: they must write the .dat the reference's CPU build wrote for the same input deck (tests/golden/ref_*.npz).
-The file sorts last on purpose: the GPU part was written after round 1's GPU budget was spent and has not run on
-hardware yet, so it is marked xfail(strict=False) -- an XPASS in the log is the first evidence, a failure does not mask
-the validated suites."""
+The file sorts last on purpose.  The programs were built after round 1's GPU budget was all but spent; the last 20 seconds
+went into ONE run of each (profiles/r01_refhost_*.log): both ran to "The program is terminated successfully", the
+explicit monitor table (inner iterations per step, maxAcc) equals the reference CPU build's line by line, the implicit one
+agrees with the oracle at the GPU build's settings to the level two BiCGStab implementations agree on this matrix.  The
+.dat files of that run held the INITIAL fields: like the original, printMonitorDataGPU has to bring the whole fields back
+every step, which the shims now do -- that version has not run on hardware yet, hence xfail(strict=False): an XPASS in
+the log is the evidence, a failure does not mask the validated suites."""
 import os
 import shutil
 import subprocess
@@ -46,9 +50,9 @@ def test_reference_host_program_links_against_the_library(scheme, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: first hardware run is this one")
+@pytest.mark.xfail(strict=False, reason="shim revision after round 1's GPU minutes were spent: first hardware run is this one")
 @pytest.mark.parametrize("name,env", [("ref_bch_cav4", {"CFDB200_CPU_SEMANTICS": "1"}), ("ref_bch_cav6c", {"CFDB200_CPU_SEMANTICS": "1"}),
-                                      ("ref_gq_cav4", {})])
+                                      ("ref_gq_cav4_tight", {"CFD_CG_TOL": "1e-12", "CFD_BICG_TOL": "1e-12", "CFD_EBE_SCATTER": "1"})])
 def test_reference_host_program_on_the_gpu_library(name, env, tmp_path):
     g, meta = load(name)
     exe = EXE[meta["scheme"]]
@@ -62,10 +66,8 @@ def test_reference_host_program_on_the_gpu_library(name, env, tmp_path):
     t = np.loadtxt(str(tmp_path / "case.dat"), skiprows=3, max_rows=NN)
     assert np.array_equal(t[:, :3], g["coord"])
     eu, ep = errors(np.concatenate([t[:, 3], t[:, 4], t[:, 5]]), t[:int(g["NNp"]), 6], g, meta, NN)
-    # explicit: the CPU build's settings were selected, so the bar is the parity bar; implicit: the GPU build's Jacobi-CG at
-    # 1e-6 against the CPU build's plain CG at 1e-3 on the under-integrated Q2 matrix -> loose
-    bar = 1e-6 if meta["scheme"] == "explicit" else 5e-3
-    assert eu <= bar and ep <= bar, (eu, ep)
+    # explicit: the CPU build's settings selected; implicit: both sides iterated to 1e-12 -> the parity bar in both cases
+    assert eu <= 1e-6 and ep <= 1e-6, (eu, ep)
     ncol = 9 if meta["scheme"] == "explicit" else 8
     rows = [ln.split() for ln in r.stdout.split("\n")]
     rows = [x for x in rows if len(x) == ncol and x[0].isdigit()]
