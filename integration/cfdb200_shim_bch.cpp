@@ -87,10 +87,12 @@ void initializeAndAllocateGPU() {   // BCH.cu:161-273
    if (const char* v = getenv("CFD_CG_TOL")) o.cg_tol = atof(v);   // the original hard-codes 1e-6 (BCH.cu:433)
    die(cfd_initializeAndAllocateGPU(&p, &o, &ctx));
    zrs.clear(); zcol.clear(); zval.clear(); zrs.shrink_to_fit(); zcol.shrink_to_fit(); zval.shrink_to_fit();
-   // the `*_d` globals timeLoop() copies between
+   // the `*_d` globals timeLoop() copies between (BCH.cpp:2866-2869, 2929-2932, 3070-3071) and reads back (:3099-3100) ...
    Un_d = dev("Un"); Unp1_d = dev("Unp1"); Unp1_prev_d = dev("Unp1_prev"); UnpHalf_d = dev("UnpHalf"); UnpHalf_prev_d = dev("UnpHalf_prev");
-   Pn_d = dev("Pn"); Pnp1_d = dev("Pnp1"); Pnp1_prev_d = dev("Pnp1_prev"); Pdot_d = dev("Pdot");
-   R1_d = dev("R1"); R2_d = dev("R2"); R3_d = dev("R3"); Acc_d = dev("Acc"); Acc_prev_d = dev("Acc_prev"); KtimesAcc_prev_d = dev("KtimesAcc_prev");
+   Pn_d = dev("Pn"); Pnp1_d = dev("Pnp1"); Pnp1_prev_d = dev("Pnp1_prev"); Acc_d = dev("Acc"); Acc_prev_d = dev("Acc_prev");
+   // ... and, for completeness, the ones only CUDAcodes.cu itself used
+   Pdot_d = (double*)cfd_device_pointer(ctx, "Pdot"); R1_d = (double*)cfd_device_pointer(ctx, "R1"); R2_d = (double*)cfd_device_pointer(ctx, "R2");
+   R3_d = (double*)cfd_device_pointer(ctx, "R3"); KtimesAcc_prev_d = (double*)cfd_device_pointer(ctx, "KtimesAcc_prev");
 }
 
 void calculateMatrixAGPU()         { die(bch_calculateMatrixAGPU(ctx)); }            // BCH.cu:906-939

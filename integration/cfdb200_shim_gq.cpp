@@ -72,8 +72,10 @@ void initializeAndAllocateGPU() {   // GQ.cu:166-295
    if (const char* v = getenv("CFD_BICG_MAXIT")) o.bicg_maxit = atoi(v);
    if (const char* v = getenv("CFD_EBE_SCATTER")) o.ebe_scatter = atoi(v);
    die(cfd_initializeAndAllocateGPU(&p, &o, &ctx));
+   // the five buffers timeLoop() copies between (GQ.cpp:3366-3368) and reads back (GQ.cpp:3397-3398, 3407-3408) ...
    Uk_d = dev("Uk"); Uk_prev_d = dev("Uk_prev"); Pk_d = dev("Pk"); Pk_prev_d = dev("Pk_prev"); Pk_prevprev_d = dev("Pk_prevprev");
-   Pdiff_d = dev("Pdiff"); R1_d = dev("R1"); R2_d = dev("R2");
+   // ... and, for completeness, the ones only CUDAcodes.cu itself used
+   Pdiff_d = (double*)cfd_device_pointer(ctx, "Pdiff"); R1_d = (double*)cfd_device_pointer(ctx, "R1"); R2_d = (double*)cfd_device_pointer(ctx, "R2");
 }
 
 void step1GPU() { die(gq_step1GPU(ctx)); }   // GQ.cu:761-890; like the original it calls calculateMatrixAGPU (:726-754) itself

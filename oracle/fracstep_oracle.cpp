@@ -1211,6 +1211,8 @@ int orc_phase(void* h, const char* name, int iter) {
    else if (n == "bch_step1") bch_step1(o);
    else if (n == "bch_step2") bch_step2(o, iter);
    else if (n == "bch_step3") bch_step3(o, iter);
+   else if (n == "bch_KtimesAcc")   // BCH.cpp:2985-3033
+      for (int c = 0; c < 3; c++) spmv(o.Mp, o.Kval.data(), &o.Acc_prev[c * o.NN], &o.KtimesAcc_prev[c * o.NN], 1.0, 0.0);
    else if (n == "gq_step1") gq_step1(o);
    else if (n == "gq_step2") gq_step2(o);
    else return -1;
