@@ -89,6 +89,25 @@ def test_reference_host_program_on_the_cpu_mock(name, env, tmp_path):
         assert np.allclose([float(x[8]) for x in rows], g["monitor"][:, 8], rtol=1e-4, atol=2e-5)     # maxAcc column
 
 
+def test_reference_step0_arrays_on_the_shipped_mesh(tmp_path):
+    """BASELINE.json configs[0] at the array level: on lidDrivenCavity_NE27000.inp (regenerated byte for byte) the reference's
+    own preprocessing and step0 -- 226 981 generated node coordinates, connectivity, the 14.0 M-entry K, G1-3, the lumped
+    masses -- are bitwise what the oracle computes; Z (3.3 M entries, the shim's product) to rounding."""
+    if not os.path.exists(MOCK["explicit"]):
+        pytest.skip("oracle/_ref/mock not built (needs the reference tree: make -C oracle refhost-mock)")
+    import meshgen
+    meshgen.cube(str(tmp_path / "case.inp"), 30, cluster=2.0, t_final=0.0005)       # one time step
+    (tmp_path / "ProblemName.txt").write_text("case\n")
+    r = subprocess.run([MOCK["explicit"]], cwd=str(tmp_path), env=dict(os.environ, CFDB200_CPU_SEMANTICS="1"), capture_output=True, text=True,
+                       stdin=subprocess.DEVNULL, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = {ln.split()[1].split(".")[1]: ln for ln in r.stderr.split("\n") if ln.startswith("mock: cfd_problem.")}
+    assert len(lines) == 19 and all(ln.endswith(" ok") for ln in lines.values()), "\n".join(lines.values())
+    assert " 13997521 values" in lines["sparseKvalue"] and " 3442951 values" in lines["sparseG1value"] and " 3307949 values" in lines["sparseZvalue"]
+    for key in ("coord", "sparseKvalue", "sparseG1value", "sparseG2value", "sparseG3value", "MdInv", "MdOrigInv"):
+        assert "= 0.00e+00 ok" in lines[key], lines[key]
+
+
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="shim revision after round 1's GPU minutes were spent: first hardware run is this one")
 @pytest.mark.parametrize("name,env", [("ref_bch_cav4", {"CFDB200_CPU_SEMANTICS": "1"}), ("ref_bch_cav6c", {"CFDB200_CPU_SEMANTICS": "1"}),
