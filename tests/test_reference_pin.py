@@ -87,7 +87,8 @@ def test_oracle_reproduces_reference_run(mesh, name):
     g, meta = load(name)
     # tight fixtures: one thread, so that the summation order -- and with it the path BiCGStab takes along the rounding
     # floor -- is the same in every run of this test
-    o = orc.Oracle(inp_for(mesh, name, meta), meta["scheme"], 1 if meta["env"] else 0, **settings(meta)[0])
+    one_thread = meta["scheme"] == "implicit" and meta["stride"] == 1      # small implicit fixtures (as-is ones too): deterministic
+    o = orc.Oracle(inp_for(mesh, name, meta), meta["scheme"], 1 if one_thread else 0, **settings(meta)[0])
     o.run(meta["steps"])
     eu, ep = errors(o.U, o.P, g, meta, o.i("NN"))
     bu, bp, dcg = bars(name, meta)
