@@ -195,8 +195,11 @@ def cpu_sample(w, steps, warmup):
               % (n_s, "Q2/Q1" if w["NENv"] == 27 else "Q1/Q1", w["scheme"], steps, warmup))
     if n_s != w["n"]:
         sample += "; steps/s scaled by element count %d^3/%d^3 to the workload mesh" % (n_s, w["n"])
+    note = ("the reference program itself (oracle/_ref) is timed on the Q2/Q1 workloads; it has no Q1/Q1 element (its NENv == 8 shape-function "
+            "branch is commented out, blascoCodinaHuerta.cpp:2303-2305), so this workload uses the oracle port, which reproduces the reference "
+            "program's output on Q2/Q1 inputs to 1e-12 (tests/test_reference_pin.py)") if w["NENv"] == 8 else "oracle/_ref not built: oracle port"
     return dict(value=scale / sec, unit="steps/s", cores=info["threads"], kind="port", sample=sample,
-                sample_steps_per_s=1.0 / sec, cg_gdof_iter_per_s=info["cg_gdof_iter_per_s"])
+                sample_steps_per_s=1.0 / sec, cg_gdof_iter_per_s=info["cg_gdof_iter_per_s"], note=note)
 
 
 def main():
