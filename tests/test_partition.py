@@ -21,7 +21,9 @@ def csr(s, v, which, shape):
 
 @pytest.mark.parametrize("cav,scheme,W", [(dict(nx=6, NENv=27), "explicit", 2), (dict(nx=6, NENv=27), "implicit", 3),
                                            (dict(nx=8, NENv=8), "explicit", 4), (dict(nx=5, ny=4, nz=7, NENv=27), "explicit", 3),
-                                           (dict(nx=8, NENv=8), "implicit", 8)])
+                                           (dict(nx=8, NENv=8), "implicit", 8),
+                                           # blocks that are not whole element layers; one element per rank
+                                           (dict(nx=3, ny=3, nz=2, NENv=27), "explicit", 5), (dict(nx=2, ny=2, nz=2, NENv=8), "implicit", 8)])
 def test_partition_consistency(cav, scheme, W):
     import fracstep
     g = fracstep.Solver(scheme=scheme, cavity=cav, init_gpu=False)
