@@ -25,3 +25,22 @@ print("NN %d, nnz %d, slices of 16 rows (T = 2)" % (NN, A.nnz))
 for k, P in orders.items():
     a, b, c = stats(np.asarray(P))
     print("%-22s nnz/slice %7.1f   32B sectors/slice %7.1f   128B lines/slice %6.1f   -> gathered bytes per non-zero (sector granularity) %.2f" % (k, a, b, c, 32 * b / a))
+
+# constrained variants: the first NCN numbers must stay with the corner (pressure) nodes
+NCN = s.i("NNp")
+def corners_first(order):
+    order = np.asarray(order)
+    return np.concatenate([order[order < NCN], order[order >= NCN]])
+for k in ("RCM", "sort by (z, y, x)"):
+    P = corners_first(orders[k])
+    a, b, c = stats(P)
+    print("%-22s nnz/slice %7.1f   32B sectors/slice %7.1f   128B lines/slice %6.1f   -> gathered bytes per non-zero (sector granularity) %.2f" % (k + ", corners first", a, b, c, 32 * b / a))
+# interleaved by element: nodes in order of first appearance in the element list (x-fastest element order), corners first
+L = s.arr("LtoGnode").reshape(-1, 27)
+seen = np.zeros(NN, bool); order = []
+for e in range(L.shape[0]):
+    for v in L[e]:
+        if not seen[v]: seen[v] = True; order.append(v)
+P = corners_first(np.array(order))
+a, b, c = stats(P)
+print("%-22s nnz/slice %7.1f   32B sectors/slice %7.1f   128B lines/slice %6.1f   -> %.2f" % ("element order, corners first", a, b, c, 32 * b / a))
