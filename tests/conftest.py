@@ -35,7 +35,11 @@ def mesh(meshdir):
 
 @pytest.fixture(scope="session", autouse=True)
 def _built():
+    import subprocess
     import fracstep
     import orc
     orc.build()
     fracstep.build()
+    # the rest of the checkers: stand-in library, and -- where the reference tree is mounted -- the reference programs themselves
+    # (oracle/_ref: git-ignored binaries, so a fresh checkout has none; a no-op on the GPU box, which gets them prebuilt)
+    subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
