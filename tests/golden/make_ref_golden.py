@@ -57,6 +57,8 @@ CASES = {
                                   dict(TIGHT, REF_SHIM_CG_TOL="1e-9"), 1),
     # a longer run: 20 time steps (73 pressure solves) on an 8^3 clustered mesh, every 7th node stored
     "ref_bch_cav8c_20steps": ("explicit", "cube", dict(n=8, cluster=2.0), 20, {}, 7),
+    # BASELINE.json configs[2] stand-in at its full size (48 x 32 x 32 channel, 409 825 velocity nodes), explicit, every 97th node stored
+    "ref_bch_chan483232": ("explicit", "channel", dict(nx=48, ny=32, nz=32), 2, {}, 97),
     # BASELINE.json configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (meshgen.cube(30, cluster=2.0) is that
     # file byte for byte, tests/test_oracle.py), only t_final shortened; every 61st node stored
     "ref_bch_ne27000": ("explicit", "cube", dict(n=30, cluster=2.0), 3, {}, 61),

@@ -26,7 +26,7 @@ SMALL = ["ref_bch_cav4", "ref_bch_cav6c", "ref_bch_chan644", "ref_gq_cav4", "ref
          "ref_gq_chan644_tight", "ref_bch_box345_nopin", "ref_bch_cav4_pin1_it1", "ref_gq_box345_nopin_tight"]
 FULL = ["ref_bch_ne27000", "ref_gq_ne27000"]
 # added after the round's GPU budget was spent: checked against the oracle here, against the CUDA path from round 2 on
-CPU_ONLY = ["ref_bch_cav8c_20steps"]
+CPU_ONLY = ["ref_bch_cav8c_20steps", "ref_bch_chan483232"]
 
 
 def load(name):
