@@ -763,6 +763,7 @@ int bicgstab(Orc& o, const double* A, const double* b, double* x) {
    for (int i = 0; i < n; i++)
       for (int k = P.rowStarts[i]; k < P.rowStarts[i + 1]; k++)
          if (P.col[k] == i) dinv[i] = 1.0 / A[k];
+#pragma omp parallel for schedule(static)
    for (int i = 0; i < n; i++) { x[i] = 0; r[i] = b[i]; p[i] = r[i]; rs[i] = r[i]; }
    double rrsOld = dot(rs.data(), r.data(), n);
    const double bnorm = std::sqrt(dot(b, b, n));
@@ -770,9 +771,11 @@ int bicgstab(Orc& o, const double* A, const double* b, double* x) {
    while (true) {
       double rnorm = std::sqrt(dot(r.data(), r.data(), n));
       if (rnorm <= o.opt.bicg_tol * bnorm || it >= o.opt.bicg_maxit) break;
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) Mp_[i] = dinv[i] * p[i];
       spmv(P, A, Mp_.data(), AMp.data(), 1.0, 0.0);
       double alpha = rrsOld / dot(rs.data(), AMp.data(), n);
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) s[i] = r[i] - alpha * AMp[i];
       double snorm = std::sqrt(dot(s.data(), s.data(), n));
       if (snorm <= o.opt.bicg_tol * bnorm) {
@@ -780,9 +783,11 @@ int bicgstab(Orc& o, const double* A, const double* b, double* x) {
          it++;
          break;
       }
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) Ms[i] = dinv[i] * s[i];
       spmv(P, A, Ms.data(), AMs.data(), 1.0, 0.0);
       double omega = dot(AMs.data(), s.data(), n) / dot(AMs.data(), AMs.data(), n);
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) {
          x[i] += alpha * Mp_[i] + omega * Ms[i];
          r[i] = s[i] - omega * AMs[i];
@@ -790,6 +795,7 @@ int bicgstab(Orc& o, const double* A, const double* b, double* x) {
       double rrsNew = dot(rs.data(), r.data(), n);
       double beta = (rrsNew / rrsOld) * (alpha / omega);
       rrsOld = rrsNew;
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) p[i] = r[i] + beta * (p[i] - omega * AMp[i]);
       it++;
    }
