@@ -438,6 +438,13 @@ double now_s() {
 int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::string& restartPath, int init_gpu, int world = 1,
                   int rank = 0) {
    s->scheme = scheme;
+   if (scheme != CFD_EXPLICIT && scheme != CFD_IMPLICIT) { set_error("scheme must be CFD_EXPLICIT (0) or CFD_IMPLICIT (1), got %d", scheme); return CFD_ERR_ARG; }
+   // the reference divides by dt and the density without looking (BCH.cpp:2822, 3240); a zero would only show up as NaN fields
+   if (!(s->mesh.dt > 0.0) || !(s->mesh.density > 0.0) || !(s->mesh.viscosity >= 0.0)) {
+      set_error("dt and density must be positive, viscosity non-negative (dt %g, density %g, viscosity %g)", s->mesh.dt, s->mesh.density, s->mesh.viscosity);
+      return CFD_ERR_ARG;
+   }
+   if (world > s->mesh.NE) { set_error("%d ranks for %d elements: an element block per rank needs world <= NE", world, s->mesh.NE); return CFD_ERR_ARG; }
    if (opt) s->opt = *opt; else cfd_default_options(&s->opt);
    {
       // one process per GPU: launchers such as torchrun pin OMP_NUM_THREADS=1; give each rank its share of the cores
