@@ -65,7 +65,7 @@ def test_partition_consistency(cav, scheme, W):
     assert len(owners) == 1 and locs[owners[0]].arr("part_presGlobal")[pins[owners[0]]] == g.i("zeroPressureNode")
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, scheme="explicit", cav=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, os.path.join(ROOT, "cfd-with-cuda_b200"))
     import torch
@@ -73,9 +73,9 @@ def _worker(rank, world, port, q):
     import fracstep
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        cav = dict(nx=6, NENv=27)
-        s = fracstep.Solver(scheme="explicit", cavity=cav, init_gpu=False, world=world, rank=rank)
-        g = fracstep.Solver(scheme="explicit", cavity=cav, init_gpu=False)
+        cav = cav or dict(nx=6, NENv=27)
+        s = fracstep.Solver(scheme=scheme, cavity=cav, init_gpu=False, world=world, rank=rank)
+        g = fracstep.Solver(scheme=scheme, cavity=cav, init_gpu=False)
         NN, NNp = g.i("NN"), g.i("NNp")
         NNl, NPl, NNo, NPo = s.i("NN"), s.i("NNp"), s.i("NN_owned"), s.i("NNp_owned")
         ng, pg = s.arr("part_nodeGlobal"), s.arr("part_presGlobal")
@@ -131,12 +131,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_halo_exchange_gloo():
+@pytest.mark.parametrize("world,scheme,cav", [(2, "explicit", dict(nx=6, NENv=27)),
+                                               # three ranks (the middle one has two peers), one halo layer, Q1/Q1, non-cubic
+                                               (3, "implicit", dict(nx=5, ny=4, nz=7, NENv=8))])
+def test_halo_exchange_gloo(world, scheme, cav):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, scheme, cav)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
