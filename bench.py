@@ -337,6 +337,7 @@ def main():
                          d2h_bytes_per_step=int(8 * (U.size + P.size)), note="per rank: its block's U,P (owned + ghost) each step"),
                 gpu_launches=int(launches),
                 roofline=dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
+                              frac_of_nominal_8000=round(achieved / 8000.0, 4),   # both the measured-copy and the nominal peak
                               traffic=traffic, peak_source=peak_src, share_of_step=round(d["ms"] / total_ms, 4) if total_ms else None,
                               note="achieved = ALGORITHMIC bytes (CSR model: 12 B per non-zero + vectors) / event time; slices with a shared "
                                    "column-offset pattern store their indices once (lossless), so on structured meshes the kernel moves fewer DRAM "
