@@ -75,16 +75,11 @@ void element_geometry(const Mesh& m, const FeTables& T, int e, ElemGeom& g) {
    }
 }
 
-inline void atomic_add(double& t, double v) {
-#pragma omp atomic
-   t += v;
-}
-
 }   // namespace
 
 // step0 (BCH.cpp:3127-3315, GQ.cpp:3425-3572): M, K, G1..3; lumped mass and Z = sum_c G_c^T Md^-1 G_c
 // (explicit, BCH.cpp:3322-3479 / BCH.cu:281-411) or the FE Laplacian Z (implicit, GQ.cpp:3677-3772).
-// Element loop in parallel with atomic adds instead of the reference's serial loop.
+// Element loop in parallel, summation order of the reference's serial loop (owner-gather, see below).
 static double wall_s() {
    timeval tv;
    gettimeofday(&tv, nullptr);
@@ -115,72 +110,96 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
       par_zero(A.Zval, (size_t)A.Zp().nnz());
       PHASE("pattern Z");
    }
-   // Elements are dealt to threads in contiguous chunks.  A node touched only by elements of one chunk is
-   // private to that thread: elements whose nodes are all private add without atomics (all but the chunk
-   // boundary layers); the others use atomic adds.
-   int nthr = 1;
+   // Deterministic assembly: every CSR entry receives its element contributions in ASCENDING ELEMENT ORDER -- the order of the
+   // reference's serial element loop (BCH.cpp:3127-3315) -- whatever the number of threads, so K, M, G and Z are bitwise the same
+   // arrays on every host (the under-integrated implicit Q2 matrices amplify last-bit differences).
+   // Elements are processed in blocks: (1) element matrices of the block in parallel into a buffer, (2) owner-gather: in parallel
+   // over the nodes the block touches, each node adds the rows it owns from its elements of the block, in element order.
+   std::vector<int> adjStart((size_t)NN + 1, 0);
+   std::vector<unsigned> adj((size_t)NE * nv);   // (element << 5) | local node, grouped by node, ascending element
+   for (size_t q = 0; q < (size_t)NE * nv; q++) adjStart[m.LtoGnode[q] + 1]++;
+   for (int n = 0; n < NN; n++) adjStart[n + 1] += adjStart[n];
+   {
+      std::vector<int> fill(adjStart.begin(), adjStart.end() - 1);
+      for (int e = 0; e < NE; e++)
+         for (int i = 0; i < nv; i++) adj[fill[m.LtoGnode[(size_t)e * nv + i]]++] = ((unsigned)e << 5) | (unsigned)i;
+   }
+   const bool implicitZ = scheme == CFD_IMPLICIT;
+   const size_t oM = 0, oK = (size_t)nv * nv, oG = 2 * (size_t)nv * nv, oZ = oG + 3 * (size_t)nv * 8, stride = oZ + (implicitZ ? 64 : 0);
+   const int B = (int)std::min<long long>(NE, std::max<long long>(4096, (long long)(256u << 20) / (long long)(8 * stride)));
+   std::vector<double> buf((size_t)B * stride);
+   std::vector<int> cursor(adjStart.begin(), adjStart.end() - 1), mark((size_t)NN, -1), touched;
+   for (int b0 = 0, blk = 0; b0 < NE; b0 += B, blk++) {
+      const int b1 = std::min(NE, b0 + B);
 #pragma omp parallel
-   {
-#pragma omp single
-      nthr = omp_get_num_threads();
-   }
-   auto chunkOf = [&](int e) { return (int)(((long long)e * nthr) / NE); };
-   std::vector<unsigned char> shared((size_t)NN, 0);
-   {
-      std::vector<short> lo((size_t)NN, 32767), hi((size_t)NN, -1);
-      for (int e = 0; e < NE; e++) {
-         const short ch = (short)chunkOf(e);
-         const int* L = &m.LtoGnode[(size_t)e * nv];
-         for (int i = 0; i < nv; i++) { lo[L[i]] = std::min(lo[L[i]], ch); hi[L[i]] = std::max(hi[L[i]], ch); }
-      }
-      for (int n = 0; n < NN; n++) shared[n] = lo[n] != hi[n];
-   }
-#pragma omp parallel num_threads(nthr)
-   {
-      ElemGeom* g = new ElemGeom;
-      const int tid = omp_get_thread_num();
-      const int e0 = (int)(((long long)NE * tid + nthr - 1) / nthr), e1 = (int)(((long long)NE * (tid + 1) + nthr - 1) / nthr);
-      for (int e = e0; e < e1; e++) {
-         element_geometry(m, T, e, *g);
-         const int* L = &m.LtoGnode[(size_t)e * nv];
-         bool priv = true;
-         for (int i = 0; i < nv; i++) priv = priv && !shared[L[i]];
-         auto add = [priv](double& t, double v) { if (priv) t += v; else atomic_add(t, v); };
-         const int* mm = &A.mapM[(size_t)e * nv * nv];
-         for (int i = 0; i < nv; i++)
-            for (int j = 0; j < nv; j++) {
-               double me = 0, ke = 0;
-               for (int k = 0; k < 8; k++) {
-                  me += T.Sv[k][i] * T.Sv[k][j] * g->fac[k];
-                  ke += (g->gv[k][i][0] * g->gv[k][j][0] + g->gv[k][i][1] * g->gv[k][j][1] + g->gv[k][i][2] * g->gv[k][j][2]) * g->fac[k];
+      {
+         ElemGeom* g = new ElemGeom;
+#pragma omp for schedule(static)
+         for (int e = b0; e < b1; e++) {
+            element_geometry(m, T, e, *g);
+            double* eb = &buf[(size_t)(e - b0) * stride];
+            for (int i = 0; i < nv; i++)
+               for (int j = 0; j < nv; j++) {
+                  double me = 0, ke = 0;
+                  for (int k = 0; k < 8; k++) {
+                     me += T.Sv[k][i] * T.Sv[k][j] * g->fac[k];
+                     ke += (g->gv[k][i][0] * g->gv[k][j][0] + g->gv[k][i][1] * g->gv[k][j][1] + g->gv[k][i][2] * g->gv[k][j][2]) * g->fac[k];
+                  }
+                  eb[oM + i * nv + j] = mscale * me;
+                  eb[oK + i * nv + j] = m.viscosity * ke;
                }
-               add(A.Mval[mm[i * nv + j]], mscale * me);
-               add(A.Kval[mm[i * nv + j]], m.viscosity * ke);
-            }
-         const int* mg = &A.mapG()[(size_t)e * nv * 8];
-         for (int i = 0; i < nv; i++)
-            for (int j = 0; j < 8; j++) {
-               double g1 = 0, g2 = 0, g3 = 0;
-               for (int k = 0; k < 8; k++) {
-                  const double w = T.Sp[k][j] * g->fac[k];
-                  g1 += w * g->gv[k][i][0]; g2 += w * g->gv[k][i][1]; g3 += w * g->gv[k][i][2];
-               }
-               add(A.G1[mg[i * 8 + j]], -invDens * g1);
-               add(A.G2[mg[i * 8 + j]], -invDens * g2);
-               add(A.G3[mg[i * 8 + j]], -invDens * g3);
-            }
-         if (scheme == CFD_IMPLICIT) {
-            const int* mz = &A.mapZ()[(size_t)e * 64];
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < nv; i++)
                for (int j = 0; j < 8; j++) {
-                  double z = 0;
-                  for (int k = 0; k < 8; k++)
-                     z += (g->gp[k][i][0] * g->gp[k][j][0] + g->gp[k][i][1] * g->gp[k][j][1] + g->gp[k][i][2] * g->gp[k][j][2]) * g->fac[k];
-                  add(A.Zval[mz[i * 8 + j]], -z);
+                  double g1 = 0, g2 = 0, g3 = 0;
+                  for (int k = 0; k < 8; k++) {
+                     const double w = T.Sp[k][j] * g->fac[k];
+                     g1 += w * g->gv[k][i][0]; g2 += w * g->gv[k][i][1]; g3 += w * g->gv[k][i][2];
+                  }
+                  eb[oG + (size_t)(i * 8 + j) * 3 + 0] = -invDens * g1;
+                  eb[oG + (size_t)(i * 8 + j) * 3 + 1] = -invDens * g2;
+                  eb[oG + (size_t)(i * 8 + j) * 3 + 2] = -invDens * g3;
                }
+            if (implicitZ)
+               for (int i = 0; i < 8; i++)
+                  for (int j = 0; j < 8; j++) {
+                     double z = 0;
+                     for (int k = 0; k < 8; k++)
+                        z += (g->gp[k][i][0] * g->gp[k][j][0] + g->gp[k][i][1] * g->gp[k][j][1] + g->gp[k][i][2] * g->gp[k][j][2]) * g->fac[k];
+                     eb[oZ + i * 8 + j] = -z;
+                  }
          }
+         delete g;
       }
-      delete g;
+      touched.clear();
+      for (int e = b0; e < b1; e++)
+         for (int i = 0; i < nv; i++) {
+            const int n = m.LtoGnode[(size_t)e * nv + i];
+            if (mark[n] != blk) { mark[n] = blk; touched.push_back(n); }
+         }
+      const long long nt = (long long)touched.size();
+#pragma omp parallel for schedule(dynamic, 256)
+      for (long long q = 0; q < nt; q++) {
+         const int n = touched[(size_t)q];
+         int c = cursor[n];
+         for (; c < adjStart[n + 1]; c++) {
+            const int e = (int)(adj[c] >> 5), i = (int)(adj[c] & 31u);
+            if (e >= b1) break;
+            const double* eb = &buf[(size_t)(e - b0) * stride];
+            const int* mm = &A.mapM[(size_t)e * nv * nv + (size_t)i * nv];
+            for (int j = 0; j < nv; j++) { A.Mval[mm[j]] += eb[oM + i * nv + j]; A.Kval[mm[j]] += eb[oK + i * nv + j]; }
+            const int* mg = &A.mapG()[(size_t)e * nv * 8 + (size_t)i * 8];
+            for (int j = 0; j < 8; j++) {
+               A.G1[mg[j]] += eb[oG + (size_t)(i * 8 + j) * 3 + 0];
+               A.G2[mg[j]] += eb[oG + (size_t)(i * 8 + j) * 3 + 1];
+               A.G3[mg[j]] += eb[oG + (size_t)(i * 8 + j) * 3 + 2];
+            }
+            if (implicitZ && i < 8) {
+               const int* mz = &A.mapZ()[(size_t)e * 64 + (size_t)i * 8];
+               for (int j = 0; j < 8; j++) A.Zval[mz[j]] += eb[oZ + i * 8 + j];
+            }
+         }
+         cursor[n] = c;
+      }
    }
    PHASE("element assembly");
    if (scheme == CFD_EXPLICIT) {
