@@ -912,19 +912,25 @@ struct BicgArgs {
    int n;
    const double* b;   // [3][n]
    double* x;         // [3][n]
-   double* w;         // work: r, rs, p, ph, AMp, sh, AMs  -> 7 x [3][n]
+   double* w;         // work: r, rs, p, ph, AMp, sh, AMs, xbest  -> 8 x [3][n]
    const double* dinv;
    double* scratch;   // 2 buffers x 6 x gridDim
-   double* info;      // [3 + s] iterations of system s
+   double* info;      // see kBicgInfo*
    double tol;
    int maxit;
+   int halfstep;      // 1 = also test the residual after the half step (cusp::krylov::bicgstab); 0 = once per iteration (PARALUTION)
+   int verify;        // 1 = accept a solve only on its TRUE residual |b - A x|; restart from it otherwise
 };
+// result slots inside cfd_ctx::kinfo (doubles)
+enum { kBicgInfoIts = 3, kBicgInfoRR = 6, kBicgInfoTrue = 9, kBicgInfoBB = 12, kBicgInfoFin = 15, kBicgInfoRestarts = 18, kBicgInfoPasses = 21,
+       kBicgInfoTimers = 32 };
 
 // out_s = A * in_s for the NA still-active systems sys[0..NA) (multi-RHS: one pass over A), fused with
 // the two dot products every BiCGStab SpMV is followed by: d0[s] += l1_s . out_s, d1[s] += out_s . out_s.
+// RES = true: residual form, out_s = l1_s - A * in_s (l1 = right-hand side), d1[s] += |out_s|^2  (true-residual check / restart).
 // Specialised on NA so that the common late phase (one slow system left) runs a lean single-vector loop
 // with four matrix pairs in flight per lane.
-template <int NA>
+template <int NA, bool RES>
 __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int dynStart, int* dynCounter, const double* __restrict__ val, int n,
                                              const double* in, double* out, const int (&sys)[3], const double* l1, double (&d0)[3], double (&d1)[3],
                                              int gwarp, int nwarps, int lane) {
@@ -933,6 +939,8 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int
    // warps whose slices were cheap (rows of a Q2 mesh differ 4.6x in length, and in how well their gathers hit L1) keep
    // working instead of waiting at the grid reduction: measured on the 30^3 Taylor-Hood cavity, block 0 used to wait 22 us
    // after a 29 us SpMV share.  `dynCounter` must be 0 on entry; the kernel resets it after the reduction that follows.
+   // (With the counter the dot-product partials depend on which warp drew which slice: results are reproducible to rounding,
+   // not bitwise; cfd_options.deterministic = 1 turns the counter off.)
    const int nstatic = dynCounter ? dynStart : A.nslices;
    const SliceRange sr = slice_range(nstatic, part, gwarp, nwarps);
    size_t base[NA];
@@ -964,9 +972,15 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int
 #pragma unroll
          for (int q = 0; q < NA; q++) {
             const size_t i = base[q] + row;
-            out[i] = acc[q];
-            s0[q] += l1[i] * acc[q];
-            s1[q] += acc[q] * acc[q];
+            if (RES) {
+               const double ri = l1[i] - acc[q];
+               out[i] = ri;
+               s1[q] += ri * ri;
+            } else {
+               out[i] = acc[q];
+               s0[q] += l1[i] * acc[q];
+               s1[q] += acc[q] * acc[q];
+            }
          }
       }
    }
@@ -978,25 +992,39 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int
       else { d0[2] += s0[q]; d1[2] += s1[q]; }
    }
 }
+template <bool RES>
 __device__ __forceinline__ void bicg_spmv_phase(const BicgArgs& a, const double* in, double* out, const bool (&act)[3], const double* l1,
                                                 double (&d0)[3], double (&d1)[3], int gwarp, int nwarps, int lane) {
    const double* __restrict__ val = sell_vals(a.A, a.vidx);
    int sys[3] = {0, 0, 0}, na = 0;
    for (int c = 0; c < 3; c++)
       if (act[c]) sys[na++] = c;
-   if (na == 1) bicg_spmv_na<1>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 2) bicg_spmv_na<2>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 3) bicg_spmv_na<3>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   if (na == 1) bicg_spmv_na<1, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 2) bicg_spmv_na<2, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 3) bicg_spmv_na<3, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
 }
 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
-// CUSP_GMRES_solver -> cusp::krylov::bicgstab, GQ.cu:369-433, x0 = 0).  The three systems share A,
-// so each of the two SpMV phases per iteration streams A once for all still-active right-hand sides.
-// Per-system scalars are block-uniform and live in shared memory (written by thread 0 after each grid
-// reduction), which keeps the register budget for the SpMV sweep.
+// CUSP_GMRES_solver -> cusp::krylov::bicgstab, GQ.cu:369-433, x0 = 0; CPU build: paralution_BiCGStab_solver, GQ.cpp:4183-4231).
+// The three systems share A, so each of the two SpMV phases per iteration streams A once for all still-active right-hand
+// sides.  Per-system scalars are block-uniform and live in shared memory (written by thread 0 after each grid reduction),
+// which keeps the register budget for the SpMV sweep.
+//
+// Acceptance is on the TRUE residual.  When the recurrence residual of a system meets the stopping rule (at the top of an
+// iteration or -- CUSP's rule -- after the half step), when it breaks down (alpha, omega or rho not finite / zero) or when
+// it runs out of iterations, r = b - A x is recomputed.  If |r| <= tol |b| the system is done and flagged converged.
+// Otherwise it is RESTARTED from that residual (new shadow residual rs = r, p = r), at most kBicgMaxRestarts times and
+// only while restarts still gain; a system that stops unconverged returns the iterate with the smallest true residual it
+// has verified, flags converged = 0 and reports that residual (cfd_step_report.bicg_true_residual).  In the common case
+// (the recurrence residual is honest) this costs one extra SpMV per system and changes neither iterates nor counts.
+// Round 1 accepted whatever iterate existed at a breakdown: on the reference's under-integrated Q2 momentum matrix at
+// 1e-12 that silently returned solves with a 1e-9 residual, i.e. 1e-5 in the fields.
+enum { kBicgMaxRestarts = 12 };
 struct BicgScalars {
-   double bb[3], rr[3], rrs[3], thresh[3], alpha[3], omega[3];
-   int its[3], act[3], half[3], act2[3];
+   double bb[3], rr[3], rrs[3], thresh[3], alpha[3], omega[3], trueRR[3], bestRR[3], prevTrue[3];
+   int its[3], act[3], half[3], act2[3], chk[3], brk[3], fin[3], restarts[3], hasBest[3];
+   int todo[3];   // after a check: 0 nothing, 1 restart, 3 restart + remember x as the best iterate, 2 give back the best iterate
+   int passes;
 };
 __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    cg::grid_group grid = cg::this_grid();
@@ -1007,6 +1035,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
    double* buf0 = a.scratch;
    double* buf1 = a.scratch + 6 * (size_t)gridDim.x;
+   double* buf2 = a.scratch + 12 * (size_t)gridDim.x;   // the true-residual check has its own (it may run between any two others)
    const int n = a.n;
    const size_t N3 = 3 * (size_t)n;
    double* r = a.w;
@@ -1016,6 +1045,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    double* AMp = a.w + 4 * N3;
    double* shv = a.w + 5 * N3;   // M s
    double* AMs = a.w + 6 * N3;
+   double* xbest = a.w + 7 * N3;
 
    double v6[6] = {0, 0, 0, 0, 0, 0}, v3[3];
    for (int c = 0; c < 3; c++) {
@@ -1031,15 +1061,22 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       v6[c] = acc;
    }
    grid_sum<6>(grid, v6, buf0, sh);
-   if (threadIdx.x == 0)
+   if (threadIdx.x == 0) {
       for (int c = 0; c < 3; c++) {
          S.bb[c] = S.rr[c] = S.rrs[c] = v6[c];
          S.thresh[c] = a.tol * sqrt(v6[c]);
-         S.its[c] = 0; S.act[c] = 1; S.half[c] = 0; S.act2[c] = 0; S.alpha[c] = 0.0; S.omega[c] = 0.0;
+         S.its[c] = 0; S.half[c] = 0; S.act2[c] = 0; S.alpha[c] = 0.0; S.omega[c] = 0.0;
+         S.chk[c] = 0; S.brk[c] = 0; S.restarts[c] = 0; S.todo[c] = 0; S.hasBest[c] = 0;
+         S.trueRR[c] = v6[c]; S.bestRR[c] = v6[c]; S.prevTrue[c] = v6[c];
+         // b = 0: x = 0 is exact (first steps of a cavity: v = w = 0)
+         S.act[c] = v6[c] > 0.0 ? 1 : 0;
+         S.fin[c] = v6[c] > 0.0 ? 0 : 1;
       }
+      S.passes = 0;
+   }
    __syncthreads();
-   // phase clock of block 0 (diagnostics build only: info[16..24] = ns in spmv1 / reduce / s-update / reduce / spmv2 / reduce /
-   // x,r-update / reduce / p-update + grid sync, info[25] = lock-step iterations)
+   // phase clock of block 0 (diagnostics build only: info[kBicgInfoTimers + 0..8] = ns in spmv1 / reduce / s-update / reduce / spmv2 /
+   // reduce / x,r-update / reduce / p-update + grid sync, [+9] = lock-step iterations)
 #ifdef CFD_BICG_PHASE_TIMERS
    unsigned long long tph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1, nit = 0;
 #define BICG_TICK(k) do { if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
@@ -1048,37 +1085,94 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
 #define BICG_TICK(k)
 #endif
    while (true) {
+      // ---- stopping rule on the recurrence residual (cusp::default_monitor: tested before each iteration), breakdowns, iteration limit
       if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++)
-            if (S.act[c] && (sqrt(S.rr[c]) <= S.thresh[c] || S.its[c] >= a.maxit)) S.act[c] = 0;
+         for (int c = 0; c < 3; c++) {
+            S.chk[c] = 0; S.todo[c] = 0;
+            if (S.act[c] && (S.brk[c] || sqrt(S.rr[c]) <= S.thresh[c] || S.its[c] >= a.maxit)) {
+               if (a.verify) S.chk[c] = 1;
+               else { S.act[c] = 0; S.fin[c] = (!S.brk[c] && sqrt(S.rr[c]) <= S.thresh[c]) ? 1 : 2; }
+            }
+         }
       __syncthreads();
+      if (S.chk[0] | S.chk[1] | S.chk[2]) {
+         // ---- true residual of the candidates: AMs = b - A x, |AMs|^2
+         double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+         const bool chk[3] = {S.chk[0] != 0, S.chk[1] != 0, S.chk[2] != 0};
+         bicg_spmv_phase<true>(a, a.x, AMs, chk, a.b, d0, d1, gwarp, nwarps, lane);
+         v3[0] = d1[0]; v3[1] = d1[1]; v3[2] = d1[2];
+         grid_sum<3>(grid, v3, buf2, sh);
+         if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+         if (threadIdx.x == 0) {
+            S.passes++;
+            for (int c = 0; c < 3; c++) {
+               if (!S.chk[c]) continue;
+               const double tr = v3[c];
+               S.trueRR[c] = tr;
+               const bool improved = tr < S.bestRR[c];
+               if (sqrt(tr) <= S.thresh[c]) { S.act[c] = 0; S.fin[c] = 1; S.bestRR[c] = tr; }
+               else if (S.its[c] >= a.maxit || S.restarts[c] >= kBicgMaxRestarts || !isfinite(tr) ||
+                        (S.restarts[c] > 0 && !(tr < 0.25 * S.prevTrue[c]))) {
+                  // out of iterations, or restarts no longer gain (attainable accuracy reached): stop, unconverged, best iterate
+                  S.act[c] = 0; S.fin[c] = 2;
+                  if (!improved && S.hasBest[c]) { S.todo[c] = 2; S.trueRR[c] = S.bestRR[c]; }
+                  else if (improved) S.bestRR[c] = tr;
+               } else {
+                  S.todo[c] = improved ? 3 : 1;   // restart (3: and remember x as the best iterate so far)
+                  if (improved) { S.bestRR[c] = tr; S.hasBest[c] = 1; }
+                  S.prevTrue[c] = tr;
+                  S.restarts[c]++;
+                  S.rr[c] = S.rrs[c] = tr;
+                  S.brk[c] = 0;
+               }
+            }
+         }
+         __syncthreads();
+         if (S.todo[0] | S.todo[1] | S.todo[2]) {
+            for (int c = 0; c < 3; c++) {
+               const int todo = S.todo[c];
+               if (!todo) continue;
+               for (int i = tid; i < n; i += nthreads) {
+                  const size_t k = (size_t)c * n + i;
+                  if (todo == 2) { a.x[k] = xbest[k]; continue; }
+                  const double ri = AMs[k];
+                  r[k] = ri; rs[k] = ri; p[k] = ri;
+                  ph[k] = a.dinv[i] * ri;
+                  if (todo == 3) xbest[k] = a.x[k];
+               }
+            }
+         }
+         grid.sync();   // ph of the restarted systems is gathered by every block; the slice counter is reset for everybody
+      }
       if (!S.act[0] && !S.act[1] && !S.act[2]) break;
       // ---- AMp = A (M p), d0 = rs . AMp
       {
          double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
          const bool act[3] = {S.act[0] != 0, S.act[1] != 0, S.act[2] != 0};
-         bicg_spmv_phase(a, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
+         bicg_spmv_phase<false>(a, ph, AMp, act, rs, d0, d1, gwarp, nwarps, lane);
          v3[0] = d0[0]; v3[1] = d0[1]; v3[2] = d0[2];
       }
       BICG_TICK(0);
       grid_sum<3>(grid, v3, buf1, sh);
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the SpMV phase
       BICG_TICK(1);
-      // Breakdown guards (the reference's libraries have none and hand back NaN fields when BiCGStab stagnates on the rounding
-      // floor, e.g. at an unattainable tolerance on the under-integrated Q2 matrix): a non-finite alpha stops the system with the
-      // iterate it has; a non-finite omega accepts the half step; a non-finite beta stops it after the full step.  All blocks
-      // see bit-identical reduced values, so they decide alike.
-      if (threadIdx.x == 0)
+      // Breakdowns (the reference's libraries have no guards and hand back NaN fields): a non-finite alpha leaves x untouched, a
+      // non-finite or zero omega keeps the half step, a non-finite beta the full step; each time the system goes through the
+      // true-residual check above and is restarted from there.  All blocks see bit-identical reduced values, so they decide alike.
+      if (threadIdx.x == 0) {
+         S.passes++;
          for (int c = 0; c < 3; c++) {
+            S.half[c] = 0; S.act2[c] = 0;
             const double al = S.act[c] ? S.rrs[c] / v3[c] : 0.0;
-            if (!isfinite(al)) { S.act[c] = 0; S.alpha[c] = 0.0; }
+            if (S.act[c] && !isfinite(al)) { S.brk[c] = 1; S.alpha[c] = 0.0; }
             else S.alpha[c] = al;
          }
+      }
       __syncthreads();
       // ---- s = r - alpha AMp (stored in r), sh = M s, |s|^2
       for (int c = 0; c < 3; c++) {
          double acc = 0.0;
-         if (S.act[c]) {
+         if (S.act[c] && !S.brk[c]) {
             const double alpha = S.alpha[c];
             for (int i = tid; i < n; i += nthreads) {
                const size_t k = (size_t)c * n + i;
@@ -1094,29 +1188,35 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       grid_sum<3>(grid, v3, buf0, sh);
       BICG_TICK(3);
       if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++) {   // converged at the half step: x += alpha M p and stop
-            S.half[c] = (S.act[c] && sqrt(v3[c]) <= S.thresh[c]) ? 1 : 0;
-            S.act2[c] = (S.act[c] && !S.half[c]) ? 1 : 0;
+         for (int c = 0; c < 3; c++) {   // converged at the half step (cusp::krylov::bicgstab): x += alpha M p, no iteration counted
+            const int go = S.act[c] && !S.brk[c];
+            S.half[c] = (go && a.halfstep && sqrt(v3[c]) <= S.thresh[c]) ? 1 : 0;
+            S.act2[c] = (go && !S.half[c]) ? 1 : 0;
+            if (S.half[c]) S.rr[c] = v3[c];
          }
       __syncthreads();
-      // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
-      {
-         double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
-         const bool act2[3] = {S.act2[0] != 0, S.act2[1] != 0, S.act2[2] != 0};
-         bicg_spmv_phase(a, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
-         v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = d1[0]; v6[4] = d1[1]; v6[5] = d1[2];
+      if (S.act2[0] | S.act2[1] | S.act2[2]) {
+         // ---- AMs = A (M s), omega = (AMs . s) / (AMs . AMs)
+         {
+            double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+            const bool act2[3] = {S.act2[0] != 0, S.act2[1] != 0, S.act2[2] != 0};
+            bicg_spmv_phase<false>(a, shv, AMs, act2, r, d0, d1, gwarp, nwarps, lane);
+            v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = d1[0]; v6[4] = d1[1]; v6[5] = d1[2];
+         }
+         BICG_TICK(4);
+         grid_sum<6>(grid, v6, buf1, sh);
+         if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+         BICG_TICK(5);
+         if (threadIdx.x == 0) {
+            S.passes++;
+            for (int c = 0; c < 3; c++) {
+               const double om = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
+               if (S.act2[c] && (!isfinite(om) || om == 0.0)) { S.act2[c] = 0; S.half[c] = 1; S.brk[c] = 1; S.omega[c] = 0.0; }   // keep x + alpha M p
+               else S.omega[c] = om;
+            }
+         }
+         __syncthreads();
       }
-      BICG_TICK(4);
-      grid_sum<6>(grid, v6, buf1, sh);
-      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
-      BICG_TICK(5);
-      if (threadIdx.x == 0)
-         for (int c = 0; c < 3; c++) {
-            const double om = S.act2[c] ? v6[c] / v6[3 + c] : 0.0;
-            if (S.act2[c] && (!isfinite(om) || om == 0.0)) { S.act2[c] = 0; S.half[c] = 1; S.omega[c] = 0.0; }   // keep x + alpha M p
-            else S.omega[c] = om;
-         }
-      __syncthreads();
       // ---- x += alpha M p + omega M s ; r = s - omega AMs ; rs.r , r.r
       for (int c = 0; c < 3; c++) {
          double a0 = 0.0, a1 = 0.0;
@@ -1139,14 +1239,14 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          v6[c] = a0; v6[3 + c] = a1;
       }
       BICG_TICK(6);
-      grid_sum<6>(grid, v6, buf0, sh);
+      if (S.act2[0] | S.act2[1] | S.act2[2]) grid_sum<6>(grid, v6, buf0, sh);
       BICG_TICK(7);
       // ---- p = r + beta (p - omega AMp) ; ph = M p
       for (int c = 0; c < 3; c++) {
          if (!S.act2[c]) continue;
          const double omega = S.omega[c];
          const double beta = (v6[c] / S.rrs[c]) * (S.alpha[c] / omega);
-         if (!isfinite(beta)) continue;   // rho = 0: the system is stopped below
+         if (!isfinite(beta) || v6[c] == 0.0) continue;   // rho = 0: breakdown, handled below
          for (int i = tid; i < n; i += nthreads) {
             const size_t k = (size_t)c * n + i;
             const double pi = r[k] + beta * (p[k] - omega * AMp[k]);
@@ -1157,9 +1257,9 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       __syncthreads();   // every thread has read S.rrs before thread 0 replaces it
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) {
-            if (S.half[c]) { S.its[c]++; S.act[c] = 0; }
-            else if (S.act2[c]) {
-               if (!isfinite((v6[c] / S.rrs[c]) * (S.alpha[c] / S.omega[c]))) S.act[c] = 0;
+            if (S.act2[c]) {   // (half steps: no iteration counted, like CUSP; the stopping rule at the top of the loop takes them)
+               const double beta = (v6[c] / S.rrs[c]) * (S.alpha[c] / S.omega[c]);
+               if (!isfinite(beta) || v6[c] == 0.0) S.brk[c] = 1;
                S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++;
             }
          }
@@ -1172,12 +1272,21 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
 #undef BICG_TICK
 #ifdef CFD_BICG_PHASE_TIMERS
    if (tid == 0) {
-      for (int k = 0; k < 9; k++) a.info[16 + k] = (double)tph[k];
-      a.info[25] = (double)nit;
+      for (int k = 0; k < 9; k++) a.info[kBicgInfoTimers + k] = (double)tph[k];
+      a.info[kBicgInfoTimers + 9] = (double)nit;
    }
 #endif
-   if (tid == 0)
-      for (int c = 0; c < 3; c++) { a.info[3 + c] = (double)S.its[c]; a.info[6 + c] = S.rr[c]; }
+   if (tid == 0) {
+      for (int c = 0; c < 3; c++) {
+         a.info[kBicgInfoIts + c] = (double)S.its[c];
+         a.info[kBicgInfoRR + c] = S.rr[c];
+         a.info[kBicgInfoTrue + c] = a.verify ? S.trueRR[c] : -1.0;
+         a.info[kBicgInfoBB + c] = S.bb[c];
+         a.info[kBicgInfoFin + c] = (double)S.fin[c];
+         a.info[kBicgInfoRestarts + c] = (double)S.restarts[c];
+      }
+      a.info[kBicgInfoPasses] = (double)S.passes;
+   }
 }
 
 }   // namespace cfdb
@@ -1388,7 +1497,17 @@ int run_bicg_dist(cfd_ctx* c) {
       CFD_CK(cudaStreamSynchronize(c->stream));
       const DBicgState* hs = (const DBicgState*)(c->h_pinned + 40);
       if (hs->done) {
-         const double info[3] = {(double)hs->its[0], (double)hs->its[1], (double)hs->its[2]};
+         // mirror the persistent kernel's result slots (this host-driven fallback trusts the recurrence residual: true = -1)
+         double info[19];
+         for (int d = 0; d < 3; d++) {
+            info[kBicgInfoIts - 3 + d] = (double)hs->its[d];
+            info[kBicgInfoRR - 3 + d] = hs->rr[d];
+            info[kBicgInfoTrue - 3 + d] = -1.0;
+            info[kBicgInfoBB - 3 + d] = hs->bb[d];
+            info[kBicgInfoFin - 3 + d] = (sqrt(hs->rr[d]) <= hs->thresh[d]) ? 1.0 : 2.0;
+            info[kBicgInfoRestarts - 3 + d] = 0.0;
+         }
+         info[kBicgInfoPasses - 3] = 0.0;
          CFD_CK(cudaMemcpyAsync(c->kinfo + 3, info, sizeof info, cudaMemcpyHostToDevice, c->stream));
          CFD_CK(cudaStreamSynchronize(c->stream));
          break;
@@ -1433,10 +1552,20 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
 }
 
 int fetch_kinfo(cfd_ctx* c) {
-   CFD_CK(cudaMemcpyAsync(c->h_pinned + 16, c->kinfo, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   double* hk = c->h_pinned + 128;
+   CFD_CK(cudaMemcpyAsync(hk, c->kinfo, 32 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    CFD_CK(cudaStreamSynchronize(c->stream));
-   c->last_cg = (int)c->h_pinned[16];
-   for (int d = 0; d < 3; d++) c->last_bicg[d] = (int)c->h_pinned[16 + 3 + d];
+   c->last_cg = (int)hk[0];
+   c->last_cg_res = hk[2] > 0.0 ? sqrt(hk[1] / hk[2]) : 0.0;
+   c->last_cg_conv = (hk[2] == 0.0 || sqrt(hk[1]) <= c->opt.cg_tol * sqrt(hk[2])) ? 1 : 0;
+   for (int d = 0; d < 3; d++) {
+      c->last_bicg[d] = (int)hk[kBicgInfoIts + d];
+      const double bb = hk[kBicgInfoBB + d], tr = hk[kBicgInfoTrue + d];
+      c->last_bicg_conv[d] = (int)hk[kBicgInfoFin + d] == 1 ? 1 : 0;
+      c->last_bicg_true[d] = tr < 0.0 ? -1.0 : (bb > 0.0 ? sqrt(tr / bb) : 0.0);
+      c->last_bicg_restarts[d] = (int)hk[kBicgInfoRestarts + d];
+   }
+   c->last_bicg_passes = (int)hk[kBicgInfoPasses];
    if (c->p2p && c->xstate) {   // a peer that never arrived: the spin-waits of k_pcg_p2p give up after 4 s and raise this word
       unsigned long long err = 0;
       CFD_CK(cudaMemcpy(&err, c->xstate + 2, sizeof err, cudaMemcpyDeviceToHost));
@@ -1452,7 +1581,8 @@ int fetch_kinfo(cfd_ctx* c) {
       const double N = c->P.NN;
       double b = 0;
       const int mx = std::max(c->last_bicg[0], std::max(c->last_bicg[1], c->last_bicg[2]));
-      b += mx * 2.0 * (12.0 * (double)c->K.nnz + 4.0 * (N + 1));       // A streamed twice per lock-step iteration
+      // A is streamed once per SpMV phase: twice per lock-step iteration, plus the true-residual checks (counted by the kernel)
+      b += (c->last_bicg_passes > 0 ? (double)c->last_bicg_passes : 2.0 * mx) * (12.0 * (double)c->K.nnz + 4.0 * (N + 1));
       for (int d = 0; d < 3; d++) b += c->last_bicg[d] * 192.0 * N;    // 24 vector reads/writes per system-iteration
       c->recs[c->lastBicgRec].bytes += b;
       c->lastBicgRec = -1;
@@ -1509,7 +1639,8 @@ double ebe_bytes(const cfd_ctx* c, bool assemble) {
 extern "C" {
 
 const char* cfd_last_error(void) { return cfdb::last_error(); }
-const char* cfd_version(void) { return "cfdb200 0.1 (sm_100a)"; }
+const char* cfd_version(void) { return "cfdb200 0.2 (sm_100a)"; }
+void cfd_struct_sizes(int out[3]) { out[0] = (int)sizeof(cfd_problem); out[1] = (int)sizeof(cfd_options); out[2] = (int)sizeof(cfd_step_report); }
 
 void cfd_default_options(cfd_options* o) {
    memset(o, 0, sizeof *o);
@@ -1577,7 +1708,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    else CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
    CFD_CK(cudaEventCreate(&c->ev0));
    CFD_CK(cudaEventCreate(&c->ev1));
-   CFD_CK(cudaMallocHost((void**)&c->h_pinned, 128 * sizeof(double)));
+   CFD_CK(cudaMallocHost((void**)&c->h_pinned, 256 * sizeof(double)));
 
    const int NN = P->NN, NNp = P->NNp, NE = P->NE, nv = P->NENv;
    // partition: NN / NNp are local (owned + ghost) counts, rows are the owned ones (numbered first)
@@ -1757,10 +1888,10 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       TRY(regvec(c, "Pk", &c->Pk, NNp)); TRY(regvec(c, "Pk_prev", &c->Pk_prev, NNp)); TRY(regvec(c, "Pk_prevprev", &c->Pk_prevprev, NNp));
       TRY(regvec(c, "Pdiff", &c->Pdiff, NNp)); TRY(regvec(c, "R2", &c->R2, NNp)); TRY(regvec(c, "R1", &c->R1i, N3));
       TRY(dalloc(c, &c->Adinv, (size_t)NN));
-      TRY(dalloc(c, &c->bw, (size_t)(7 * N3)));
+      TRY(dalloc(c, &c->bw, (size_t)(8 * N3)));
    }
    TRY(dalloc(c, &c->cg_r, (size_t)NNp)); TRY(dalloc(c, &c->cg_p, (size_t)NNp)); TRY(dalloc(c, &c->cg_q, (size_t)NNp));
-   TRY(dalloc(c, &c->kinfo, 32)); TRY(dalloc(c, &c->scal, 16));
+   TRY(dalloc(c, &c->kinfo, 64)); TRY(dalloc(c, &c->scal, 16));
    // initial state (applyBC_initial, BCH.cpp:4062-4110 / GQ.cpp:4559-4607)
    {
       std::vector<double> u0((size_t)N3, 0.0);
@@ -1828,7 +1959,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       int blocks2 = c->numSMs * occ2;
       if (needed2 < blocks2) blocks2 = std::max(c->numSMs, ((needed2 + c->numSMs - 1) / c->numSMs) * c->numSMs);
       c->bicg_blocks = std::min(blocks2, c->numSMs * occ2);
-      TRY(dalloc(c, &c->partials, (size_t)2 * 6 * std::max(c->pcg_blocks, c->bicg_blocks)));
+      TRY(dalloc(c, &c->partials, (size_t)3 * 6 * std::max(c->pcg_blocks, c->bicg_blocks)));
       auto partition = [](const std::vector<long long>& off, int nblk) {
          const int ns = (int)off.size() - 1;
          std::vector<int> part(nblk + 1, ns);
@@ -1846,7 +1977,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          // static share = the first ~88 % of the stored entries, balanced over the CTAs; the rest is the dynamic tail
          const int nsZ = (int)c->hostOffZ.size() - 1;
          int dynStart = nsZ;
-         const bool useDyn = getenv("CFD_NO_DYN") == nullptr && nsZ >= 4 * c->pcg_blocks * (c->pcg_threads / 32);
+         const bool useDyn = !o.deterministic && getenv("CFD_NO_DYN") == nullptr && nsZ >= 4 * c->pcg_blocks * (c->pcg_threads / 32);
          if (useDyn) {
             double frac = 0.88;
             if (const char* e = getenv("CFD_DYN_STATIC_FRAC")) frac = std::min(1.0, std::max(0.5, atof(e)));
@@ -1866,7 +1997,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          const int nsK = (int)c->hostOffK.size() - 1;
          const int nwarps = c->bicg_blocks * (c->bicg_threads / 32);
          int dynStart = nsK;
-         const bool useDyn = getenv("CFD_NO_DYN") == nullptr && nsK > nwarps;
+         const bool useDyn = !o.deterministic && getenv("CFD_NO_DYN") == nullptr && nsK > nwarps;
          if (useDyn) {
             dynStart = 0;
             if (nsK >= 4 * nwarps) {
@@ -2185,6 +2316,7 @@ int gq_step1GPU(cfd_ctx* c) {
       BicgArgs a;
       a.A = c->K; a.part = c->bicgPart; a.dynStart = c->bicgDynStart; a.dynCounter = c->bicgDynCounter; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
       a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
+      a.halfstep = c->opt.bicg_no_halfstep ? 0 : 1; a.verify = c->opt.bicg_no_verify ? 0 : 1;
       void* args[] = {&a};
       ProfScope ps(c, "bicgstab", 0.0);
       c->lastBicgRec = ps.idx;
@@ -2194,7 +2326,7 @@ int gq_step1GPU(cfd_ctx* c) {
       {
          double h[10];
          CFD_CK(cudaStreamSynchronize(c->stream));
-         CFD_CK(cudaMemcpy(h, c->kinfo + 16, sizeof h, cudaMemcpyDeviceToHost));
+         CFD_CK(cudaMemcpy(h, c->kinfo + kBicgInfoTimers, sizeof h, cudaMemcpyDeviceToHost));
          if (h[9] > 0)
             fprintf(stderr, "bicgstab phases (us / lock-step iteration, block 0; %d iterations): spmv1 %.2f red %.2f | s-upd %.2f red %.2f | spmv2 %.2f red %.2f | "
                             "xr-upd %.2f red %.2f | p-upd+sync %.2f\n", (int)h[9], h[0] / h[9] * 1e-3, h[1] / h[9] * 1e-3, h[2] / h[9] * 1e-3, h[3] / h[9] * 1e-3,
@@ -2267,6 +2399,20 @@ int cfd_last_bicgstab_iterations(cfd_ctx* c, int its[3]) {
    for (int d = 0; d < 3; d++) its[d] = c->last_bicg[d];
    return CFD_OK;
 }
+int cfd_last_krylov_status(cfd_ctx* c, int* cg_converged, double* cg_residual, int bicg_converged[3], double bicg_true_residual[3],
+                           int bicg_restarts[3]) {
+   if (!c) return CFD_ERR_ARG;
+   int rc = fetch_kinfo(c);
+   if (rc) return rc;
+   if (cg_converged) *cg_converged = c->last_cg_conv;
+   if (cg_residual) *cg_residual = c->last_cg_res;
+   for (int d = 0; d < 3; d++) {
+      if (bicg_converged) bicg_converged[d] = c->last_bicg_conv[d];
+      if (bicg_true_residual) bicg_true_residual[d] = c->last_bicg_true[d];
+      if (bicg_restarts) bicg_restarts[d] = c->last_bicg_restarts[d];
+   }
+   return CFD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // whole time steps
@@ -2278,6 +2424,8 @@ int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* re
    for (; s < nsteps; s++) {
       cfd_step_report rep;
       memset(&rep, 0, sizeof rep);
+      rep.cg_converged = 1;
+      for (int d = 0; d < 3; d++) { rep.bicg_converged[d] = 1; rep.bicg_true_residual[d] = -1.0; }
       if (c->P.scheme == CFD_EXPLICIT) {
          if ((rc = bch_beginTimeStep(c))) return rc;
          int iter;
@@ -2290,6 +2438,8 @@ int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* re
             if ((rc = bch_checkConvergenceGPU(c, &conv))) return rc;
             rep.cg_iterations += c->last_cg;
             rep.cg_solves++;
+            rep.cg_converged &= c->last_cg_conv;
+            rep.cg_residual = std::max(rep.cg_residual, c->last_cg_res);
             if (conv) break;
             if ((rc = bch_rotateIterates(c))) return rc;
             if ((rc = bch_calculate_KtimesAcc_prevGPU(c))) return rc;
@@ -2305,7 +2455,14 @@ int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* re
          rep.iter = 1;
          rep.cg_iterations = c->last_cg;
          rep.cg_solves = 1;
-         for (int d = 0; d < 3; d++) rep.bicg_iterations[d] = c->last_bicg[d];
+         rep.cg_converged = c->last_cg_conv;
+         rep.cg_residual = c->last_cg_res;
+         for (int d = 0; d < 3; d++) {
+            rep.bicg_iterations[d] = c->last_bicg[d];
+            rep.bicg_converged[d] = c->last_bicg_conv[d];
+            rep.bicg_true_residual[d] = c->last_bicg_true[d];
+            rep.bicg_restarts[d] = c->last_bicg_restarts[d];
+         }
          if ((rc = gq_endTimeStep(c))) return rc;
       }
       rep.timeN = c->timeN;

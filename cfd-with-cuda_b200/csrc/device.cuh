@@ -108,13 +108,13 @@ struct cfd_ctx {
    double *Uk = nullptr, *Uk_prev = nullptr, *Pk = nullptr, *Pk_prev = nullptr, *Pk_prevprev = nullptr, *Pdiff = nullptr;
    double* R1i = nullptr;       // [3][NN] the three momentum right-hand sides
    double* Adinv = nullptr;     // [NN]
-   double* bw = nullptr;        // BiCGStab work: 7 x [3][NN]
+   double* bw = nullptr;        // BiCGStab work: 8 x [3][NN]
    // Krylov work
    double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;
    double* partials = nullptr;  // grid-reduction scratch
    double* kinfo = nullptr;     // device: Krylov results (iterations, residuals)
    double* scal = nullptr;      // device: [0..3] convergence sums, [4] maxAcc bits
-   double* h_pinned = nullptr;  // pinned host mirror for read-backs (64 doubles)
+   double* h_pinned = nullptr;  // pinned host mirror for read-backs (256 doubles; [128..191] = Krylov results)
    int pcg_blocks = 0, pcg_threads = 512, bicg_blocks = 0, bicg_threads = 512;
    int pcg_minb = 3;
    int pcgDynStart = 0;             // slices >= this are scheduled dynamically inside k_pcg
@@ -126,6 +126,8 @@ struct cfd_ctx {
    // bookkeeping
    int timeN = 0;
    int last_cg = 0, last_bicg[3] = {0, 0, 0};
+   int last_cg_conv = 1, last_bicg_conv[3] = {1, 1, 1}, last_bicg_restarts[3] = {0, 0, 0}, last_bicg_passes = 0;
+   double last_cg_res = 0.0, last_bicg_true[3] = {0, 0, 0};
    long long launches = 0;
    bool profile = false;
    std::map<std::string, cfdb::ProfEntry> prof;

@@ -706,6 +706,11 @@ int cfd_solver_main(const char* workdir, int scheme, int max_steps) {
    if (const char* v = getenv("CFD_BICG_MAXIT")) opt.bicg_maxit = atoi(v);
    if (const char* v = getenv("CFD_MAXACC_RULE")) opt.maxacc_rule = atoi(v);
    if (const char* v = getenv("CFD_DEVICE")) opt.device = atoi(v);
+   if (const char* v = getenv("CFD_EBE_SCATTER")) opt.ebe_scatter = atoi(v);
+   if (const char* v = getenv("CFD_DETERMINISTIC")) opt.deterministic = atoi(v);
+   if (const char* v = getenv("CFD_BICG_NO_HALFSTEP")) opt.bicg_no_halfstep = atoi(v);
+   if (const char* v = getenv("CFD_BICG_NO_VERIFY")) opt.bicg_no_verify = atoi(v);
+   if (const char* v = getenv("CFD_CG_VARIANT")) opt.cg_variant = atoi(v);
    int rc = cfd_solver_create_from_inp((dir + name + ".inp").c_str(), scheme, &opt, 1, &s);
    if (rc) return rc;
    const Mesh& m = s->mesh;

@@ -54,7 +54,8 @@ class cfd_options(C.Structure):
     _fields_ = [
         ("cg_tol", C.c_double), ("cg_maxit", C.c_int), ("cg_warm_start", C.c_int),
         ("bicg_tol", C.c_double), ("bicg_maxit", C.c_int), ("maxacc_rule", C.c_int),
-        ("device", C.c_int), ("ebe_scatter", C.c_int), ("cg_no_precond", C.c_int), ("reserved", C.c_int * 6), ("cuda_stream", C.c_void_p),
+        ("device", C.c_int), ("ebe_scatter", C.c_int), ("cg_no_precond", C.c_int), ("deterministic", C.c_int), ("bicg_no_halfstep", C.c_int), ("bicg_no_verify", C.c_int), ("cg_variant", C.c_int),
+        ("reserved", C.c_int * 2), ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -62,6 +63,8 @@ class cfd_step_report(C.Structure):
     _fields_ = [
         ("timeN", C.c_int), ("iter", C.c_int), ("cg_iterations", C.c_int), ("cg_solves", C.c_int),
         ("bicg_iterations", C.c_int * 3), ("maxAcc", C.c_double), ("steady", C.c_int), ("monitor", C.c_double * 4),
+        ("cg_converged", C.c_int), ("bicg_converged", C.c_int * 3), ("bicg_restarts", C.c_int * 3),
+        ("cg_residual", C.c_double), ("bicg_true_residual", C.c_double * 3),
     ]
 
 
@@ -105,6 +108,7 @@ def lib():
     L.cfd_printMonitorDataGPU.argtypes = [vp, _dp]
     L.cfd_last_cg_iterations.argtypes = [vp]
     L.cfd_last_bicgstab_iterations.argtypes = [vp, _ip]
+    L.cfd_last_krylov_status.argtypes = [vp, _ip, _dp, _ip, _dp, _ip]
     L.cfd_timeLoop.argtypes = [vp, C.c_int, C.c_int, C.POINTER(cfd_step_report), _ip]
     L.cfd_timeLoop_timed.argtypes = [vp, C.c_int, C.POINTER(cfd_step_report), _dp]
     L.cfd_timeStep_host.argtypes = [vp, _dp, _dp, C.POINTER(cfd_step_report), _dp]
@@ -292,19 +296,27 @@ class Context:
         _check(self.L.cfd_last_bicgstab_iterations(self.h, its))
         return list(its)
 
+    def krylov_status(self):
+        """Status of the most recent solves: dict(cg_converged, cg_residual, bicg_converged[3], bicg_true_residual[3], bicg_restarts[3])."""
+        cc, cr = C.c_int(), C.c_double()
+        bc, bt, br = (C.c_int * 3)(), (C.c_double * 3)(), (C.c_int * 3)()
+        _check(self.L.cfd_last_krylov_status(self.h, C.byref(cc), C.byref(cr), bc, bt, br))
+        return dict(cg_converged=bool(cc.value), cg_residual=cr.value, bicg_converged=[bool(v) for v in bc],
+                    bicg_true_residual=list(bt), bicg_restarts=list(br))
+
     def time_loop(self, nsteps, stop_on_steady=False):
         reps = (cfd_step_report * nsteps)()
         done = C.c_int()
         _check(self.L.cfd_timeLoop(self.h, nsteps, int(stop_on_steady), reps, C.byref(done)))
-        return [dict(timeN=r.timeN, iter=r.iter, cg_iterations=r.cg_iterations, cg_solves=r.cg_solves,
-                     bicg_iterations=list(r.bicg_iterations), maxAcc=r.maxAcc, steady=bool(r.steady),
-                     monitor=list(r.monitor)) for r in reps[:done.value]]
+        return [self._rep(r) for r in reps[:done.value]]
 
     @staticmethod
     def _rep(r):
         return dict(timeN=r.timeN, iter=r.iter, cg_iterations=r.cg_iterations, cg_solves=r.cg_solves,
                     bicg_iterations=list(r.bicg_iterations), maxAcc=r.maxAcc, steady=bool(r.steady),
-                    monitor=list(r.monitor))
+                    monitor=list(r.monitor), cg_converged=bool(r.cg_converged), cg_residual=r.cg_residual,
+                    bicg_converged=[bool(v) for v in r.bicg_converged], bicg_restarts=list(r.bicg_restarts),
+                    bicg_true_residual=list(r.bicg_true_residual))
 
     def time_loop_timed(self, nsteps):
         """nsteps time steps; returns (reports, device milliseconds by CUDA events on the launch stream)."""

@@ -111,13 +111,26 @@ typedef struct cfd_options {
                          per colour, plain stores, bitwise reproducible (the reference's scheme, BCH.cu:906-939) */
    int cg_no_precond; /* 0 (default) = Jacobi-preconditioned CG (BCH.cpp:4017, BCH.cu:437, GQ.cu:348); 1 = plain CG, what the
                          reference's implicit CPU build runs (its Jacobi line is commented out, GQ.cpp:4514) */
-   int reserved[6];
+   int deterministic; /* 0 (default) = the persistent Krylov kernels hand the tail of each SpMV sweep out through a shared counter
+                         (load balance; dot products then depend on which warp drew which slice: reproducible to rounding);
+                         1 = static slice assignment only: bitwise reproducible from run to run (with ebe_scatter = 1) */
+   int bicg_no_halfstep; /* 0 (default) = BiCGStab also tests |s| after the half step, like cusp::krylov::bicgstab (GQ.cu:404-414);
+                            1 = one test per iteration, where a PARALUTION-style solver (GQ.cpp:4190-4229) stops */
+   int bicg_no_verify;   /* 0 (default) = a momentum solve is accepted on its TRUE residual |b - A x| <= bicg_tol |b| and restarted from it
+                            otherwise (breakdowns included); 1 = trust the recurrence residual, as the reference's libraries do */
+   int cg_variant;    /* pressure CG recurrences: 0 (default) = classical two-reduction PCG, the reference's (BCH.cu:418-451);
+                         1 = Chronopoulos-Gear single-reduction form (same iterates in exact arithmetic, one grid-wide / cross-GPU
+                         reduction per iteration instead of two) */
+   int reserved[2];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 
 void cfd_default_options(cfd_options* opt);
 const char* cfd_last_error(void);
 const char* cfd_version(void);
+/* sizeof(cfd_problem), sizeof(cfd_options), sizeof(cfd_step_report) as this library was compiled: lets a binding written in
+ * another language (ctypes, cgo, JNI) check its mirror of the three structs at load time */
+void cfd_struct_sizes(int out[3]);
 
 /* replaces selectCUDAdevice()            BCH.cu:126-154 (no "last device" heuristic: explicit ordinal) */
 int cfd_selectCUDAdevice(int device);
@@ -181,6 +194,10 @@ int cfd_printMonitorDataGPU(cfd_ctx* ctx, double out[4]);
 /* Krylov statistics of the most recent step2 / step1 call */
 int cfd_last_cg_iterations(cfd_ctx* ctx);
 int cfd_last_bicgstab_iterations(cfd_ctx* ctx, int its[3]);
+/* status of the most recent solves: converged flags, relative residuals at exit (pressure: recurrence residual; momentum: true
+ * residual ||b - A x|| / ||b||, -1 if bicg_no_verify), restarts of each momentum system.  Any pointer may be NULL. */
+int cfd_last_krylov_status(cfd_ctx* ctx, int* cg_converged, double* cg_residual, int bicg_converged[3], double bicg_true_residual[3],
+                           int bicg_restarts[3]);
 
 /* ---- whole time steps (the fused fast path; same arithmetic as the seam sequence) ------------ */
 typedef struct cfd_step_report {
@@ -192,6 +209,12 @@ typedef struct cfd_step_report {
    double maxAcc;
    int steady;           /* maxAcc <= convergenceCriteria */
    double monitor[4];    /* u,v,w,p at monPoint */
+   /* Krylov status of the step (the reference's solvers report nothing: MKL failure -> print and return, BCH.cpp:4007) */
+   int cg_converged;     /* every pressure solve of the step met ||r|| <= cg_tol ||b|| (recurrence residual) within cg_maxit */
+   int bicg_converged[3];        /* implicit: momentum system d met the stopping rule on its TRUE residual (0 = stopped unconverged) */
+   int bicg_restarts[3];         /* restarts from the true residual (0 in the normal case) */
+   double cg_residual;           /* max over the step's pressure solves of ||r|| / ||b|| at exit */
+   double bicg_true_residual[3]; /* ||b - A x|| / ||b|| at exit (-1 when verification is off) */
 } cfd_step_report;
 /* runs `nsteps` passes of the time-loop body; `reports` may be NULL or hold nsteps entries.
  * Stops early (returning the number of steps done in *done) when a step reports steady state
@@ -274,7 +297,8 @@ int cfd_solver_read_restart(cfd_solver* s, const char* dat_path);
 /* the reference's main(): reads ./ProblemName.txt, runs to t_final, prints the monitor table,
  * writes <name>.dat.  max_steps > 0 bounds the run.  Solver settings: cfd_default_options (= the reference's GPU builds),
  * overridden by the environment variables CFD_CG_TOL, CFD_CG_MAXIT, CFD_CG_WARM_START, CFD_CG_NO_PRECOND, CFD_BICG_TOL,
- * CFD_BICG_MAXIT, CFD_MAXACC_RULE, CFD_DEVICE (same meaning as the cfd_options fields).
+ * CFD_BICG_MAXIT, CFD_MAXACC_RULE, CFD_DEVICE, CFD_EBE_SCATTER, CFD_DETERMINISTIC, CFD_BICG_NO_HALFSTEP, CFD_BICG_NO_VERIFY,
+ * CFD_CG_VARIANT (same meaning as the cfd_options fields).
  * csrc/solver_main.cpp wraps this into the executables bin/solverGPU_explicit and bin/solverGPU_implicit, which -- like the
  * reference's solverGPU (makeBCH:16-18) -- take no arguments and work on the current directory. */
 int cfd_solver_main(const char* workdir, int scheme, int max_steps);

@@ -71,6 +71,8 @@ void initializeAndAllocateGPU() {   // GQ.cu:166-295
    if (const char* v = getenv("CFD_BICG_TOL")) o.bicg_tol = atof(v);
    if (const char* v = getenv("CFD_BICG_MAXIT")) o.bicg_maxit = atoi(v);
    if (const char* v = getenv("CFD_EBE_SCATTER")) o.ebe_scatter = atoi(v);
+   if (const char* v = getenv("CFD_DETERMINISTIC")) o.deterministic = atoi(v);
+   if (const char* v = getenv("CFD_BICG_NO_HALFSTEP")) o.bicg_no_halfstep = atoi(v);
    die(cfd_initializeAndAllocateGPU(&p, &o, &ctx));
    // the five buffers timeLoop() copies between (GQ.cpp:3366-3368) and reads back (GQ.cpp:3397-3398, 3407-3408) ...
    Uk_d = dev("Uk"); Uk_prev_d = dev("Uk_prev"); Pk_d = dev("Pk"); Pk_prev_d = dev("Pk_prev"); Pk_prevprev_d = dev("Pk_prevprev");

@@ -72,6 +72,7 @@ struct Options {
    int cg_precond = 1;    // 0 = implicit CPU build (GQ.cpp:4514 Jacobi line commented out)
    double bicg_tol = 1e-6;
    int bicg_maxit = 1000;
+   int bicg_halfstep = 1;   // 1 = also test |s| after the half step (CUSP, GQ.cu:404-414); 0 = once per iteration (PARALUTION, GQ.cpp:4190-4229)
    int maxacc_rule = 0;   // 0: max|dU|/dt (BCH.cpp:3053); 1: max|dU| (BCH.cu:107-117)
 };
 
@@ -778,9 +779,9 @@ int bicgstab(Orc& o, const double* A, const double* b, double* x) {
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < n; i++) s[i] = r[i] - alpha * AMp[i];
       double snorm = std::sqrt(dot(s.data(), s.data(), n));
-      if (snorm <= o.opt.bicg_tol * bnorm) {
+      if (o.opt.bicg_halfstep && snorm <= o.opt.bicg_tol * bnorm) {
+         // cusp::krylov::bicgstab leaves here BEFORE `++monitor`: the half step is not counted as an iteration
          for (int i = 0; i < n; i++) x[i] += alpha * Mp_[i];
-         it++;
          break;
       }
 #pragma omp parallel for schedule(static)
@@ -1169,6 +1170,7 @@ int orc_set(void* h, const char* name, double v) {
    if (n == "cg_tol") o.opt.cg_tol = v; else if (n == "cg_maxit") o.opt.cg_maxit = (int)v;
    else if (n == "cg_warm") o.opt.cg_warm = (int)v; else if (n == "cg_precond") o.opt.cg_precond = (int)v;
    else if (n == "bicg_tol") o.opt.bicg_tol = v; else if (n == "bicg_maxit") o.opt.bicg_maxit = (int)v;
+   else if (n == "bicg_halfstep") o.opt.bicg_halfstep = (int)v;
    else if (n == "maxacc_rule") o.opt.maxacc_rule = (int)v; else if (n == "maxIter") o.maxIter = (int)v;
    else if (n == "tolerance") o.tolerance = v;
    else return -1;

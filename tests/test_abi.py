@@ -32,8 +32,10 @@ def test_struct_layouts_match_header():
     o = fracstep.options()
     assert o.cg_tol == 1e-6 and o.cg_maxit == 1000 and o.bicg_tol == 1e-6 and o.bicg_maxit == 1000
     assert o.cg_warm_start == 0 and o.maxacc_rule == 0 and o.device == -1 and not o.cuda_stream
-    assert ctypes.sizeof(fracstep.cfd_options) == 80
-    assert ctypes.sizeof(fracstep.cfd_step_report) == 80
+    sz = (ctypes.c_int * 3)()
+    fracstep.lib().cfd_struct_sizes(sz)      # the sizes the C side was compiled with
+    assert [ctypes.sizeof(fracstep.cfd_problem), ctypes.sizeof(fracstep.cfd_options), ctypes.sizeof(fracstep.cfd_step_report)] == list(sz)
+    assert o.deterministic == 0 and o.bicg_no_halfstep == 0 and o.bicg_no_verify == 0 and o.cg_variant == 0
 
 
 def test_argument_errors_without_gpu():

@@ -111,29 +111,39 @@ def test_time_loop_parity(mesh, name, scheme, setting):
     import orc
     kw = TIGHT if setting == "tight" else {}
     path = mesh(name, **CASES[name])
-    o = orc.Oracle(path, scheme, **kw)
-    c = fracstep.Context(fracstep.Problem(o, scheme), fracstep.options(**kw) if kw else None)
+    # tight: one oracle thread and a bitwise reproducible product run (coloured scatter, static slice assignment)
+    o = orc.Oracle(path, scheme, 1 if kw else 0, **kw)
+    c = fracstep.Context(fracstep.Problem(o, scheme), fracstep.options(ebe_scatter=1, deterministic=1, **kw) if kw else None)
     n = 5
     o.run(n)
     reps = c.time_loop(n)
     U, P = c.fields()
     q2_implicit_ref = scheme == "implicit" and setting == "reference" and CASES[name].get("NENv", 27) == 27
-    bar = 5e-3 if q2_implicit_ref else 1e-6
+    # Q2/Q1 implicit at the reference tolerance (1e-6 on a matrix with cond ~ 1e4): the measured floor of the comparison, not a
+    # parity bar -- see tests/test_reference_pin.py::bars and profiles/r02_asis_spread.txt; the 1e-6 bar is asserted at "tight"
+    bar, barP = (3e-4, 2e-3) if q2_implicit_ref else (1e-6, 1e-6)
     assert rel(U, o.U) <= bar, rel(U, o.U)
     assert rel_free(U, o.U, o) <= 20 * bar, rel_free(U, o.U, o)   # interior field is ~1e-3 of the lid speed this early
-    assert rel(P, o.P) <= bar, rel(P, o.P)
+    assert rel(P, o.P) <= barP, rel(P, o.P)
+    assert all(r["cg_converged"] for r in reps)
+    if scheme == "implicit":
+        tol = kw.get("bicg_tol", 1e-6)
+        assert all(v <= (tol if tol > 1e-9 else 10 * tol) for r in reps for v in r["bicg_true_residual"]), [r["bicg_true_residual"] for r in reps]
+        if not kw:
+            assert all(all(r["bicg_converged"]) for r in reps)
     ocg = o.arr("cgIters")
     if scheme == "explicit":
         assert [r["iter"] for r in reps] == list(o.arr("innerIters"))
         assert abs(sum(r["cg_iterations"] for r in reps) - ocg.sum()) <= 2 * len(ocg)
     else:
-        slack = 8 if q2_implicit_ref else 2
+        slack = 4 if q2_implicit_ref else 2
         for r, k in zip(reps, ocg):
             assert abs(r["cg_iterations"] - k) <= slack
         ob = o.arr("bicgIters").reshape(-1, 3)
         for r, k in zip(reps, ob):
-            # BiCGStab iteration counts on these systems move with rounding: loose bound
-            assert all(abs(a - b) <= max(20, 0.6 * b) and a < 1000 for a, b in zip(r["bicg_iterations"], k)), (r["bicg_iterations"], k)
+            # BiCGStab iteration counts on these systems move with rounding (the oracle's own counts move by +-10 % with its
+            # thread count, profiles/r02_asis_spread.txt): a sanity bound, not a parity claim
+            assert all(abs(a - b) <= max(12, 0.35 * b) and a < 1000 for a, b in zip(r["bicg_iterations"], k)), (r["bicg_iterations"], k)
     mon = np.array(reps[-1]["monitor"])
     mp, NN = o.i("monPoint"), o.i("NN")
     ref = np.array([o.U[mp], o.U[NN + mp], o.U[2 * NN + mp], o.P[mp]])
@@ -233,6 +243,74 @@ def test_ne27000_full_size(mesh, scheme, steps):
         assert abs(reps[0]["cg_iterations"] - int(o.arr("cgIters")[0])) <= 2
 
 
+def test_momentum_solves_meet_their_true_residual(mesh):
+    """|b - A x| <= tol |b| for the three momentum systems, recomputed on the host with the ORACLE's assembled A (same state, so the
+    same matrix to rounding) from the right-hand sides and solutions the product holds -- and the status the product reports."""
+    import scipy.sparse as sp
+    import fracstep
+    o, c = make_pair(mesh, "q2_c4", "implicit")
+    o.run(2)
+    c.time_loop(2)
+    for nm in ("Uk_prev", "Pk_prev", "Pk_prevprev"):
+        c.upload(nm, o.arr(nm))
+    o.phase("gq_step1")
+    c.call("gq_step1GPU")
+    NN = o.i("NN")
+    A = sp.csr_matrix((o.arr("sparseAvalue"), o.arr("sparseMcol"), o.arr("sparseMrowStarts")), shape=(NN, NN))
+    b, x = c.download("R1"), c.download("Uk")
+    st = c.krylov_status()
+    for d in range(3):
+        bd, xd = b[d * NN:(d + 1) * NN], x[d * NN:(d + 1) * NN]
+        true = np.linalg.norm(bd - A @ xd) / np.linalg.norm(bd)
+        assert true <= 1.0001e-6, (d, true)
+        assert st["bicg_converged"][d] and abs(st["bicg_true_residual"][d] - true) <= 1e-9 and st["bicg_restarts"][d] == 0
+    # an unattainable tolerance is REPORTED, not silently accepted: 1e-15 cannot be met in double precision on this matrix
+    c2 = fracstep.Context(fracstep.Problem(o, "implicit"), fracstep.options(bicg_tol=1e-15, bicg_maxit=3000))
+    for nm in ("Uk_prev", "Pk_prev", "Pk_prevprev"):
+        c2.upload(nm, o.arr(nm))
+    c2.call("gq_step1GPU")
+    st = c2.krylov_status()
+    assert not any(st["bicg_converged"]) and all(0 < v < 1e-10 for v in st["bicg_true_residual"]), st
+    x2 = c2.download("Uk")
+    assert np.isfinite(x2).all() and rel(x2, x) < 1e-4
+
+
+HEADLINE = {
+    # BASELINE.json configs[3]/[4] element and scheme (Q1/Q1, implicit) at 128^3 -- the largest mesh the CPU oracle steps in seconds
+    "q1_128_implicit": dict(n=128, NENv=8, scheme="implicit", steps=2),
+    # configs[3] "EBE" element (Q2/Q1), explicit, 64^3 = 2.1 M velocity nodes
+    "q2_64_explicit": dict(n=64, NENv=27, scheme="explicit", steps=1),
+}
+
+
+@pytest.mark.parametrize("name", list(HEADLINE))
+def test_headline_config_fields_against_oracle(mesh, name):
+    """Fields of the benchmark configurations themselves, not only of small meshes: rel-L2 <= 1e-6, CG counts +-2.
+    (Q1/Q1 is oracle-only parity by construction: the reference's NENv == 8 shape-function branch is commented out,
+    blascoCodinaHuerta.cpp:2303-2305, so the reference program cannot run these meshes.)"""
+    import fracstep
+    import orc
+    h = HEADLINE[name]
+    path = mesh("headline_" + name, n=h["n"], NENv=h["NENv"], full_precision=True)
+    o = orc.Oracle(path, h["scheme"])
+    s = fracstep.Solver(path, h["scheme"])
+    o.run(h["steps"])
+    reps = s.ctx.time_loop(h["steps"])
+    U, P = s.ctx.fields()
+    assert rel(U, o.U) <= 1e-6, rel(U, o.U)
+    # pressure: both sides stop CG at 1e-6 |b|; the field error is that times cond(Z) (oracle-vs-oracle: test_oracle.py)
+    assert rel(P, o.P) <= (1e-6 if h["scheme"] == "implicit" else 1e-5), rel(P, o.P)
+    ocg = list(o.arr("cgIters"))
+    if h["scheme"] == "explicit":
+        assert [r["iter"] for r in reps] == list(o.arr("innerIters"))
+        assert abs(sum(r["cg_iterations"] for r in reps) - sum(ocg)) <= 2 * len(ocg)
+    else:
+        assert all(abs(r["cg_iterations"] - k) <= 2 for r, k in zip(reps, ocg)), ([r["cg_iterations"] for r in reps], ocg)
+        assert all(all(r["bicg_converged"]) and max(r["bicg_true_residual"]) <= 1e-6 for r in reps)
+    s.close()
+    o.close()
+
+
 def test_large_mesh_properties():
     """Size-independent properties on a mesh the oracle would take minutes for (64^3 Q1/Q1, implicit):
     Dirichlet values are reproduced to the solver tolerance, the pressure solve meets its stopping rule, the velocity
@@ -292,13 +370,14 @@ def test_channel_standin_implicit(mesh):
     import orc
     path = mesh("chan_gpu", kind="channel", nx=12, ny=8, nz=8, full_precision=True)
     opt = dict(cg_tol=1e-12, bicg_tol=1e-9, cg_maxit=5000, bicg_maxit=5000)
-    o = orc.Oracle(path, "implicit", **opt)
+    o = orc.Oracle(path, "implicit", 1, **opt)
     s = fracstep.Solver(path, "implicit", opts=fracstep.options(**opt))
     o.run(3)
     reps = s.ctx.time_loop(3)
     U, P = s.ctx.fields()
     assert np.isfinite(U).all() and np.isfinite(P).all() and np.isfinite(o.U).all()
     assert all(max(r["bicg_iterations"]) < 5000 for r in reps) and o.arr("bicgIters").max() < 5000
+    assert all(all(r["bicg_converged"]) and max(r["bicg_true_residual"]) <= 1e-9 for r in reps), reps
     assert rel(U, o.U) <= 1e-6 and rel_free(U, o.U, o) <= 2e-5 and rel(P, o.P) <= 1e-5
 
 

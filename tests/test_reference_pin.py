@@ -41,13 +41,15 @@ def settings(meta):
     env = meta["env"]
     if env:   # tight: REF_SHIM_* told the stand-ins what to do
         ct, bt = float(env["REF_SHIM_CG_TOL"]), float(env["REF_SHIM_BICG_TOL"])
-        # GPU side: the reproducible (coloured) element scatter, so that -- these meshes being too small for the dynamic slice
-        # scheduling -- the run is bitwise repeatable.  BiCGStab sits on the rounding floor of the under-integrated Q2 matrix
-        # for hundreds of iterations at 1e-12; with atomics the path it takes there changes from run to run and it
-        # occasionally stagnates (1 run in ~5 on the Re = 1000 fixture); 1e-10 instead moves the fields by ~1e-6 (measured).
-        return dict(cg_tol=ct, bicg_tol=bt, cg_precond=1), dict(cg_tol=ct, bicg_tol=bt, ebe_scatter=1)
-    if meta["scheme"] == "implicit":   # GQ.cpp:4510-4515: no Jacobi, dpar[0] = 1e-6 on SQUARED norms
-        return dict(cg_precond=0, cg_tol=1e-3), dict(cg_no_precond=1, cg_tol=1e-3)
+        # GPU side: coloured element scatter + static slice assignment = a bitwise repeatable run.  BiCGStab sits on the rounding
+        # floor of the under-integrated Q2 matrix for hundreds of iterations at 1e-12 and the path it takes there moves with every
+        # rounding change; what makes the comparison robust is that the product accepts a momentum solve only on its TRUE residual
+        # (restart otherwise) -- test_tight_fixture_is_robust_to_rounding_paths repeats the run with the atomic scatter.
+        return dict(cg_tol=ct, bicg_tol=bt, cg_precond=1), dict(cg_tol=ct, bicg_tol=bt, ebe_scatter=1, deterministic=1)
+    if meta["scheme"] == "implicit":
+        # GQ.cpp:4510-4515: no Jacobi, dpar[0] = 1e-6 on SQUARED norms; BiCGStab: one residual test per iteration, which is where the
+        # PARALUTION-style solver of the reference's CPU build stops (GQ.cpp:4190-4229)
+        return dict(cg_precond=0, cg_tol=1e-3, bicg_halfstep=0), dict(cg_no_precond=1, cg_tol=1e-3, bicg_no_halfstep=1)
     return {}, {}
 
 
@@ -73,7 +75,15 @@ def bars(name, meta):
         return 1e-10, 1e-10, 0
     if meta["env"]:   # forced to 1e-12: the last iterations sit on the rounding floor, the count there is noisy (the +-2 bar
         return 1e-7, 1e-7, 5   # of BASELINE.json is for the reference tolerance and is applied to the as-is fixtures)
-    return (5e-3, 5e-3, None) if "ne27000" in name else (1e-3, 1e-3, 2)
+    # Implicit at the reference's own tolerances (BiCGStab 1e-6, plain CG 1e-3): NOT a parity bar but the measured floor of the
+    # comparison.  Both sides solve A u = b to |b - A u| <= 1e-6 |b| with cond(A) ~ 1e4 (under-integrated Q2 mass matrix,
+    # GQ.cpp:3490-3500), so two correct runs may differ by ~1e-6 * cond in the fields.  Measured (scripts/asis_spread.py,
+    # profiles/r02_asis_spread.txt): the ORACLE against itself with 1 vs 8 threads (= another summation order of its dot
+    # products) moves by 2.4e-5 / 2.4e-4 (U / P) on the 4^3 fixture and 3.8e-5 / 2.8e-5 on the shipped mesh; oracle vs reference
+    # 1.6e-5..8.6e-5 / 1.4e-4..5.8e-4 and 1.6e-5..3.8e-5 / 4.7e-7..2.8e-5.  Bars = 3x the largest measured value; the arithmetic
+    # inside PARALUTION's BiCGStab is a stand-in (oracle/shim), so this comparison is "parity unpinned" by construction and the
+    # 1e-6 parity claim rests on the tight fixtures above.
+    return (1.2e-4, 1e-4, 6) if "ne27000" in name else (3e-4, 2e-3, 2)   # (plain CG stopped at 1e-3: its count moves by up to 5 of ~150)
 
 
 def inp_for(mesh, name, meta):
@@ -236,12 +246,40 @@ def test_cuda_path_reproduces_reference_run(mesh, name):
     bu, bp, dcg = bars(name, meta)
     bu, bp = max(bu, 1e-6), max(bp, 1e-6)
     assert eu <= bu and ep <= bp, (name, eu, ep)
+    assert all(r["cg_converged"] for r in reps)
     if meta["scheme"] == "explicit":
         assert [r["iter"] for r in reps] == [int(v) for v in g["monitor"][:, 1]]
         assert abs(sum(r["cg_iterations"] for r in reps) - int(g["cg"][:, 0].sum())) <= 2 * len(g["cg"])
-    elif dcg is not None:
+    else:
         assert all(abs(r["cg_iterations"] - k) <= max(dcg, 2) for r, k in zip(reps, g["cg"][:, 0]))
+        # every momentum solve is accepted on its true residual |b - A x| / |b|: at the reference tolerance that is the stopping
+        # rule itself; at 1e-12 the attainable accuracy of this matrix is about 1e-12, a decade is allowed
+        tol = popt.get("bicg_tol", 1e-6)
+        assert all(v <= (tol if tol > 1e-9 else 10 * tol) for r in reps for v in r["bicg_true_residual"]), [r["bicg_true_residual"] for r in reps]
+        if tol > 1e-9:
+            assert all(all(r["bicg_converged"]) for r in reps)
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_gq_cav6c_tight", "ref_gq_chan644_tight"])
+def test_tight_fixture_is_robust_to_rounding_paths(mesh, name):
+    """Round 1's failure mode: the same fixture gave 3e-8 on one box and 6.5e-5 on another.  Ten runs in a row with the ATOMIC
+    element scatter and the dynamically scheduled sweeps (every run rounds differently, so BiCGStab takes another path along the
+    rounding floor each time) must all meet the 1e-6 bar, each solve with a verified true residual."""
+    import fracstep
+    g, meta = load(name)
+    popt = dict(settings(meta)[1], ebe_scatter=0, deterministic=0)
+    worst = (0.0, 0.0, 0.0)
+    for _ in range(10):
+        s = fracstep.Solver(inp_for(mesh, name, meta), meta["scheme"], opts=fracstep.options(**popt))
+        reps = s.ctx.time_loop(meta["steps"])
+        U, P = s.ctx.fields()
+        eu, ep = errors(U, P, g, meta, s.i("NN"))
+        tr = max(v for r in reps for v in r["bicg_true_residual"])
+        worst = (max(worst[0], eu), max(worst[1], ep), max(worst[2], tr))
+        s.close()
+    assert worst[0] <= 1e-6 and worst[1] <= 1e-6 and worst[2] <= 1e-11, worst
 
 
 @pytest.mark.gpu

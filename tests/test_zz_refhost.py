@@ -7,13 +7,7 @@ preprocessing, step0(), timeLoop() with its own cudaMemcpy rotations on the `*_d
 
 CPU part: the programs exist (where the reference tree was mounted at build time) and stop with an error code without a GPU.
 GPU part: they must write the .dat the reference's CPU build wrote for the same input deck (tests/golden/ref_*.npz).
-The file sorts last on purpose.  The programs were built after round 1's GPU budget was all but spent; the last 20 seconds
-went into ONE run of each (profiles/r01_refhost_*.log): both ran to "The program is terminated successfully", the
-explicit monitor table (inner iterations per step, maxAcc) equals the reference CPU build's line by line, the implicit one
-agrees with the oracle at the GPU build's settings to the level two BiCGStab implementations agree on this matrix.  The
-.dat files of that run held the INITIAL fields: like the original, printMonitorDataGPU has to bring the whole fields back
-every step, which the shims now do -- that version has not run on hardware yet, hence xfail(strict=False): an XPASS in
-the log is the evidence, a failure does not mask the validated suites."""
+The file sorts last on purpose (the programs are the slowest to start)."""
 import os
 import shutil
 import subprocess
@@ -109,9 +103,9 @@ def test_reference_step0_arrays_on_the_shipped_mesh(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="shim revision after round 1's GPU minutes were spent: first hardware run is this one")
 @pytest.mark.parametrize("name,env", [("ref_bch_cav4", {"CFDB200_CPU_SEMANTICS": "1"}), ("ref_bch_cav6c", {"CFDB200_CPU_SEMANTICS": "1"}),
-                                      ("ref_gq_cav4_tight", {"CFD_CG_TOL": "1e-12", "CFD_BICG_TOL": "1e-12", "CFD_EBE_SCATTER": "1"})])
+                                      ("ref_gq_cav4_tight", {"CFD_CG_TOL": "1e-12", "CFD_BICG_TOL": "1e-12", "CFD_EBE_SCATTER": "1",
+                                                             "CFD_DETERMINISTIC": "1"})])
 def test_reference_host_program_on_the_gpu_library(name, env, tmp_path):
     g, meta = load(name)
     exe = EXE[meta["scheme"]]
