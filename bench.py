@@ -35,7 +35,7 @@ WORKLOADS = {
     "channel_48x32x32_implicit": dict(n=48, ny=32, nz=32, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3, inp=True, channel=True),
 }
 DEFAULT_WORKLOAD = "cavity256_q1_implicit"
-CPU_SAMPLE_N = 64   # mesh edge of the bounded CPU sample for workloads larger than this
+CPU_SAMPLE_N = 128   # mesh edge of the bounded CPU sample for Q1/Q1 workloads larger than this (the oracle steps 128^3 in seconds)
 
 
 def sizes(w):
@@ -140,8 +140,10 @@ def run_reference_binary(w, steps, warmup, n):
         make_inp(w, os.path.join(d, "case.inp"), n, t_final=(total - 0.5) * w["dt"], converge=-1e30)
         with open(os.path.join(d, "ProblemName.txt"), "w") as f:
             f.write("case\n")
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)   # the program sets its own 8 threads (BCH.cpp:85-86); the stand-ins' loops follow the same runtime
         out = subprocess.run([REF_BIN[w["scheme"]]], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, stdin=subprocess.DEVNULL,
-                             text=True, check=True).stdout
+                             text=True, check=True, env=env).stdout
     ncol, tcol = (9, 7) if w["scheme"] == "explicit" else (8, 6)
     rows = [ln.split() for ln in out.splitlines()]
     rows = [r for r in rows if len(r) == ncol and r[0].isdigit()]
@@ -150,11 +152,21 @@ def run_reference_binary(w, steps, warmup, n):
     return sum(float(r[tcol]) for r in rows[warmup:]) / steps
 
 
+def host_threads():
+    """Cores this process may use.  Never inherited from OMP_NUM_THREADS: torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    workers, which in round 1 made the reference arm of the N > 1 runs a one-core measurement."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_oracle(w, steps, warmup, n, threads=0):
-    """The CPU oracle (line-faithful restatement of the reference's CPU path; the reference itself does not
-    compile: MKL/CSparse/Paralution absent) on an n^3 mesh of the workload's kind.  Returns seconds per step."""
+    """The CPU oracle (line-faithful restatement of the reference's CPU path) on an n^3 mesh of the workload's kind, on `threads`
+    host threads (0 = every core of the box, set explicitly).  Returns seconds per step."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
+    threads = threads or host_threads()
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "sample.inp")
         make_inp(w, path, n)
@@ -186,8 +198,9 @@ def cpu_sample(w, steps, warmup):
                      ("%d^3" % n_s) if not w.get("channel") else "%d/%d-scale channel" % (n_s, w["n"]), w["scheme"], steps, warmup))
         if n_s != w["n"]:
             sample += "; steps/s scaled by element count %d^3/%d^3 to the workload mesh" % (n_s, w["n"])
-        return dict(value=scale / sec, unit="steps/s", cores=min(8, os.cpu_count() or 8), kind="reference", sample=sample,
-                    sample_steps_per_s=1.0 / sec)
+        return dict(value=scale / sec, unit="steps/s", cores=min(8, host_threads()), kind="reference", sample=sample,
+                    sample_steps_per_s=1.0 / sec, extrapolated=n_s != w["n"], sample_mesh=n_s, workload_mesh=w["n"],
+                    extrapolation=None if n_s == w["n"] else "steps/s x (sample NE / workload NE); Krylov iteration growth with n ignored, which favours the CPU")
     n_s = min(w["n"], CPU_SAMPLE_N)
     sec, info = run_oracle(w, steps, warmup, n_s)
     scale = (n_s / float(w["n"])) ** 3   # per-step work ~ elements (Krylov iteration growth with n ignored: favours the CPU)
@@ -199,7 +212,9 @@ def cpu_sample(w, steps, warmup):
             "branch is commented out, blascoCodinaHuerta.cpp:2303-2305), so this workload uses the oracle port, which reproduces the reference "
             "program's output on Q2/Q1 inputs to 1e-12 (tests/test_reference_pin.py)") if w["NENv"] == 8 else "oracle/_ref not built: oracle port"
     return dict(value=scale / sec, unit="steps/s", cores=info["threads"], kind="port", sample=sample,
-                sample_steps_per_s=1.0 / sec, cg_gdof_iter_per_s=info["cg_gdof_iter_per_s"], note=note)
+                sample_steps_per_s=1.0 / sec, cg_gdof_iter_per_s=info["cg_gdof_iter_per_s"], note=note,
+                extrapolated=n_s != w["n"], sample_mesh=n_s, workload_mesh=w["n"], sample_cg_iterations_per_solve=info["cg_iterations_per_solve"],
+                extrapolation=None if n_s == w["n"] else "steps/s x (sample NE / workload NE); Krylov iteration growth with n ignored, which favours the CPU")
 
 
 def main():
@@ -229,6 +244,11 @@ def main():
                     ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic", impl="reference", config=config, cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        if cb.get("extrapolated"):
+            # machine-readable: `value` / `ms_per_step` are for the workload mesh, the process only ran the sample
+            line["consistency"] = dict(fits_in_driver_run=False, same_config=False, measured_ms_per_step_on_sample=1e3 / cb["sample_steps_per_s"],
+                                       why="the CPU path cannot step the %d^3 workload within minutes: timed on a %d^3 sample of the same mesh kind and scaled by "
+                                           "element count (CPU-favouring)" % (cb["workload_mesh"], cb["sample_mesh"]))
         print(json.dumps(line))
         return 0
 
@@ -273,6 +293,9 @@ def main():
     # ---- warm-up, then the timed region (state resident in HBM)
     if a.warmup:
         c.time_loop(a.warmup)
+    # the state the timed region starts from, kept on the host so that the end-to-end leg repeats the SAME K steps
+    state_names = ("Un", "Pn", "Unp1_prev") if w["scheme"] == "explicit" else ("Uk_prev", "Pk_prev", "Pk_prevprev")
+    state0 = {nm: c.download(nm) for nm in state_names}
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -290,20 +313,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
-    # ---- end to end: host buffers in, host buffers out, every step
-    U, P = c.fields()
-    Uh = torch.from_numpy(U).pin_memory().numpy()
-    Ph = torch.from_numpy(P).pin_memory().numpy()
+    def global_norms():
+        """||U||_2, ||P||_2 over the whole mesh (owned entries of every rank): identical numbers at N = 1, 2, 4, 8 mean identical fields."""
+        _, Uo, _, Po = s.owned_fields()
+        v = torch.tensor([float((Uo * Uo).sum()), float((Po * Po).sum())], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(v)
+        return float(v[0].sqrt().item()), float(v[1].sqrt().item())
+
+    normU, normP = global_norms()
+
+    # ---- end to end: the same K steps again, from the same state, host buffers in / host buffers out every step
+    for nm in state_names:
+        c.upload(nm, state0[nm])
+    Uh = torch.from_numpy(state0[state_names[0]].copy()).pin_memory().numpy()
+    Ph = torch.from_numpy(state0[state_names[1]].copy()).pin_memory().numpy()
     barrier()
     e2e_ms = 0.0
+    e2e_reps = []
     for _ in range(a.steps):
-        _, m1 = c.time_step_host(Uh, Ph)
+        r1, m1 = c.time_step_host(Uh, Ph)
+        e2e_reps.append(r1)
         e2e_ms += m1
     barrier()
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    normU2, normP2 = global_norms()
 
     if rank != 0:
         return 0
@@ -312,42 +349,47 @@ def main():
     total_ms = sum(p["ms"] for k, p in prof.items() if k != "halo")   # halo swaps inside Krylov solves are already in pcg / bicgstab
     dom = max((k for k in prof if k != "halo"), key=lambda k: prof[k]["ms"])
     d = prof[dom]
-    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    sec = d["ms"] * 1e-3
+    alg = d["bytes"] / sec / 1e9 if sec > 0 else 0.0
+    lay = d["layout_bytes"] / sec / 1e9 if sec > 0 else 0.0
     cg_its = sum(r["cg_iterations"] for r in reps)
-    cg_its_local = cg_its
     traffic = ncu_traffic(a.workload, dom)
-    # the same event time expressed in the bytes the device layout actually stores (padding in, compressed indices out)
-    layout = None
-    if dom == "pcg" and d["ms"] > 0:
-        zs = c.matrix_stats("Z")
-        n_loc = c.NNp
-        per_it = 8.0 * zs["stored_values"] + 4.0 * zs["stored_indices"] + 4.0 * (n_loc + 1) + 104.0 * n_loc
-        layout = dict(gbs=round(per_it * cg_its_local / (d["ms"] * 1e-3) / 1e9, 1), matrix=zs)
     cg_ms = prof["pcg"]["ms"]
-    kernels = {k: dict(ms=round(v["ms"], 3), launches=v["launches"], gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
+    kernels = {k: dict(ms=round(v["ms"], 3), launches=v["launches"],
+                       gbs=round(v["layout_bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
+                       gbs_algorithmic=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
                        share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
-    config.update(parallelism="1 GPU" if world == 1 else "%d element blocks (z-slabs), one per GPU; NCCL halo swap + allreduce" % world,
-                  l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["bytes"] for v in prof.values()) / a.steps / 1e9),
+    config.update(parallelism="1 GPU" if world == 1 else "%d element blocks (z-slabs), one per GPU; peer-memory Krylov kernels + NCCL halo swap / allreduce" % world,
+                  l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["layout_bytes"] for v in prof.values()) / a.steps / 1e9),
                   setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps),
                   bicgstab_iterations_last_step=reps[-1]["bicg_iterations"])
+    krylov_ok = all(r["cg_converged"] for r in reps) and all(all(r["bicg_converged"]) for r in reps)
     line = dict(metric="time steps/s", value=n_rep * a.steps / (ms_max * 1e-3), unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=ms_max / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 config=config, clocks=clk,
-                e2e=dict(value=n_rep * a.steps / (e2e_ms * 1e-3), unit="steps/s", h2d_bytes_per_step=int(8 * (U.size + P.size)),
-                         d2h_bytes_per_step=int(8 * (U.size + P.size)), note="per rank: its block's U,P (owned + ghost) each step"),
+                e2e=dict(value=n_rep * a.steps / (e2e_ms * 1e-3), unit="steps/s", h2d_bytes_per_step=int(8 * (Uh.size + Ph.size)),
+                         d2h_bytes_per_step=int(8 * (Uh.size + Ph.size)),
+                         note="per rank: its block's U,P (owned + ghost) each step; the same K steps as `value`, restarted from the same saved state",
+                         fields_vs_device_run=dict(normU_rel_diff=abs(normU2 / normU - 1.0) if normU else 0.0,
+                                                   normP_rel_diff=abs(normP2 / normP - 1.0) if normP else 0.0)),
                 gpu_launches=int(launches),
-                roofline=dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
-                              frac_of_nominal_8000=round(achieved / 8000.0, 4),   # both the measured-copy and the nominal peak
+                # fields after the timed steps: the same numbers at every N = the partitioned runs compute the same thing
+                fields=dict(normU=normU, normP=normP, monitor=reps[-1]["monitor"], maxAcc=reps[-1]["maxAcc"],
+                            cg_iterations=[r["cg_iterations"] for r in reps], krylov_converged=krylov_ok,
+                            bicg_true_residual_max=max([v for r in reps for v in r["bicg_true_residual"]] + [-1.0])),
+                roofline=dict(bound="hbm", kernel=dom, achieved=round(lay, 1), peak=peak, unit="GB/s", frac=round(lay / peak, 4),
+                              frac_of_nominal_8000=round(lay / 8000.0, 4),   # both the measured-copy and the nominal peak
+                              achieved_algorithmic=round(alg, 1), frac_algorithmic=round(alg / peak, 4),
                               traffic=traffic, peak_source=peak_src, share_of_step=round(d["ms"] / total_ms, 4) if total_ms else None,
-                              note="achieved = ALGORITHMIC bytes (CSR model: 12 B per non-zero + vectors) / event time; slices with a shared "
-                                   "column-offset pattern store their indices once (lossless), so on structured meshes the kernel moves fewer DRAM "
-                                   "bytes than the model and frac can exceed 1; `traffic` is the DRAM byte count ncu measured for one launch; "
-                                   "`layout` re-expresses the same time in the bytes the device layout stores",
-                              layout=layout),
+                              note="achieved = bytes the kernel has to move for its launches in the layout it stores (Sell: zero padding in, per-slice "
+                                   "compressed column indices counted once; vectors as in the algorithmic model) / CUDA-event time of those launches: "
+                                   "cannot exceed the bandwidth.  achieved_algorithmic = the CSR model of SURVEY.md 8(d) (12 B per non-zero + vectors) over "
+                                   "the same time: what a CSR kernel would have had to sustain, > 1 of peak where the compression pays.  traffic = ncu "
+                                   "dram__bytes per launch from the committed capture (profiles/traffic.json)"),
                 cg_gdof_iter_per_s=(sz["NNp"] * cg_its / (cg_ms * 1e-3) / 1e9) if cg_ms > 0 else None,
                 kernels=kernels)
     if world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_sample(w, 2, 1)
+        line["cpu_baseline"] = cpu_sample(w, 3, 1)
     print(json.dumps(line))
     s.close()
     if dist is not None:

@@ -1302,17 +1302,18 @@ namespace {
 struct ProfScope {
    cfd_ctx* c;
    int idx = -1;
-   ProfScope(cfd_ctx* c_, const char* n, double b) : c(c_) {
+   ProfScope(cfd_ctx* c_, const char* n, Bytes b) : c(c_) {
       if (!c->profile || c->recsUsed >= (1u << 16)) return;
       if (c->recsUsed == c->recs.size()) {
          cfd_ctx::ProfRec r;
-         r.cls = n; r.bytes = 0;
+         r.cls = n; r.bytes = 0; r.lbytes = 0;
          if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
          c->recs.push_back(r);
       }
       idx = (int)c->recsUsed++;
       c->recs[idx].cls = n;
-      c->recs[idx].bytes = b;
+      c->recs[idx].bytes = b.a;
+      c->recs[idx].lbytes = b.l;
       cudaEventRecord(c->recs[idx].a, c->stream);
    }
    ~ProfScope() {
@@ -1327,7 +1328,7 @@ void profile_collect(cfd_ctx* c) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, c->recs[i].a, c->recs[i].b) != cudaSuccess) continue;
       ProfEntry& p = c->prof[c->recs[i].cls];
-      p.ms += ms; p.launches += 1; p.bytes += c->recs[i].bytes;
+      p.ms += ms; p.launches += 1; p.bytes += c->recs[i].bytes; p.lbytes += c->recs[i].lbytes;
    }
    c->recsUsed = 0;
    c->lastPcgRec = c->lastBicgRec = -1;
@@ -1358,8 +1359,11 @@ int regvec(cfd_ctx* c, const char* name, double** p, long long n) {
 }
 
 // algorithmic bytes of a CSR SpMV with nvec right-hand sides
-double spmv_bytes(const Sell& A, int nval, int nvec, bool accumulate) {
-   return (8.0 * nval + 4.0) * (double)A.nnz + 4.0 * (A.nrows + 1.0) + 8.0 * nvec * ((double)A.ncols + (double)A.nrows * (accumulate ? 2 : 1));
+// ... and the same launch in the bytes the Sell layout stores: padded values, (compressed) column indices, slice offsets
+double matrix_lbytes(const Sell& A, int nval) { return 8.0 * nval * (double)A.padded + 4.0 * (double)A.nindex + 16.0 * A.nslices; }
+Bytes spmv_bytes(const Sell& A, int nval, int nvec, bool accumulate) {
+   const double vec = 8.0 * nvec * ((double)A.ncols + (double)A.nrows * (accumulate ? 2 : 1));
+   return Bytes((8.0 * nval + 4.0) * (double)A.nnz + 4.0 * (A.nrows + 1.0) + vec, matrix_lbytes(A, nval) + vec);
 }
 
 // ---- multi-GPU primitives -----------------------------------------------------------------------------------
@@ -1575,16 +1579,18 @@ int fetch_kinfo(cfd_ctx* c) {
    if (c->lastPcgRec >= 0) {
       const double N = c->P.NNp;
       c->recs[c->lastPcgRec].bytes += 48.0 * N + c->last_cg * (12.0 * (double)c->Z.nnz + 4.0 * (N + 1) + 104.0 * N);
+      c->recs[c->lastPcgRec].lbytes += 48.0 * N + c->last_cg * (matrix_lbytes(c->Z, 1) + 104.0 * N);
       c->lastPcgRec = -1;
    }
    if (c->lastBicgRec >= 0) {
       const double N = c->P.NN;
-      double b = 0;
       const int mx = std::max(c->last_bicg[0], std::max(c->last_bicg[1], c->last_bicg[2]));
       // A is streamed once per SpMV phase: twice per lock-step iteration, plus the true-residual checks (counted by the kernel)
-      b += (c->last_bicg_passes > 0 ? (double)c->last_bicg_passes : 2.0 * mx) * (12.0 * (double)c->K.nnz + 4.0 * (N + 1));
-      for (int d = 0; d < 3; d++) b += c->last_bicg[d] * 192.0 * N;    // 24 vector reads/writes per system-iteration
-      c->recs[c->lastBicgRec].bytes += b;
+      const double passes = c->last_bicg_passes > 0 ? (double)c->last_bicg_passes : 2.0 * mx;
+      double vec = 0;
+      for (int d = 0; d < 3; d++) vec += c->last_bicg[d] * 192.0 * N;    // 24 vector reads/writes per system-iteration
+      c->recs[c->lastBicgRec].bytes += passes * (12.0 * (double)c->K.nnz + 4.0 * (N + 1)) + vec;
+      c->recs[c->lastBicgRec].lbytes += passes * matrix_lbytes(c->K, 1) + vec;
       c->lastBicgRec = -1;
    }
    return CFD_OK;
@@ -1625,7 +1631,7 @@ int launch_ebe_assemble(cfd_ctx* c, const double* Uadv, double* Aval) {
    return CFD_OK;
 }
 
-double ebe_bytes(const cfd_ctx* c, bool assemble) {
+Bytes ebe_bytes(const cfd_ctx* c, bool assemble) {
    // per element: node ids + 8 corner coordinates + gather of the advecting field (+ second field and
    // scatter RMW for the apply form; + map and RMW of NENv^2 matrix entries for the assembly form)
    const double nv = c->P.NENv;
@@ -2522,6 +2528,12 @@ int cfd_profile_get(cfd_ctx* c, const char* name, double* ms, long long* launche
    if (launches) *launches = it->second.launches;
    if (bytes) *bytes = it->second.bytes;
    return CFD_OK;
+}
+int cfd_profile_get_layout_bytes(cfd_ctx* c, const char* name, double* layout_bytes) {
+   profile_collect(c);
+   auto it = c->prof.find(name);
+   if (layout_bytes) *layout_bytes = it == c->prof.end() ? 0.0 : it->second.lbytes;
+   return it == c->prof.end() ? CFD_ERR_ARG : CFD_OK;
 }
 long long cfd_kernel_launches(cfd_ctx* c) { return c->launches; }
 

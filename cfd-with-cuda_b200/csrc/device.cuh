@@ -68,8 +68,16 @@ struct Comm;   // NCCL communicator wrapper (dist.cuh)
 struct ProfEntry {
    double ms = 0;
    long long launches = 0;
-   double bytes = 0;
+   double bytes = 0;    // algorithmic bytes (CSR model)
+   double lbytes = 0;   // bytes of the device layout as stored (padding in, compressed indices out): what the kernel has to move
 };
+// the two byte counts of one launch
+struct Bytes {
+   double a, l;
+   Bytes(double v = 0.0) : a(v), l(v) {}
+   Bytes(double a_, double l_) : a(a_), l(l_) {}
+};
+inline Bytes operator+(const Bytes& x, const Bytes& y) { return Bytes(x.a + y.a, x.l + y.l); }
 
 }   // namespace cfdb
 
@@ -131,7 +139,7 @@ struct cfd_ctx {
    long long launches = 0;
    bool profile = false;
    std::map<std::string, cfdb::ProfEntry> prof;
-   struct ProfRec { const char* cls; cudaEvent_t a, b; double bytes; };
+   struct ProfRec { const char* cls; cudaEvent_t a, b; double bytes, lbytes; };
    std::vector<ProfRec> recs;   // event-pair pool (grown on demand, reused)
    size_t recsUsed = 0;
    int lastPcgRec = -1, lastBicgRec = -1;

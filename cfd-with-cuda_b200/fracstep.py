@@ -114,6 +114,7 @@ def lib():
     L.cfd_timeStep_host.argtypes = [vp, _dp, _dp, C.POINTER(cfd_step_report), _dp]
     L.cfd_profile.argtypes = [vp, C.c_int]
     L.cfd_profile_get.argtypes = [vp, C.c_char_p, _dp, C.POINTER(C.c_longlong), _dp]
+    L.cfd_profile_get_layout_bytes.argtypes = [vp, C.c_char_p, _dp]
     L.cfd_kernel_launches.argtypes = [vp]
     L.cfd_kernel_launches.restype = C.c_longlong
     L.cfd_matrix_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]
@@ -340,8 +341,10 @@ class Context:
         ms = C.c_double()
         n = C.c_longlong()
         b = C.c_double()
+        lb = C.c_double()
         self.L.cfd_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n), C.byref(b))
-        return dict(ms=ms.value, launches=n.value, bytes=b.value)
+        self.L.cfd_profile_get_layout_bytes(self.h, name.encode(), C.byref(lb))
+        return dict(ms=ms.value, launches=n.value, bytes=b.value, layout_bytes=lb.value)
 
     def matrix_stats(self, name):
         a, b, c_, t = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int()

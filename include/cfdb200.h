@@ -234,6 +234,10 @@ int cfd_timeStep_host(cfd_ctx* ctx, double* U, double* P, cfd_step_report* repor
  * `bytes` = algorithmic bytes of the launches (DESIGN.md byte model). */
 int cfd_profile(cfd_ctx* ctx, int enable);
 int cfd_profile_get(cfd_ctx* ctx, const char* name, double* ms, long long* launches, double* bytes);
+/* the same launches counted in the bytes the device layout STORES (zero padding of the sliced layout included, per-slice compressed
+ * column indices counted once): the traffic the kernel cannot avoid, so achieved-GB/s figures formed with it cannot exceed the
+ * memory bandwidth -- the algorithmic count above can (structured meshes store fewer index bytes than the CSR model charges) */
+int cfd_profile_get_layout_bytes(cfd_ctx* ctx, const char* name, double* layout_bytes);
 long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context so far */
 /* layout statistics of a device matrix ("K", "G", "GT", "Z"): true non-zeros, stored value slots (padding included),
  * stored index integers (after per-slice offset compression), lanes per row */
