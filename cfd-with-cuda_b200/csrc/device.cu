@@ -811,11 +811,12 @@ struct PcgP2PArgs {
    XComm xc;
 };
 
-// Multi-GPU Jacobi-PCG: k_pcg with the two exchange steps folded in (fused compute + collective over peer memory).
-// One persistent cooperative kernel per GPU; per iteration: q = Z p on the owned rows (ghost p entries were written by
-// the neighbours), p.q all-reduced through mailboxes, fused x/r update, (r.z, r.r) all-reduced, p update whose
+// Multi-GPU Jacobi-PCG, classical recurrences: k_pcg with the two exchange steps folded in (fused compute + collective over
+// peer memory).  One persistent cooperative kernel per GPU; per iteration: q = Z p on the owned rows (ghost p entries were
+// written by the neighbours), p.q all-reduced through mailboxes, fused x/r update, (r.z, r.r) all-reduced, p update whose
 // interface values are stored directly into the neighbours' ghost entries over NVLink.  Identical recurrences and
 // stopping rule on every rank (the reduced scalars are bit-identical everywhere), so all ranks leave together.
+// (cfd_options.cg_variant = 1 on partitioned runs; the default there is the single-reduction kernel k_pcg_cg<true> below.)
 __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[3 * 32];
@@ -843,19 +844,19 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
       const double zi = a.dinv[i] * ri;
       v3[0] += ri * zi; v3[1] += bi * bi; v3[2] += ri * ri;
    }
-   xgrid_sum<3>(grid, v3, buf0, sh, xc, epoch);
+   if (!xgrid_sum<3>(v3, buf0, sh, xc, epoch)) return;
    double rz = v3[0];
    const double bb = v3[1];
    double rr = v3[2];
    const double thresh = a.tol * sqrt(bb);
    int it = 0;
    if (!(sqrt(rr) <= thresh || it >= a.maxit))
-      p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i]; });
+      if (!p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i]; })) return;
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       double v1[1];
       v1[0] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.p, a.q, gwarp, nwarps, lane);
-      xgrid_sum<1>(grid, v1, buf1, sh, xc, epoch);
+      if (!xgrid_sum<1>(v1, buf1, sh, xc, epoch)) return;
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
       const double alpha = rz / v1[0];
       double v2[2] = {0, 0};
@@ -866,19 +867,214 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
          v2[0] += ri * (a.dinv[i] * ri);
          v2[1] += ri * ri;
       }
-      xgrid_sum<2>(grid, v2, buf0, sh, xc, epoch);
+      if (!xgrid_sum<2>(v2, buf0, sh, xc, epoch)) return;
       const double beta = v2[0] / rz;
       rz = v2[0];
       rr = v2[1];
       it++;
       if (sqrt(rr) <= thresh || it >= a.maxit) break;   // converged: the next search direction is never used
-      p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i] + beta * a.p[i]; });
+      if (!p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i] + beta * a.p[i]; })) return;
    }
    grid.sync();
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
       xc.xstate[0] = epoch; xc.xstate[1] = hepoch;
-   }   // (xstate[3] = ticket counter, back to 0 after every reduction)
+   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Jacobi-PCG in the single-reduction form of Chronopoulos & Gear: the same iterates as the classical recurrences in exact
+// arithmetic, but ONE grid-wide (DIST: cross-GPU) reduction per iteration instead of two, and two synchronisation points
+// instead of three.  With u = M^-1 r, w = Z u:
+//    p = u + beta p ;  s = w + beta s (= Z p) ;  x += alpha p ;  r -= alpha s ;  u = M^-1 r           (one vector pass)
+//    w = Z u ;  gamma = r.u , delta = w.u , |r|^2                                                        (one sweep + ONE reduction)
+//    beta = gamma / gamma_old ;  alpha = gamma / (delta - beta gamma / alpha_old)
+// Stopping rule and iteration count as in k_pcg (cusp::default_monitor): |r| <= tol |b| tested before each iteration.  The
+// price is 16 bytes per row and iteration of extra vector traffic and one more sweep at the end, so the library uses it
+// where synchronisation dominates: small (L2-resident) systems and partitioned runs (choose_cg_variant).
+//
+// DIST = true: fused compute + collective over peer memory.  u lives in this rank's exchange window; the vector pass does
+// the rows some neighbour holds as ghosts FIRST and stores their new u straight into the neighbours' windows over NVLink,
+// the last block to finish them raises the neighbours' halo flags, and only then come the interior rows -- the transfer
+// and the flag flight overlap the bulk of the pass.  The one reduction per iteration is the fused cross-GPU barrier
+// xgrid_sum.  No NCCL call and no host round trip inside a solve.
+struct PcgCgArgs {
+   Sell Z;
+   const int* part;
+   int dynStart;
+   int* dynCounter;
+   int n;
+   const double* b;
+   double* x;
+   double *r, *u, *w, *p, *s;
+   const double* dinv;
+   double* scratch;   // 4 x gridDim doubles
+   double* info;      // [0]=iterations [1]=|r|^2 [2]=|b|^2
+   double tol;
+   int maxit;
+   int x0zero;
+   XComm xc;          // DIST only
+};
+
+// One slice of w = Z u by one warp, plus this lane's share of r.u, w.u and r.r over the slice's rows.
+__device__ __forceinline__ void pcgcg_slice(const Sell& Z, const double* __restrict__ val, int s, const double* u, const double* r, double* w, int lane,
+                                            double& g, double& d, double& rr) {
+   const int T = Z.T, sub = lane % T;
+   double acc = 0.0;
+   sell_pairs<4>(Z, s, lane, [&](long long e, int2 c2) {
+      const double2 v2 = ldnc_d2(val + e);
+      acc += v2.x * u[c2.x] + v2.y * u[c2.y];
+   });
+   for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   const int row = s * Z.R + lane / T;
+   if (sub == 0 && row < Z.nrows) {
+      const double ri = r[row], ui = u[row];
+      w[row] = acc;
+      g += ri * ui; d += acc * ui; rr += ri * ri;
+   }
+}
+__device__ __forceinline__ void pcgcg_sweep(const PcgCgArgs& a, int gwarp, int nwarps, int lane, double& g, double& d, double& rr) {
+   const double* __restrict__ val = a.Z.vals[0];
+   const int nstatic = a.dynCounter ? a.dynStart : a.Z.nslices;
+   const SliceRange sr = slice_range(nstatic, a.part, gwarp, nwarps);
+   for (int s = sr.begin; s < sr.end; s += sr.step) pcgcg_slice(a.Z, val, s, a.u, a.r, a.w, lane, g, d, rr);
+   if (a.dynCounter) {
+      while (true) {
+         int base = 0;
+         if (lane == 0) base = atomicAdd(a.dynCounter, 2);
+         base = __shfl_sync(0xffffffffu, base, 0) + a.dynStart;
+         if (base >= a.Z.nslices) break;
+         pcgcg_slice(a.Z, val, base, a.u, a.r, a.w, lane, g, d, rr);
+         if (base + 1 < a.Z.nslices) pcgcg_slice(a.Z, val, base + 1, a.u, a.r, a.w, lane, g, d, rr);
+      }
+   }
+}
+
+// The vector pass over rows i = f(t), t in [t0, t1): `first` = no previous search direction (beta = 0: p = u, s = w exactly).
+template <bool DIST, typename RowOf>
+__device__ __forceinline__ void pcgcg_rows(const PcgCgArgs& a, int t0, int t1, int stride, bool first, double alpha, double beta, RowOf rowOf) {
+   for (int t = t0; t < t1; t += stride) {
+      const int i = rowOf(t);
+      if (i < 0) continue;
+      const double ui = a.u[i], wi = a.w[i];
+      const double pi = first ? ui : ui + beta * a.p[i];
+      const double si = first ? wi : wi + beta * a.s[i];
+      a.p[i] = pi; a.s[i] = si;
+      a.x[i] += alpha * pi;
+      const double ri = a.r[i] - alpha * si;
+      a.r[i] = ri;
+      const double un = a.dinv[i] * ri;
+      a.u[i] = un;
+      if (DIST)
+         for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
+            const int2 dst = a.xc.pushDst[e];
+            st_sys_f64(a.xc.peerP[dst.x] + dst.y, un);
+         }
+   }
+}
+
+// After this rank's interface values have been stored into the neighbours' windows: the last block to get here raises the halo flags.
+__device__ __forceinline__ void pcgcg_signal(const XComm& xc, unsigned long long hepoch) {
+   __shared__ int s_lastI;
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const unsigned long long G = gridDim.x;
+      s_lastI = (atomicAdd(xc.xstate + 4, 1ull) % G == G - 1) ? 1 : 0;
+   }
+   __syncthreads();
+   if (s_lastI && threadIdx.x < xc.npeers) {
+      __threadfence_system();
+      st_rel_sys(win_haloflag(xc.peerWin[xc.peerRank[threadIdx.x]], xc.rank), hepoch);
+   }
+}
+__device__ __forceinline__ bool pcgcg_wait(const XComm& xc, unsigned long long hepoch) {
+   bool ok = true;
+   if (threadIdx.x < xc.npeers) ok = wait_flag(win_haloflag(xc.peerWin[xc.rank], xc.peerRank[threadIdx.x]), hepoch, xc.xstate + 2, xc.timeoutNs);
+   return __syncthreads_and(ok ? 1 : 0) != 0;
+}
+
+template <bool DIST, int MINB>
+__global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
+   cg::grid_group grid = cg::this_grid();
+   __shared__ double sh[4 * 32];
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int gwarp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
+   const int n = a.n;
+   unsigned long long epoch = 0, hepoch = 0;
+   if (DIST) { epoch = a.xc.xstate[0]; hepoch = a.xc.xstate[1]; }
+
+   if (!a.x0zero) {
+      // r = b - Z x (warm start, BCH.cu:418-451 keeps the previous Pdot; DIST: ghost entries of x were refreshed by the caller)
+      pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.x, a.w, gwarp, nwarps, lane);
+      grid.sync();
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+   }
+   double v4[4] = {0, 0, 0, 0};
+   // u = M^-1 r: interface rows first (DIST), then everything else
+   auto initRow = [&](int i) {
+      const double bi = a.b[i];
+      double ri = bi;
+      if (a.x0zero) a.x[i] = 0.0; else ri = bi - a.w[i];
+      a.r[i] = ri;
+      const double un = a.dinv[i] * ri;
+      a.u[i] = un;
+      v4[3] += bi * bi;
+      if (DIST)
+         for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
+            const int2 dst = a.xc.pushDst[e];
+            st_sys_f64(a.xc.peerP[dst.x] + dst.y, un);
+         }
+   };
+   if (DIST) {
+      for (int t = tid; t < a.xc.nIface; t += nthreads) initRow(a.xc.ifaceRows[t]);
+      hepoch++;
+      pcgcg_signal(a.xc, hepoch);
+      for (int i = tid; i < n; i += nthreads)
+         if (a.xc.pushPtr[i + 1] == a.xc.pushPtr[i]) initRow(i);
+   } else {
+      for (int i = tid; i < n; i += nthreads) initRow(i);
+   }
+   grid.sync();
+   if (DIST && !pcgcg_wait(a.xc, hepoch)) return;
+   pcgcg_sweep(a, gwarp, nwarps, lane, v4[0], v4[1], v4[2]);
+   if (DIST) { if (!xgrid_sum<4>(v4, a.scratch, sh, a.xc, epoch)) return; }
+   else grid_sum<4>(grid, v4, a.scratch, sh);
+   if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+   double gamma = v4[0], rr = v4[2];
+   const double bb = v4[3];
+   const double thresh = a.tol * sqrt(bb);
+   double alpha = gamma / v4[1], beta = 0.0;
+   int it = 0;
+   while (true) {
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;
+      const bool first = it == 0;
+      if (DIST) {
+         pcgcg_rows<true>(a, tid, a.xc.nIface, nthreads, first, alpha, beta, [&](int t) { return a.xc.ifaceRows[t]; });
+         hepoch++;
+         pcgcg_signal(a.xc, hepoch);
+         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [&](int t) { return a.xc.pushPtr[t + 1] == a.xc.pushPtr[t] ? t : -1; });
+      } else {
+         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [](int t) { return t; });
+      }
+      it++;
+      grid.sync();   // every block's u is in place (DIST: and the neighbours' interface values, once their flags are up)
+      if (DIST && !pcgcg_wait(a.xc, hepoch)) return;
+      double v3[3] = {0, 0, 0};
+      pcgcg_sweep(a, gwarp, nwarps, lane, v3[0], v3[1], v3[2]);
+      if (DIST) { if (!xgrid_sum<3>(v3, a.scratch, sh, a.xc, epoch)) return; }
+      else grid_sum<3>(grid, v3, a.scratch, sh);
+      if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the sweep; the next one comes after grid.sync()
+      beta = v3[0] / gamma;
+      alpha = v3[0] / (v3[1] - beta * v3[0] / alpha);
+      gamma = v3[0];
+      rr = v3[2];
+   }
+   if (tid == 0) {
+      a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
+      if (DIST) { a.xc.xstate[0] = epoch; a.xc.xstate[1] = hepoch; }
+   }
 }
 
 // Diagnostic: cost of the grid-wide primitives the persistent Krylov kernels are built from.
@@ -1414,6 +1610,20 @@ int allreduce(cfd_ctx* c, double* dev, int n, int op) {
    return CFD_OK;
 }
 
+// Every rank must take the same Krylov path (peer-memory kernels or host-driven NCCL): a rank whose window mapping failed, or that
+// was started with CFD_NO_P2P, switches ALL ranks to the NCCL path -- otherwise the ranks would wait for each other in different
+// protocols.  (min-reduction of the local decision over the communicator; without a communicator the local decision stands.)
+int p2p_agree(cfd_ctx* c) {
+   if (!c->comm || !c->comm->comm) return CFD_OK;
+   double v = c->p2p ? 1.0 : 0.0;
+   CFD_CK(cudaMemcpyAsync(c->dacc + 48, &v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+   CFD_NCCL(c->comm, c->comm->AllReduce(c->dacc + 48, c->dacc + 48, 1, kNcclFloat64, kNcclMin, c->comm->comm, c->stream));
+   CFD_CK(cudaMemcpyAsync(&v, c->dacc + 48, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   c->p2p = v > 0.5;
+   return CFD_OK;
+}
+
 // Distributed Jacobi-PCG (phase kernels + NCCL; see dist.cuh).  State read back once per batch of iterations.
 int run_pcg_dist(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    const int n = c->NPo;
@@ -1521,6 +1731,17 @@ int run_bicg_dist(cfd_ctx* c) {
    return CFD_OK;
 }
 
+static void* pcgcg_kernel(bool dist, int minb) {
+   if (dist) return minb == 2 ? (void*)k_pcg_cg<true, 2> : (void*)k_pcg_cg<true, 3>;
+   return minb == 2 ? (void*)k_pcg_cg<false, 2> : (void*)k_pcg_cg<false, 3>;
+}
+void fill_xcomm(cfd_ctx* c, XComm& xc) {
+   xc.world = c->P.world; xc.rank = c->P.rank; xc.npeers = (int)c->peerRank.size();
+   xc.peerWin = c->dPeerWin; xc.peerRank = c->dPeerRank; xc.peerP = c->dPeerP; xc.pushPtr = c->pushPtrP; xc.pushDst = c->pushDstP;
+   xc.ifaceRows = c->ifaceP; xc.nIface = c->nIfaceP;
+   xc.xstate = c->xstate; xc.timeoutNs = c->p2pTimeoutNs;
+}
+
 // Peer-memory PCG: one cooperative launch per rank, all exchange inside the kernel (k_pcg_p2p).
 int run_pcg_p2p(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    int rc;
@@ -1529,26 +1750,43 @@ int run_pcg_p2p(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    PcgArgs& a = pa.a;
    a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->NPo; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
-   XComm& xc = pa.xc;
-   xc.world = c->P.world; xc.rank = c->P.rank; xc.npeers = (int)c->peerRank.size();
-   xc.peerWin = c->dPeerWin; xc.peerRank = c->dPeerRank; xc.peerP = c->dPeerP; xc.pushPtr = c->pushPtrP; xc.pushDst = c->pushDstP;
-   xc.xstate = c->xstate;
+   fill_xcomm(c, pa.xc);
    void* args[] = {&pa};
-   ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
+   ProfScope ps(c, "pcg", x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false));
    c->lastPcgRec = ps.idx;
    CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_p2p, dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
    c->launches++;
    return CFD_OK;
 }
 
+// Single-reduction (Chronopoulos-Gear) PCG: one cooperative launch; on partitions the peer-memory form.
+int run_pcg_cg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
+   const bool dist = parted(c);
+   int rc;
+   if (dist && !x0zero && (rc = halo(c, x, false))) return rc;
+   PcgCgArgs a;
+   a.Z = c->Z; a.part = c->pcgcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = dist ? c->NPo : c->P.NNp; a.b = b; a.x = x;
+   a.r = c->cg_r; a.u = c->cg_p; a.w = c->cg_q; a.p = c->cg_pp; a.s = c->cg_s; a.dinv = c->Zdinv;
+   a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
+   memset(&a.xc, 0, sizeof a.xc);
+   if (dist) fill_xcomm(c, a.xc);
+   void* args[] = {&a};
+   ProfScope ps(c, "pcg", spmv_bytes(c->Z, 1, 1, false) + (x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false)));   // one sweep more than iterations
+   c->lastPcgRec = ps.idx;
+   CFD_CK(cudaLaunchCooperativeKernel(pcgcg_kernel(dist, c->pcg_minb), dim3(c->pcgcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
+   c->launches++;
+   return CFD_OK;
+}
+
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
-   if (parted(c) && c->p2p) return run_pcg_p2p(c, b, x, x0zero);
-   if (parted(c)) return run_pcg_dist(c, b, x, x0zero);
+   if (parted(c) && !c->p2p) return run_pcg_dist(c, b, x, x0zero);
+   if (c->cg_variant == 2) return run_pcg_cg(c, b, x, x0zero);
+   if (parted(c)) return run_pcg_p2p(c, b, x, x0zero);
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
    void* args[] = {&a};
-   ProfScope ps(c, "pcg", x0zero ? 0.0 : spmv_bytes(c->Z, 1, 1, false));
+   ProfScope ps(c, "pcg", x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false));
    c->lastPcgRec = ps.idx;
    CFD_CK(cudaLaunchCooperativeKernel(pcg_kernel(c->pcg_minb), dim3(c->pcg_blocks), dim3(c->pcg_threads), args, 0, c->stream));
    c->launches++;
@@ -1578,8 +1816,10 @@ int fetch_kinfo(cfd_ctx* c) {
    // algorithmic bytes of the Krylov launches are known only now (iteration counts): DESIGN.md byte model
    if (c->lastPcgRec >= 0) {
       const double N = c->P.NNp;
-      c->recs[c->lastPcgRec].bytes += 48.0 * N + c->last_cg * (12.0 * (double)c->Z.nnz + 4.0 * (N + 1) + 104.0 * N);
-      c->recs[c->lastPcgRec].lbytes += 48.0 * N + c->last_cg * (matrix_lbytes(c->Z, 1) + 104.0 * N);
+      // classical: 104 B per row and iteration; single-reduction form: 12 vector accesses in the pass + w, r, u in the sweep
+      const double vecB = c->cg_variant == 2 && !(parted(c) && !c->p2p) ? 120.0 : 104.0;
+      c->recs[c->lastPcgRec].bytes += 48.0 * N + c->last_cg * (12.0 * (double)c->Z.nnz + 4.0 * (N + 1) + vecB * N);
+      c->recs[c->lastPcgRec].lbytes += 48.0 * N + c->last_cg * (matrix_lbytes(c->Z, 1) + vecB * N);
       c->lastPcgRec = -1;
    }
    if (c->lastBicgRec >= 0) {
@@ -1897,6 +2137,9 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       TRY(dalloc(c, &c->bw, (size_t)(8 * N3)));
    }
    TRY(dalloc(c, &c->cg_r, (size_t)NNp)); TRY(dalloc(c, &c->cg_p, (size_t)NNp)); TRY(dalloc(c, &c->cg_q, (size_t)NNp));
+   // pressure CG recurrences (cfd_options.cg_variant): the single-reduction form where synchronisation dominates
+   c->cg_variant = o.cg_variant == 1 || o.cg_variant == 2 ? o.cg_variant : ((parted || NPo < 500000) ? 2 : 1);
+   if (c->cg_variant == 2) { TRY(dalloc(c, &c->cg_s, (size_t)NNp)); TRY(dalloc(c, &c->cg_pp, (size_t)NNp)); }
    TRY(dalloc(c, &c->kinfo, 64)); TRY(dalloc(c, &c->scal, 16));
    // initial state (applyBC_initial, BCH.cpp:4062-4110 / GQ.cpp:4559-4607)
    {
@@ -1944,13 +2187,16 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       CFD_CK(cudaMalloc((void**)&c->win, c->winBytes));
       CFD_CK(cudaMemset(c->win, 0, c->winBytes));
       c->cg_p = (double*)(c->win + c->winOffP);
-      TRY(dalloc(c, &c->xstate, 4));
+      TRY(dalloc(c, &c->xstate, 8));
+      if (const char* e = getenv("CFD_P2P_TIMEOUT_MS")) c->p2pTimeoutNs = (unsigned long long)std::max(1.0, atof(e)) * 1000000ull;
    }
    // ---- cooperative launch geometry: persistent kernels, a whole number of CTAs per SM
    {
       int occ = 0;
+      if (c->cg_variant == 2) c->pcg_minb = 2;   // the single-reduction kernel needs 64 registers to stay free of spills
       if (const char* e = getenv("CFD_PCG_OCC")) c->pcg_minb = atoi(e) == 2 ? 2 : 3;
-      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_kernel(c->pcg_minb), c->pcg_threads, 0));
+      const void* pcgK = c->cg_variant == 2 ? pcgcg_kernel(parted, c->pcg_minb) : (parted ? (const void*)k_pcg_p2p : (const void*)pcg_kernel(c->pcg_minb));
+      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcgK, c->pcg_threads, 0));
       if (occ < 1) { set_error("k_pcg does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
       const long long wantWarps = std::max<long long>(c->Z.nslices, ((long long)NNp + 31) / 32);
       int blocks = c->numSMs * occ;
@@ -1994,6 +2240,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          std::vector<long long> offStatic(c->hostOffZ.begin(), c->hostOffZ.begin() + dynStart + 1);
          std::vector<int> pz = partition(offStatic, c->pcg_blocks);
          TRY(dupload(c, &c->pcgPart, pz.data(), pz.size()));
+         c->pcgcgPart = c->pcgPart; c->pcgcg_blocks = c->pcg_blocks;
          c->pcgDynStart = dynStart;
          if (useDyn) TRY(dalloc(c, &c->pcgDynCounter, 4));
       }
@@ -2107,7 +2354,23 @@ int cfd_p2p_attach(cfd_ctx* c, const char* all) {
    if ((rc = dupload(c, &c->dPeerRank, c->peerRank.data(), c->peerRank.size()))) return rc;
    if ((rc = dupload(c, &c->pushPtrP, ptr.data(), ptr.size()))) return rc;
    if ((rc = dupload(c, &c->pushDstP, dst.data(), dst.size()))) return rc;
+   std::vector<int> iface;
+   for (int i = 0; i < NPo; i++)
+      if (ptr[i + 1] > ptr[i]) iface.push_back(i);
+   c->nIfaceP = (int)iface.size();
+   if ((rc = dupload(c, &c->ifaceP, iface.data(), iface.size()))) return rc;
    c->p2p = getenv("CFD_NO_P2P") == nullptr;
+   return p2p_agree(c);
+}
+
+int cfd_p2p_reset(cfd_ctx* c) {
+   if (!c) return CFD_ERR_ARG;
+   if (!c->win) { set_error("no exchange window (context is not partitioned)"); return CFD_ERR_STATE; }
+   CFD_CK(cudaSetDevice(c->device));
+   CFD_CK(cudaStreamSynchronize(c->stream));
+   CFD_CK(cudaMemset(c->win, 0, kWinHeader));
+   CFD_CK(cudaMemset(c->xstate, 0, 8 * sizeof(unsigned long long)));
+   CFD_CK(cudaDeviceSynchronize());
    return CFD_OK;
 }
 
@@ -2665,11 +2928,12 @@ int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_o
    return CFD_OK;
 }
 
-int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x, double tol, int maxit,
-                int* its, double* ms) {
+int cfd_csr_pcg_variant(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x, double tol, int maxit,
+                        int variant, int* its, double* ms) {
    int ndev = 0;
    CFD_CK(cudaGetDeviceCount(&ndev));
    if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return CFD_ERR_CUDA; }
+   if (variant != 1 && variant != 2) { set_error("variant must be 1 (classical) or 2 (Chronopoulos-Gear)"); return CFD_ERR_ARG; }
    SellHost h;
    sell_build_host(n, n, rowStarts, col, choose_T(n, rowStarts[n]), h);
    Sell Z;
@@ -2680,9 +2944,10 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    for (int r = 0; r < n; r++)
       for (int k = rowStarts[r]; k < rowStarts[r + 1]; k++)
          if (col[k] == r) { dinv[r] = 1.0 / val[k]; break; }
-   double *db, *dx, *dr, *dp, *dq, *dd, *scr, *info;
+   double *db, *dx, *dr, *dp, *dq, *dd, *ds, *dpp, *scr, *info;
    CFD_CK(cudaMalloc(&db, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dx, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dr, 16 * (size_t)n));
    CFD_CK(cudaMalloc(&dp, 16 * (size_t)n)); CFD_CK(cudaMalloc(&dq, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dd, 8 * (size_t)n));
+   CFD_CK(cudaMalloc(&ds, 8 * (size_t)n)); CFD_CK(cudaMalloc(&dpp, 8 * (size_t)n));
    CFD_CK(cudaMalloc(&info, 8 * 16));
    CFD_CK(cudaMemcpy(db, b, 8 * (size_t)n, cudaMemcpyHostToDevice));
    CFD_CK(cudaMemcpy(dx, x, 8 * (size_t)n, cudaMemcpyHostToDevice));
@@ -2690,17 +2955,22 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    int dev = 0, sms = 0, occ = 0;
    cudaGetDevice(&dev);
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pcg_kernel(3), 512, 0));
+   const void* kern = variant == 2 ? pcgcg_kernel(false, 3) : pcg_kernel(3);
+   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, 0));
    const int blocks = sms * std::max(1, occ);
-   CFD_CK(cudaMalloc(&scr, 8 * (size_t)6 * blocks));
+   CFD_CK(cudaMalloc(&scr, 8 * (size_t)8 * blocks));
    PcgArgs a;
    a.Z = Z; a.part = nullptr; a.dynStart = Z.nslices; a.dynCounter = nullptr; a.n = n; a.b = db; a.x = dx; a.r = dr; a.p = dp; a.q = dq; a.dinv = dd; a.scratch = scr; a.info = info;
    a.tol = tol; a.maxit = maxit; a.x0zero = 0;
-   void* args[] = {&a};
+   PcgCgArgs g;
+   g.Z = Z; g.part = nullptr; g.dynStart = Z.nslices; g.dynCounter = nullptr; g.n = n; g.b = db; g.x = dx; g.r = dr; g.u = dp; g.w = dq; g.p = dpp; g.s = ds;
+   g.dinv = dd; g.scratch = scr; g.info = info; g.tol = tol; g.maxit = maxit; g.x0zero = 0;
+   memset(&g.xc, 0, sizeof g.xc);
+   void* args[] = {variant == 2 ? (void*)&g : (void*)&a};
    cudaEvent_t e0, e1;
    cudaEventCreate(&e0); cudaEventCreate(&e1);
    cudaEventRecord(e0);
-   CFD_CK(cudaLaunchCooperativeKernel(pcg_kernel(3), dim3(blocks), dim3(512), args, 0, 0));
+   CFD_CK(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(512), args, 0, 0));
    cudaEventRecord(e1);
    CFD_CK(cudaEventSynchronize(e1));
    float t = 0;
@@ -2710,13 +2980,17 @@ int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, 
    CFD_CK(cudaMemcpy(x, dx, 8 * (size_t)n, cudaMemcpyDeviceToHost));
    if (its) *its = (int)hinfo[0];
    if (ms) *ms = t;
-   if (getenv("CFD_PCG_PHASES") && hinfo[0] > 0)
+   if (variant == 1 && getenv("CFD_PCG_PHASES") && hinfo[0] > 0)
       fprintf(stderr, "pcg phases (us/iter, block 0): spmv %.2f  reduce1 %.2f  update %.2f  reduce2 %.2f  pupdate+sync %.2f\n", hinfo[8] / hinfo[0] * 1e-3,
               hinfo[9] / hinfo[0] * 1e-3, hinfo[10] / hinfo[0] * 1e-3, hinfo[11] / hinfo[0] * 1e-3, hinfo[12] / hinfo[0] * 1e-3);
    cudaEventDestroy(e0); cudaEventDestroy(e1);
-   cudaFree(db); cudaFree(dx); cudaFree(dr); cudaFree(dp); cudaFree(dq); cudaFree(dd); cudaFree(scr); cudaFree(info);
+   cudaFree(db); cudaFree(dx); cudaFree(dr); cudaFree(dp); cudaFree(dq); cudaFree(dd); cudaFree(ds); cudaFree(dpp); cudaFree(scr); cudaFree(info);
    sell_free(Z);
    return CFD_OK;
+}
+int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x, double tol, int maxit,
+                int* its, double* ms) {
+   return cfd_csr_pcg_variant(n, rowStarts, col, val, b, x, tol, maxit, 1, its, ms);
 }
 
 }   // extern "C"

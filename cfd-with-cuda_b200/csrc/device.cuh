@@ -118,7 +118,9 @@ struct cfd_ctx {
    double* Adinv = nullptr;     // [NN]
    double* bw = nullptr;        // BiCGStab work: 8 x [3][NN]
    // Krylov work
-   double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;
+   double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_s = nullptr, *cg_pp = nullptr;   // (cg_s, cg_pp: single-reduction form only)
+   int cg_variant = 1;          // 1 classical, 2 Chronopoulos-Gear (resolved from cfd_options.cg_variant at init)
+   int pcgcg_blocks = 0;
    double* partials = nullptr;  // grid-reduction scratch
    double* kinfo = nullptr;     // device: Krylov results (iterations, residuals)
    double* scal = nullptr;      // device: [0..3] convergence sums, [4] maxAcc bits
@@ -130,6 +132,7 @@ struct cfd_ctx {
    int bicgDynStart = 0;            // same for the momentum matrix inside k_bicgstab3
    int* bicgDynCounter = nullptr;
    int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
+   int* pcgcgPart = nullptr;                      // (= pcgPart: the context runs one of the two PCG kernels)
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
    int timeN = 0;
@@ -166,7 +169,10 @@ struct cfd_ctx {
    double** dPeerP = nullptr;       // [nPeers] start of my block inside each peer's p ghosts
    int* dPeerRank = nullptr;
    int* pushPtrP = nullptr;         // [NPo+1] CSR of (peer, slot) pushes per owned pressure DOF
+   int* ifaceP = nullptr;           // owned pressure DOFs with at least one push (done first, so the transfer overlaps the rest)
+   int nIfaceP = 0;
+   unsigned long long p2pTimeoutNs = 4000000000ull;
    int2* pushDstP = nullptr;
-   unsigned long long* xstate = nullptr;   // device: [0] allreduce epoch [1] halo epoch [2] error
+   unsigned long long* xstate = nullptr;   // device: [0] allreduce epoch [1] halo epoch [2] error [3] reduction ticket [4] interface ticket
    std::vector<int> remoteVoff, remotePoff;
 };

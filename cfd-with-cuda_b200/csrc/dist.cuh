@@ -17,7 +17,7 @@
 
 typedef struct ncclComm* ncclComm_t;
 struct NcclUniqueId { char internal[128]; };
-enum { kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };
 
 struct Comm {
    void* lib = nullptr;
@@ -344,10 +344,13 @@ struct XComm {
    int world, rank, npeers;
    char* const* peerWin;               // [world] window bases (own included)
    const int* peerRank;                // [npeers]
-   double* const* peerP;               // [npeers]
+   double* const* peerP;               // [npeers] start of my block inside each peer's ghost range of the gathered pressure vector
    const int* pushPtr;                 // [n+1]
    const int2* pushDst;                // (peer index, slot)
-   unsigned long long* xstate;         // [0] allreduce epoch [1] halo epoch [2] error
+   const int* ifaceRows;               // [nIface] owned pressure DOFs that some peer holds as a ghost
+   int nIface;
+   unsigned long long* xstate;         // [0] allreduce epoch [1] halo epoch [2] error [3] reduction ticket [4] interface ticket
+   unsigned long long timeoutNs;       // spin-waits give up after this long (a peer died): error word set, every block leaves the kernel
 };
 __device__ __forceinline__ unsigned long long* win_arflag(char* w, int slot, int src) { return (unsigned long long*)w + slot * kMaxRanks + src; }
 __device__ __forceinline__ unsigned long long* win_haloflag(char* w, int src) { return (unsigned long long*)w + 3 * kMaxRanks + src; }
@@ -372,16 +375,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
    return t;
 }
-// Spin until *f >= want.  Never hangs: after 4 s (a peer died) the error word is set and every later wait returns at once.
-__device__ __forceinline__ void wait_flag(const unsigned long long* f, unsigned long long want, unsigned long long* err) {
+// Spin until *f >= want; false after the time-out (a peer died) or when another block already raised the error word.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* f, unsigned long long want, unsigned long long* err, unsigned long long timeoutNs) {
    const unsigned long long t0 = gtimer();
    unsigned spins = 0;
    while (ld_acq_sys(f) < want) {
       if ((++spins & 255u) == 0) {
-         if (*(volatile unsigned long long*)err) return;
-         if (gtimer() - t0 > 4000000000ull) { *(volatile unsigned long long*)err = 1; return; }
+         if (*(volatile unsigned long long*)err) return false;
+         if (gtimer() - t0 > timeoutNs) { *(volatile unsigned long long*)err = 1; return false; }
       }
    }
+   return true;
 }
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -397,37 +401,41 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 // (local partials in a fixed order, then ranks in rank order), so every block takes the same branches.
 // One fused barrier instead of "local grid reduction, then exchange":
 //   * every block publishes its partial and takes a ticket; the LAST block to arrive reduces the partials and
-//     delivers this rank's sums to every rank's mailbox (its own included)
+//     delivers this rank's sums to every rank's mailbox (its own included).  Tickets only ever count up (64 bit): the last
+//     block of reduction k is the one that draws k*G - 1, so there is no reset that a fast block could overtake
 //   * delivery uses flag-in-data words (low / high half of the double + the 32-bit epoch in one 8-byte store, the
-//     scheme of NCCL's LL protocol): no fence and no separate flag, one NVLink traversal
+//     scheme of NCCL's LL protocol): no separate flag, one NVLink traversal.  The delivering lanes fence at system scope
+//     first, so that everything this rank wrote before the reduction (peer-memory pushes included) is visible to whoever
+//     sees the words
 //   * every block polls its own mailbox; seeing all ranks' words of this epoch implies that every block of every
-//     rank has finished the phase before the reduction -> this IS the grid + cross-GPU barrier
+//     rank has finished the phase before the reduction -> this IS the grid + cross-GPU barrier.  Every polling lane
+//     fences after its own poll (acquire side).
+// Returns false -- in every thread of the block -- after a time-out: the caller must leave the kernel at once (no further
+// grid-wide or cross-GPU synchronisation; every block of every rank runs into the same time-out or sees the error word).
 template <int N>
-__device__ __forceinline__ void xgrid_sum(cg::grid_group& grid, double (&v)[N], double* buf, double* sh, const XComm& xc,
-                                          unsigned long long& epoch) {
-   (void)grid;
-   __shared__ int s_last;
+__device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* sh, const XComm& xc, unsigned long long& epoch) {
+   __shared__ int s_last, s_fail;
    block_sum<N>(v, sh);
    epoch++;
    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
    const int slot = (int)(epoch % 3);
-   const int G = gridDim.x;
-   unsigned int* ticket = (unsigned int*)(xc.xstate + 3);
+   const unsigned long long G = gridDim.x;
+   unsigned long long* ticket = xc.xstate + 3;
    if (threadIdx.x == 0) {
 #pragma unroll
       for (int i = 0; i < N; i++) buf[(size_t)i * G + blockIdx.x] = v[i];
       __threadfence();
-      s_last = (atomicAdd(ticket, 1u) == (unsigned)(G - 1)) ? 1 : 0;
+      s_last = (atomicAdd(ticket, 1ull) % G == G - 1) ? 1 : 0;
+      s_fail = 0;
    }
    __syncthreads();
    if (s_last && threadIdx.x < 32) {
-      __threadfence();
-      if (threadIdx.x == 0) *ticket = 0u;   // nobody takes a ticket again before this reduction has been delivered
+      __threadfence_system();
       double tot[N];
 #pragma unroll
       for (int i = 0; i < N; i++) {
          double s = 0.0;
-         for (int b = threadIdx.x; b < G; b += 32) s += __ldcg(buf + (size_t)i * G + b);
+         for (int b = threadIdx.x; b < (int)G; b += 32) s += __ldcg(buf + (size_t)i * G + b);
          tot[i] = warp_sum(s);
       }
       if (threadIdx.x < xc.world) {   // lane q delivers to rank q
@@ -448,20 +456,23 @@ __device__ __forceinline__ void xgrid_sum(cg::grid_group& grid, double (&v)[N], 
          const unsigned long long* mb = (const unsigned long long*)win_mail(xc.peerWin[xc.rank], slot, threadIdx.x);
          const unsigned long long t0 = gtimer();
          unsigned spins = 0;
+         bool ok = true;
 #pragma unroll
          for (int i = 0; i < N; i++) {
-            unsigned long long lo, hi;
-            while (true) {
+            unsigned long long lo = 0, hi = 0;
+            while (ok) {
                lo = ld_sys_u64(mb + 2 * i);
                hi = ld_sys_u64(mb + 2 * i + 1);
                if ((lo >> 32) == (tag >> 32) && (hi >> 32) == (tag >> 32)) break;
                if ((++spins & 255u) == 0) {
-                  if (*(volatile unsigned long long*)(xc.xstate + 2)) break;
-                  if (gtimer() - t0 > 4000000000ull) { *(volatile unsigned long long*)(xc.xstate + 2) = 1; break; }
+                  if (*(volatile unsigned long long*)(xc.xstate + 2)) ok = false;
+                  else if (gtimer() - t0 > xc.timeoutNs) { *(volatile unsigned long long*)(xc.xstate + 2) = 1; ok = false; }
                }
             }
             mine[i] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
          }
+         if (!ok) s_fail = 1;
+         __threadfence_system();   // acquire side, in every lane that observed a word
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -469,17 +480,19 @@ __device__ __forceinline__ void xgrid_sum(cg::grid_group& grid, double (&v)[N], 
          for (int q = 0; q < xc.world; q++) s += __shfl_sync(0xffffffffu, mine[i], q);   // rank order
          if (threadIdx.x == 0) sh[i] = s;
       }
-      if (threadIdx.x == 0) __threadfence();   // acquire side: drops this SM's L1 lines before the block reads other blocks' data
    }
    __syncthreads();
 #pragma unroll
    for (int i = 0; i < N; i++) v[i] = sh[i];
+   const bool ok = s_fail == 0;
    __syncthreads();
+   return ok;
 }
 
 // p <- values (owned rows), pushed to the neighbours' ghost entries; then signal and wait for their pushes.
+// Returns false (block-uniform) after a time-out: leave the kernel.
 template <typename F>
-__device__ __forceinline__ void p_update_and_push(cg::grid_group& grid, int n, double* p, const XComm& xc, unsigned long long& hepoch,
+__device__ __forceinline__ bool p_update_and_push(cg::grid_group& grid, int n, double* p, const XComm& xc, unsigned long long& hepoch,
                                                   int tid, int nthreads, F value) {
    for (int i = tid; i < n; i += nthreads) {
       const double pn = value(i);
@@ -493,6 +506,7 @@ __device__ __forceinline__ void p_update_and_push(cg::grid_group& grid, int n, d
    grid.sync();
    hepoch++;
    if (blockIdx.x == 0 && threadIdx.x < xc.npeers) st_rel_sys(win_haloflag(xc.peerWin[xc.peerRank[threadIdx.x]], xc.rank), hepoch);
-   if (threadIdx.x < xc.npeers) wait_flag(win_haloflag(xc.peerWin[xc.rank], xc.peerRank[threadIdx.x]), hepoch, xc.xstate + 2);
-   __syncthreads();
+   bool ok = true;
+   if (threadIdx.x < xc.npeers) ok = wait_flag(win_haloflag(xc.peerWin[xc.rank], xc.peerRank[threadIdx.x]), hepoch, xc.xstate + 2, xc.timeoutNs);
+   return __syncthreads_and(ok ? 1 : 0) != 0;
 }

@@ -120,6 +120,8 @@ def lib():
     L.cfd_matrix_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]
     L.cfd_csr_spmv.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.cfd_csr_pcg.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, _ip, _dp]
+    L.cfd_csr_pcg_variant.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp]
+    L.cfd_p2p_reset.argtypes = [vp]
     L.cfd_solver_create_from_inp.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
     L.cfd_solver_create_cavity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                            C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
@@ -500,7 +502,8 @@ def sell_layout_check(rowStarts, col, val, ncols, T=0):
     return int(bad), int(ns.value), int(nc.value), float(ratio.value)
 
 
-def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000):
+def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000, variant=1):
+    """Jacobi-PCG on the GPU; variant 1 = classical recurrences, 2 = Chronopoulos-Gear single-reduction form."""
     rs = np.ascontiguousarray(rowStarts, np.int32)
     cl = np.ascontiguousarray(col, np.int32)
     vl = np.ascontiguousarray(val, np.float64)
@@ -508,7 +511,7 @@ def csr_pcg(rowStarts, col, val, b, x0=None, tol=1e-6, maxit=1000):
     x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, np.float64).copy()
     its = C.c_int()
     ms = C.c_double()
-    _check(lib().cfd_csr_pcg(len(b), _i(rs), _i(cl), _d(vl), _d(b), _d(x), tol, maxit, C.byref(its), C.byref(ms)))
+    _check(lib().cfd_csr_pcg_variant(len(b), _i(rs), _i(cl), _d(vl), _d(b), _d(x), tol, maxit, variant, C.byref(its), C.byref(ms)))
     return x, its.value, ms.value
 
 

@@ -118,9 +118,11 @@ typedef struct cfd_options {
                             1 = one test per iteration, where a PARALUTION-style solver (GQ.cpp:4190-4229) stops */
    int bicg_no_verify;   /* 0 (default) = a momentum solve is accepted on its TRUE residual |b - A x| <= bicg_tol |b| and restarted from it
                             otherwise (breakdowns included); 1 = trust the recurrence residual, as the reference's libraries do */
-   int cg_variant;    /* pressure CG recurrences: 0 (default) = classical two-reduction PCG, the reference's (BCH.cu:418-451);
-                         1 = Chronopoulos-Gear single-reduction form (same iterates in exact arithmetic, one grid-wide / cross-GPU
-                         reduction per iteration instead of two) */
+   int cg_variant;    /* pressure CG recurrences: 1 = classical two-reduction PCG, as the reference runs it (BCH.cu:418-451);
+                         2 = Chronopoulos-Gear single-reduction form (same iterates in exact arithmetic, one grid-wide / cross-GPU
+                         reduction per iteration instead of two, 16 B per row more vector traffic); 0 (default) = the library
+                         chooses: single-reduction where synchronisation dominates (partitioned runs, systems under 500 000 rows),
+                         classical otherwise */
    int reserved[2];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
@@ -151,6 +153,10 @@ int cfd_comm_init(cfd_ctx* ctx, const char id[128]);
  * and all-reduces its dot products through peer mailboxes -- no host round trip and no NCCL call per iteration. */
 int cfd_p2p_export(cfd_ctx* ctx, char desc[96]);
 int cfd_p2p_attach(cfd_ctx* ctx, const char* all_desc /* [world][96] */);
+/* After a peer-memory time-out (CFD_ERR_STATE from a step: a rank stopped participating for longer than CFD_P2P_TIMEOUT_MS,
+ * default 4000): zero this rank's exchange window and epochs.  Collective in the sense that EVERY rank must call it, with a
+ * host-side barrier before and after, before the contexts are used again. */
+int cfd_p2p_reset(cfd_ctx* ctx);
 
 /* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
  * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);
@@ -258,6 +264,9 @@ int cfd_diag_sync(int blocks, int threads, int iters, int mode, double* us_per_o
 /* Jacobi-PCG on a CSR matrix: returns iterations in *its */
 int cfd_csr_pcg(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x,
                 double tol, int maxit, int* its, double* ms);
+/* same with the recurrences chosen explicitly: variant 1 = classical, 2 = Chronopoulos-Gear (see cfd_options.cg_variant) */
+int cfd_csr_pcg_variant(int n, const int* rowStarts, const int* col, const double* val, const double* b, double* x,
+                        double tol, int maxit, int variant, int* its, double* ms);
 
 /* =============================================================================
  * Solver-level API: the whole `solverGPU` program of the reference as a library

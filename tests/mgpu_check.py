@@ -1,4 +1,5 @@
-"""torchrun --nproc-per-node N scratch/mgpu_check.py : partitioned run vs single-GPU run of the same problem."""
+"""torchrun --nproc-per-node N tests/mgpu_check.py : partitioned run vs single-GPU run of the same problem.
+Environment: NO_P2P=1 -> host-driven NCCL Krylov path; CG_VARIANTS=0,1,2 -> pressure-CG recurrences to run (cfd_options.cg_variant)."""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'cfd-with-cuda_b200'))
@@ -13,8 +14,9 @@ def bcast_id():
 cases = [(dict(nx=8, NENv=27), 'explicit', 3, {}), (dict(nx=12, NENv=8), 'implicit', 3, {}),
          (dict(nx=8, NENv=27, cluster=2.0), 'implicit', 2, dict(cg_tol=1e-12, bicg_tol=1e-12, cg_maxit=5000, bicg_maxit=5000)),
          (dict(nx=12, NENv=8), 'explicit', 2, {})]
-for cav, scheme, steps, kw in cases:
-    opts = fracstep.options(device=lr, **kw)
+variants = [int(v) for v in os.environ.get('CG_VARIANTS', '0').split(',')]
+for (cav, scheme, steps, kw), variant in [(cs, v) for cs in cases for v in variants]:
+    opts = fracstep.options(device=lr, cg_variant=variant, **kw)
     s = fracstep.Solver(scheme=scheme, cavity=cav, opts=opts, world=world, rank=rank)
     fracstep.setup_distributed(s, dist, torch, peer_memory=os.environ.get('NO_P2P') is None)
     reps = s.ctx.time_loop(steps)
@@ -33,7 +35,7 @@ for cav, scheme, steps, kw in cases:
     dist.all_reduce(errs)
     if rank == 0:
         e = errs.cpu().numpy()
-        print(cav, scheme, 'world', world, 'relU %.2e relP %.2e' % (np.sqrt(e[0] / e[1]), np.sqrt(e[2] / e[3])))
+        print(cav, scheme, 'cg_variant', variant, 'world', world, 'relU %.2e relP %.2e' % (np.sqrt(e[0] / e[1]), np.sqrt(e[2] / e[3])))
         print('   part: iter', [r['iter'] for r in reps], 'cg', [r['cg_iterations'] for r in reps], 'bicg', [r['bicg_iterations'] for r in reps], 'mon', reps[-1]['monitor'], 'maxAcc', reps[-1]['maxAcc'])
         print('   single: iter', [r['iter'] for r in gre], 'cg', [r['cg_iterations'] for r in gre], 'bicg', [r['bicg_iterations'] for r in gre], 'mon', gre[-1]['monitor'], 'maxAcc', gre[-1]['maxAcc'])
         g.close()

@@ -123,7 +123,9 @@ def test_time_loop_parity(mesh, name, scheme, setting):
     # parity bar -- see tests/test_reference_pin.py::bars and profiles/r02_asis_spread.txt; the 1e-6 bar is asserted at "tight"
     bar, barP = (3e-4, 2e-3) if q2_implicit_ref else (1e-6, 1e-6)
     assert rel(U, o.U) <= bar, rel(U, o.U)
-    assert rel_free(U, o.U, o) <= 20 * bar, rel_free(U, o.U, o)   # interior field is ~1e-3 of the lid speed this early
+    # interior field alone (~1e-3 of the lid speed this early).  At the reference tolerance the stopping rule |b - A u| <= 1e-6 |b| is
+    # dominated by the lid rows of b, so the interior is only determined to ~1e-6 x 1e3 x cond: measured 1.4e-2 on the 4^3 mesh (B200)
+    assert rel_free(U, o.U, o) <= (0.1 if q2_implicit_ref else 2e-5), rel_free(U, o.U, o)
     assert rel(P, o.P) <= barP, rel(P, o.P)
     assert all(r["cg_converged"] for r in reps)
     if scheme == "implicit":
@@ -191,9 +193,37 @@ def test_spmv_and_pcg_kernels(mesh):
     x, its, _ = fracstep.csr_pcg(zr, zc, zv, b, tol=1e-10, maxit=2000)
     assert np.linalg.norm(Z @ x - b) <= 1.01e-10 * np.linalg.norm(b)
     assert 0 < its < 2000
+    # the single-reduction (Chronopoulos-Gear) recurrences: same iterates in exact arithmetic -> same count (+-2), same solution
+    x2, its2, _ = fracstep.csr_pcg(zr, zc, zv, b, tol=1e-10, maxit=2000, variant=2)
+    assert np.linalg.norm(Z @ x2 - b) <= 1.5e-10 * np.linalg.norm(b) and abs(its2 - its) <= 2 and rel(x2, x) < 1e-8
+    x0 = rng.standard_normal(NNp)   # warm start
+    xa, ia, _ = fracstep.csr_pcg(zr, zc, zv, b, x0=x0, tol=1e-8, maxit=2000)
+    xb, ib, _ = fracstep.csr_pcg(zr, zc, zv, b, x0=x0, tol=1e-8, maxit=2000, variant=2)
+    assert abs(ia - ib) <= 2 and rel(xb, xa) < 1e-6
     # empty right-hand side: zero iterations, x untouched (CUSP monitor semantics)
-    x, its, _ = fracstep.csr_pcg(zr, zc, zv, np.zeros(NNp))
-    assert its == 0 and not x.any()
+    for variant in (1, 2):
+        x, its, _ = fracstep.csr_pcg(zr, zc, zv, np.zeros(NNp), variant=variant)
+        assert its == 0 and not x.any()
+
+
+@pytest.mark.parametrize("name,scheme", [("q2_c4", "explicit"), ("q1_u8", "implicit"), ("q2_u5", "explicit")])
+def test_both_cg_recurrences_against_oracle(mesh, name, scheme):
+    """cfd_options.cg_variant: the classical PCG (what the reference runs) and the single-reduction form the library picks for
+    small / partitioned systems must both meet the parity bar: fields 1e-6, CG counts within +-2 of the oracle per solve."""
+    import fracstep
+    import orc
+    path = mesh(name, **CASES[name])
+    o = orc.Oracle(path, scheme)
+    o.run(4)
+    ocg = o.arr("cgIters")
+    for variant in (1, 2):
+        c = fracstep.Context(fracstep.Problem(o, scheme), fracstep.options(cg_variant=variant))
+        reps = c.time_loop(4)
+        U, P = c.fields()
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= (1e-6 if scheme == "implicit" else 1e-5), (variant, rel(U, o.U), rel(P, o.P))
+        assert abs(sum(r["cg_iterations"] for r in reps) - int(ocg.sum())) <= 2 * len(ocg), (variant, [r["cg_iterations"] for r in reps], list(ocg))
+        assert all(r["cg_converged"] for r in reps)
+        c.close()
 
 
 GOLDEN = ["q2_c4_explicit", "q2_c6_explicit", "q1_u8_explicit", "q1_u8_implicit", "q2_c4_implicit_tight"]
@@ -348,13 +378,15 @@ def test_two_gpu_partitioned_run(peer_memory, tmp_path):
     env = dict(os.environ)
     if not peer_memory:
         env["NO_P2P"] = "1"
+    else:
+        env["CG_VARIANTS"] = "1,2"   # both peer-memory PCG kernels: classical and single-reduction
     port = 29600 + os.getpid() % 300 + (7 if peer_memory else 0)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), os.path.join(root, "tests", "mgpu_check.py")], cwd=root, env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     lines = [l for l in out.stdout.split("\n") if "relU" in l]
-    assert len(lines) == 4, out.stdout[-3000:]
+    assert len(lines) == (8 if peer_memory else 4), out.stdout[-3000:]
     for l in lines:
         relU, relP = float(l.split("relU")[1].split()[0]), float(l.split("relP")[1].split()[0])
         assert relU <= 1e-6 and relP <= 1e-5, l
