@@ -1047,6 +1047,14 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
    const double thresh = a.tol * sqrt(bb);
    double alpha = gamma / v4[1], beta = 0.0;
    int it = 0;
+   // phase clock of block 0 (diagnostics build: info[8..11] = ns in vector pass / grid sync (+ halo wait) / sweep / reduction)
+#ifdef CFD_PCG_PHASE_TIMERS
+   unsigned long long tph[4] = {0, 0, 0, 0}, t0 = 0, t1;
+#define PCG_TICK(k) do { if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define PCG_TICK(k)
+#endif
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       const bool first = it == 0;
@@ -1059,18 +1067,27 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
          pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [](int t) { return t; });
       }
       it++;
+      PCG_TICK(0);
       grid.sync();   // every block's u is in place (DIST: and the neighbours' interface values, once their flags are up)
       if (DIST && !pcgcg_wait(a.xc, hepoch)) return;
+      PCG_TICK(1);
       double v3[3] = {0, 0, 0};
       pcgcg_sweep(a, gwarp, nwarps, lane, v3[0], v3[1], v3[2]);
+      PCG_TICK(2);
       if (DIST) { if (!xgrid_sum<3>(v3, a.scratch, sh, a.xc, epoch)) return; }
       else grid_sum<3>(grid, v3, a.scratch, sh);
+      PCG_TICK(3);
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the sweep; the next one comes after grid.sync()
       beta = v3[0] / gamma;
       alpha = v3[0] / (v3[1] - beta * v3[0] / alpha);
       gamma = v3[0];
       rr = v3[2];
    }
+#undef PCG_TICK
+#ifdef CFD_PCG_PHASE_TIMERS
+   if (tid == 0)
+      for (int k = 0; k < 4; k++) a.info[8 + k] = (double)tph[k];
+#endif
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
       if (DIST) { a.xc.xstate[0] = epoch; a.xc.xstate[1] = hepoch; }
@@ -2983,6 +3000,9 @@ int cfd_csr_pcg_variant(int n, const int* rowStarts, const int* col, const doubl
    if (variant == 1 && getenv("CFD_PCG_PHASES") && hinfo[0] > 0)
       fprintf(stderr, "pcg phases (us/iter, block 0): spmv %.2f  reduce1 %.2f  update %.2f  reduce2 %.2f  pupdate+sync %.2f\n", hinfo[8] / hinfo[0] * 1e-3,
               hinfo[9] / hinfo[0] * 1e-3, hinfo[10] / hinfo[0] * 1e-3, hinfo[11] / hinfo[0] * 1e-3, hinfo[12] / hinfo[0] * 1e-3);
+   if (variant == 2 && getenv("CFD_PCG_PHASES") && hinfo[0] > 0)
+      fprintf(stderr, "pcg (single-reduction) phases (us/iter, block 0): vector pass %.2f  grid sync %.2f  sweep %.2f  reduction %.2f\n",
+              hinfo[8] / hinfo[0] * 1e-3, hinfo[9] / hinfo[0] * 1e-3, hinfo[10] / hinfo[0] * 1e-3, hinfo[11] / hinfo[0] * 1e-3);
    cudaEventDestroy(e0); cudaEventDestroy(e1);
    cudaFree(db); cudaFree(dx); cudaFree(dr); cudaFree(dp); cudaFree(dq); cudaFree(dd); cudaFree(ds); cudaFree(dpp); cudaFree(scr); cudaFree(info);
    sell_free(Z);
