@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CFD_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cg-variant", type=int, default=0, help="cfd_options.cg_variant: 0 library default, 1 classical PCG, 2 single-reduction PCG")
+    ap.add_argument("--deterministic", type=int, default=0, help="cfd_options.deterministic")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
     sz = sizes(w)
@@ -266,7 +268,7 @@ def main():
         fracstep.build()
     if dist is not None:
         dist.barrier()
-    opts = fracstep.options(device=local_rank)
+    opts = fracstep.options(device=local_rank, cg_variant=a.cg_variant, deterministic=a.deterministic)
     t0 = time.time()
     tmp = None
     if w.get("inp"):
@@ -361,7 +363,7 @@ def main():
                        share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
     config.update(parallelism="1 GPU" if world == 1 else "%d element blocks (z-slabs), one per GPU; peer-memory Krylov kernels + NCCL halo swap / allreduce" % world,
                   l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["layout_bytes"] for v in prof.values()) / a.steps / 1e9),
-                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps),
+                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps), cg_variant=a.cg_variant,
                   bicgstab_iterations_last_step=reps[-1]["bicg_iterations"])
     krylov_ok = all(r["cg_converged"] for r in reps) and all(all(r["bicg_converged"]) for r in reps)
     line = dict(metric="time steps/s", value=n_rep * a.steps / (ms_max * 1e-3), unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
