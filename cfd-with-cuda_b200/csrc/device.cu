@@ -879,6 +879,7 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
       xc.xstate[0] = epoch; xc.xstate[1] = hepoch;
+      xc.xstate[3] = 0; xc.xstate[4] = 0;   // tickets count modulo the grid size, which differs between the Krylov kernels
    }
 }
 
@@ -1090,7 +1091,7 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
 #endif
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
-      if (DIST) { a.xc.xstate[0] = epoch; a.xc.xstate[1] = hepoch; }
+      if (DIST) { a.xc.xstate[0] = epoch; a.xc.xstate[1] = hepoch; a.xc.xstate[3] = 0; a.xc.xstate[4] = 0; }
    }
 }
 
@@ -1116,23 +1117,33 @@ __global__ void __launch_bounds__(1024) k_diag_sync(int iters, int mode, double*
    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = acc;
 }
 
+// peer-memory exchange of the velocity-row vectors the momentum SpMV gathers (partitioned runs)
+struct XVel {
+   double* const* peerV;   // [npeers] start of MY block inside the peer's ghost range of its ph region (shv region: + 3 * peerLd)
+   const int* peerLd;      // [npeers] the peer's component stride (its local NN)
+   const int* pushPtr;     // [n+1] CSR of (peer index, slot) pushes per owned velocity node
+   const int2* pushDst;
+};
 struct BicgArgs {
    Sell A;
    const int* part;   // per-block slice ranges of the static share
    int dynStart;      // first slice handed out through dynCounter (0 = everything dynamic)
    int* dynCounter;   // NULL = everything static
    int vidx;
-   int n;
-   const double* b;   // [3][n]
-   double* x;         // [3][n]
-   double* w;         // work: r, rs, p, ph, AMp, sh, AMs, xbest  -> 8 x [3][n]
+   int n;             // rows (owned velocity nodes)
+   long long ld;      // component stride of every vector below (local velocity nodes, owned + ghost)
+   const double* b;   // [3][ld]
+   double* x;         // [3][ld]
+   double *r, *rs, *p, *ph, *AMp, *shv, *AMs, *xbest;   // work vectors [3][ld]; DIST: ph and shv live in the exchange window
    const double* dinv;
-   double* scratch;   // 2 buffers x 6 x gridDim
+   double* scratch;   // 3 buffers x 6 x gridDim
    double* info;      // see kBicgInfo*
    double tol;
    int maxit;
    int halfstep;      // 1 = also test the residual after the half step (cusp::krylov::bicgstab); 0 = once per iteration (PARALUTION)
    int verify;        // 1 = accept a solve only on its TRUE residual |b - A x|; restart from it otherwise
+   XComm xc;          // DIST only
+   XVel xv;           // DIST only
 };
 // result slots inside cfd_ctx::kinfo (doubles)
 enum { kBicgInfoIts = 3, kBicgInfoRR = 6, kBicgInfoTrue = 9, kBicgInfoBB = 12, kBicgInfoFin = 15, kBicgInfoRestarts = 18, kBicgInfoPasses = 21,
@@ -1144,7 +1155,7 @@ enum { kBicgInfoIts = 3, kBicgInfoRR = 6, kBicgInfoTrue = 9, kBicgInfoBB = 12, k
 // Specialised on NA so that the common late phase (one slow system left) runs a lean single-vector loop
 // with four matrix pairs in flight per lane.
 template <int NA, bool RES>
-__device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int dynStart, int* dynCounter, const double* __restrict__ val, int n,
+__device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int dynStart, int* dynCounter, const double* __restrict__ val, int n, long long ld,
                                              const double* in, double* out, const int (&sys)[3], const double* l1, double (&d0)[3], double (&d1)[3],
                                              int gwarp, int nwarps, int lane) {
    const int T = A.T, sub = lane % T;
@@ -1159,7 +1170,7 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int
    size_t base[NA];
    double s0[NA], s1[NA];   // dot-product partials stay in registers (no dynamically indexed local arrays in the loop)
 #pragma unroll
-   for (int q = 0; q < NA; q++) { base[q] = (size_t)sys[q] * n; s0[q] = 0.0; s1[q] = 0.0; }
+   for (int q = 0; q < NA; q++) { base[q] = (size_t)sys[q] * (size_t)ld; s0[q] = 0.0; s1[q] = 0.0; }
    int next = sr.begin;
    while (true) {
       int s;
@@ -1212,9 +1223,9 @@ __device__ __forceinline__ void bicg_spmv_phase(const BicgArgs& a, const double*
    int sys[3] = {0, 0, 0}, na = 0;
    for (int c = 0; c < 3; c++)
       if (act[c]) sys[na++] = c;
-   if (na == 1) bicg_spmv_na<1, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 2) bicg_spmv_na<2, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
-   else if (na == 3) bicg_spmv_na<3, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   if (na == 1) bicg_spmv_na<1, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, a.ld, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 2) bicg_spmv_na<2, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, a.ld, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
+   else if (na == 3) bicg_spmv_na<3, RES>(a.A, a.part, a.dynStart, a.dynCounter, val, a.n, a.ld, in, out, sys, l1, d0, d1, gwarp, nwarps, lane);
 }
 
 // Jacobi-preconditioned BiCGStab for the three momentum systems in lock-step (replaces 3 calls of
@@ -1239,6 +1250,22 @@ struct BicgScalars {
    int todo[3];   // after a check: 0 nothing, 1 restart, 3 restart + remember x as the best iterate, 2 give back the best iterate
    int passes;
 };
+
+// DIST: store a freshly computed entry of ph (which = 0) or shv (which = 1) into the ghost copies the neighbours hold
+__device__ __forceinline__ void bicg_push(const BicgArgs& a, int which, int c, int i, double v) {
+   for (int e = a.xv.pushPtr[i]; e < a.xv.pushPtr[i + 1]; e++) {
+      const int2 d = a.xv.pushDst[e];
+      st_sys_f64(a.xv.peerV[d.x] + (size_t)(which * 3 + c) * (size_t)a.xv.peerLd[d.x] + d.y, v);
+   }
+}
+
+// DIST = true (partitioned runs): the same kernel as a fused compute + collective over peer memory.  ph and shv -- the vectors
+// the two SpMV phases gather -- live in this rank's exchange window; the passes that produce them store interface values
+// straight into the neighbours' ghost entries over NVLink, every reduction is the fused cross-GPU barrier xgrid_sum (which
+// also publishes the pushes made before it), and the one hand-over without a reduction (after the p update) is a flag
+// exchange.  All ranks see bit-identical scalars, take the same branches and leave together.  No NCCL call and no host
+// round trip inside the solve (round 1: 4 ncclAllReduce + 2 halo swaps + 7 launches per iteration, driven from the host).
+template <bool DIST>
 __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    cg::grid_group grid = cg::this_grid();
    __shared__ double sh[6 * 32];
@@ -1250,30 +1277,40 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    double* buf1 = a.scratch + 6 * (size_t)gridDim.x;
    double* buf2 = a.scratch + 12 * (size_t)gridDim.x;   // the true-residual check has its own (it may run between any two others)
    const int n = a.n;
-   const size_t N3 = 3 * (size_t)n;
-   double* r = a.w;
-   double* rs = a.w + N3;
-   double* p = a.w + 2 * N3;
-   double* ph = a.w + 3 * N3;    // M p
-   double* AMp = a.w + 4 * N3;
-   double* shv = a.w + 5 * N3;   // M s
-   double* AMs = a.w + 6 * N3;
-   double* xbest = a.w + 7 * N3;
+   const size_t ld = (size_t)a.ld;
+   double *r = a.r, *rs = a.rs, *p = a.p, *ph = a.ph, *AMp = a.AMp, *shv = a.shv, *AMs = a.AMs, *xbest = a.xbest;
+   unsigned long long epoch = 0, hepoch = 0;
+   if (DIST) { epoch = a.xc.xstate[0]; hepoch = a.xc.xstate[1]; }
+   // grid-wide (DIST: cross-GPU) sum; false = a peer timed out: leave at once
+#define BICG_SUM(NV, v, buf) (DIST ? xgrid_sum<NV>(v, buf, sh, a.xc, epoch) : (grid_sum<NV>(grid, v, buf, sh), true))
+   // hand-over of pushed values without a reduction: flags + local grid sync
+#define BICG_HANDOVER()                                   \
+   do {                                                   \
+      if (DIST) {                                         \
+         hepoch++;                                        \
+         pcgcg_signal(a.xc, hepoch);                      \
+         grid.sync();                                     \
+         if (!pcgcg_wait(a.xc, hepoch)) return;           \
+      } else grid.sync();                                 \
+   } while (0)
 
    double v6[6] = {0, 0, 0, 0, 0, 0}, v3[3];
    for (int c = 0; c < 3; c++) {
       double acc = 0.0;
       for (int i = tid; i < n; i += nthreads) {
-         const size_t k = (size_t)c * n + i;
+         const size_t k = (size_t)c * ld + i;
          const double bi = a.b[k];
          a.x[k] = 0.0;
          r[k] = bi; rs[k] = bi; p[k] = bi;
-         ph[k] = a.dinv[i] * bi;
+         const double phi = a.dinv[i] * bi;
+         ph[k] = phi;
+         if (DIST) bicg_push(a, 0, c, i, phi);
          acc += bi * bi;
       }
       v6[c] = acc;
    }
-   grid_sum<6>(grid, v6, buf0, sh);
+   if (DIST) __threadfence_system();
+   if (!BICG_SUM(6, v6, buf0)) return;
    if (threadIdx.x == 0) {
       for (int c = 0; c < 3; c++) {
          S.bb[c] = S.rr[c] = S.rrs[c] = v6[c];
@@ -1310,11 +1347,23 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       __syncthreads();
       if (S.chk[0] | S.chk[1] | S.chk[2]) {
          // ---- true residual of the candidates: AMs = b - A x, |AMs|^2
+         if (DIST) {   // x of the candidates goes through shv (free at this point) so that the neighbours' values can be gathered
+            for (int c = 0; c < 3; c++) {
+               if (!S.chk[c]) continue;
+               for (int i = tid; i < n; i += nthreads) {
+                  const size_t k = (size_t)c * ld + i;
+                  const double xi = a.x[k];
+                  shv[k] = xi;
+                  bicg_push(a, 1, c, i, xi);
+               }
+            }
+            BICG_HANDOVER();
+         }
          double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
          const bool chk[3] = {S.chk[0] != 0, S.chk[1] != 0, S.chk[2] != 0};
-         bicg_spmv_phase<true>(a, a.x, AMs, chk, a.b, d0, d1, gwarp, nwarps, lane);
+         bicg_spmv_phase<true>(a, DIST ? shv : a.x, AMs, chk, a.b, d0, d1, gwarp, nwarps, lane);
          v3[0] = d1[0]; v3[1] = d1[1]; v3[2] = d1[2];
-         grid_sum<3>(grid, v3, buf2, sh);
+         if (!BICG_SUM(3, v3, buf2)) return;
          if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
          if (threadIdx.x == 0) {
             S.passes++;
@@ -1346,16 +1395,18 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
                const int todo = S.todo[c];
                if (!todo) continue;
                for (int i = tid; i < n; i += nthreads) {
-                  const size_t k = (size_t)c * n + i;
+                  const size_t k = (size_t)c * ld + i;
                   if (todo == 2) { a.x[k] = xbest[k]; continue; }
                   const double ri = AMs[k];
                   r[k] = ri; rs[k] = ri; p[k] = ri;
-                  ph[k] = a.dinv[i] * ri;
+                  const double phi = a.dinv[i] * ri;
+                  ph[k] = phi;
+                  if (DIST) bicg_push(a, 0, c, i, phi);
                   if (todo == 3) xbest[k] = a.x[k];
                }
             }
          }
-         grid.sync();   // ph of the restarted systems is gathered by every block; the slice counter is reset for everybody
+         BICG_HANDOVER();   // ph of the restarted systems is gathered by every block; the slice counter is reset for everybody
       }
       if (!S.act[0] && !S.act[1] && !S.act[2]) break;
       // ---- AMp = A (M p), d0 = rs . AMp
@@ -1366,7 +1417,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          v3[0] = d0[0]; v3[1] = d0[1]; v3[2] = d0[2];
       }
       BICG_TICK(0);
-      grid_sum<3>(grid, v3, buf1, sh);
+      if (!BICG_SUM(3, v3, buf1)) return;
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;   // every block is past the SpMV phase
       BICG_TICK(1);
       // Breakdowns (the reference's libraries have no guards and hand back NaN fields): a non-finite alpha leaves x untouched, a
@@ -1388,17 +1439,20 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          if (S.act[c] && !S.brk[c]) {
             const double alpha = S.alpha[c];
             for (int i = tid; i < n; i += nthreads) {
-               const size_t k = (size_t)c * n + i;
+               const size_t k = (size_t)c * ld + i;
                const double si = r[k] - alpha * AMp[k];
                r[k] = si;
-               shv[k] = a.dinv[i] * si;
+               const double shi = a.dinv[i] * si;
+               shv[k] = shi;
+               if (DIST) bicg_push(a, 1, c, i, shi);
                acc += si * si;
             }
          }
          v3[c] = acc;
       }
+      if (DIST) __threadfence_system();   // the reduction that follows publishes the pushes
       BICG_TICK(2);
-      grid_sum<3>(grid, v3, buf0, sh);
+      if (!BICG_SUM(3, v3, buf0)) return;
       BICG_TICK(3);
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) {   // converged at the half step (cusp::krylov::bicgstab): x += alpha M p, no iteration counted
@@ -1417,7 +1471,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
             v6[0] = d0[0]; v6[1] = d0[1]; v6[2] = d0[2]; v6[3] = d1[0]; v6[4] = d1[1]; v6[5] = d1[2];
          }
          BICG_TICK(4);
-         grid_sum<6>(grid, v6, buf1, sh);
+         if (!BICG_SUM(6, v6, buf1)) return;
          if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
          BICG_TICK(5);
          if (threadIdx.x == 0) {
@@ -1436,12 +1490,12 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          const double alpha = S.alpha[c], omega = S.omega[c];
          if (S.half[c]) {
             for (int i = tid; i < n; i += nthreads) {
-               const size_t k = (size_t)c * n + i;
+               const size_t k = (size_t)c * ld + i;
                a.x[k] += alpha * ph[k];
             }
          } else if (S.act2[c]) {
             for (int i = tid; i < n; i += nthreads) {
-               const size_t k = (size_t)c * n + i;
+               const size_t k = (size_t)c * ld + i;
                a.x[k] += alpha * ph[k] + omega * shv[k];
                const double ri = r[k] - omega * AMs[k];
                r[k] = ri;
@@ -1452,7 +1506,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          v6[c] = a0; v6[3 + c] = a1;
       }
       BICG_TICK(6);
-      if (S.act2[0] | S.act2[1] | S.act2[2]) grid_sum<6>(grid, v6, buf0, sh);
+      if (S.act2[0] | S.act2[1] | S.act2[2]) { if (!BICG_SUM(6, v6, buf0)) return; }
       BICG_TICK(7);
       // ---- p = r + beta (p - omega AMp) ; ph = M p
       for (int c = 0; c < 3; c++) {
@@ -1461,10 +1515,12 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          const double beta = (v6[c] / S.rrs[c]) * (S.alpha[c] / omega);
          if (!isfinite(beta) || v6[c] == 0.0) continue;   // rho = 0: breakdown, handled below
          for (int i = tid; i < n; i += nthreads) {
-            const size_t k = (size_t)c * n + i;
+            const size_t k = (size_t)c * ld + i;
             const double pi = r[k] + beta * (p[k] - omega * AMp[k]);
             p[k] = pi;
-            ph[k] = a.dinv[i] * pi;
+            const double phi = a.dinv[i] * pi;
+            ph[k] = phi;
+            if (DIST) bicg_push(a, 0, c, i, phi);
          }
       }
       __syncthreads();   // every thread has read S.rrs before thread 0 replaces it
@@ -1476,13 +1532,15 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
                S.rrs[c] = v6[c]; S.rr[c] = v6[3 + c]; S.its[c]++;
             }
          }
-      grid.sync();
+      BICG_HANDOVER();
       BICG_TICK(8);
 #ifdef CFD_BICG_PHASE_TIMERS
       nit++;
 #endif
    }
 #undef BICG_TICK
+#undef BICG_SUM
+#undef BICG_HANDOVER
 #ifdef CFD_BICG_PHASE_TIMERS
    if (tid == 0) {
       for (int k = 0; k < 9; k++) a.info[kBicgInfoTimers + k] = (double)tph[k];
@@ -1499,6 +1557,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          a.info[kBicgInfoRestarts + c] = (double)S.restarts[c];
       }
       a.info[kBicgInfoPasses] = (double)S.passes;
+      if (DIST) { a.xc.xstate[0] = epoch; a.xc.xstate[1] = hepoch; a.xc.xstate[3] = 0; a.xc.xstate[4] = 0; }
    }
 }
 
@@ -2200,10 +2259,12 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       c->remotePoff.assign(P->remotePoff ? P->remotePoff : P->recvPoff, (P->remotePoff ? P->remotePoff : P->recvPoff) + np);
       // exchange window for the peer-memory path: flags | mailboxes | p  (p moves into the window)
       c->winOffP = kWinHeader;
-      c->winBytes = (size_t)kWinHeader + sizeof(double) * (size_t)NNp;
+      c->winOffV = kWinHeader + (long long)sizeof(double) * (((long long)NNp + 15) & ~15LL);
+      c->winBytes = (size_t)c->winOffV + (P->scheme == CFD_IMPLICIT ? sizeof(double) * 6 * (size_t)NN : 0);
       CFD_CK(cudaMalloc((void**)&c->win, c->winBytes));
       CFD_CK(cudaMemset(c->win, 0, c->winBytes));
       c->cg_p = (double*)(c->win + c->winOffP);
+      if (P->scheme == CFD_IMPLICIT) { c->bw_ph = (double*)(c->win + c->winOffV); c->bw_shv = c->bw_ph + 3 * (size_t)NN; }
       TRY(dalloc(c, &c->xstate, 8));
       if (const char* e = getenv("CFD_P2P_TIMEOUT_MS")) c->p2pTimeoutNs = (unsigned long long)std::max(1.0, atof(e)) * 1000000ull;
    }
@@ -2222,7 +2283,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       c->pcg_blocks = std::min(blocks, c->numSMs * occ);
       if (const char* e = getenv("CFD_PCG_BLOCKS")) c->pcg_blocks = std::max(1, std::min(atoi(e), c->numSMs * occ));
       int occ2 = 0;
-      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_bicgstab3, c->bicg_threads, 0));
+      CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, parted ? k_bicgstab3<true> : k_bicgstab3<false>, c->bicg_threads, 0));
       if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
       const int needed2 = (int)std::max<long long>(1, ((long long)c->K.nslices * 32 + c->bicg_threads - 1) / c->bicg_threads);
       int blocks2 = c->numSMs * occ2;
@@ -2328,6 +2389,8 @@ int cfd_p2p_export(cfd_ctx* c, char desc[96]) {
    CFD_CK(cudaIpcGetMemHandle(&h, c->win));
    memcpy(desc, &h, sizeof h);
    memcpy(desc + 64, &c->winOffP, sizeof(long long));
+   memcpy(desc + 72, &c->winOffV, sizeof(long long));
+   memcpy(desc + 80, &c->P.NN, sizeof(int));
    return CFD_OK;
 }
 
@@ -2339,8 +2402,12 @@ int cfd_p2p_attach(cfd_ctx* c, const char* all) {
    CFD_CK(cudaSetDevice(c->device));
    c->peerWin.assign(world, nullptr);
    c->peerOffP.assign(world, 0);
+   c->peerOffV.assign(world, 0);
+   c->peerNN.assign(world, 0);
    for (int q = 0; q < world; q++) {
       memcpy(&c->peerOffP[q], all + 96 * q + 64, sizeof(long long));
+      memcpy(&c->peerOffV[q], all + 96 * q + 72, sizeof(long long));
+      memcpy(&c->peerNN[q], all + 96 * q + 80, sizeof(int));
       if (q == rank) { c->peerWin[q] = c->win; continue; }
       cudaIpcMemHandle_t h;
       memcpy(&h, all + 96 * q, sizeof h);
@@ -2371,6 +2438,31 @@ int cfd_p2p_attach(cfd_ctx* c, const char* all) {
    if ((rc = dupload(c, &c->dPeerRank, c->peerRank.data(), c->peerRank.size()))) return rc;
    if ((rc = dupload(c, &c->pushPtrP, ptr.data(), ptr.size()))) return rc;
    if ((rc = dupload(c, &c->pushDstP, dst.data(), dst.size()))) return rc;
+   if (c->P.scheme == CFD_IMPLICIT) {
+      // the same for the velocity-row vectors of the momentum solve (ph | shv inside the windows)
+      const int NNo = c->NNo;
+      std::vector<double*> peerV(np);
+      std::vector<int> peerLd(np);
+      for (int j = 0; j < np; j++) {
+         peerV[j] = (double*)(c->peerWin[c->peerRank[j]] + c->peerOffV[c->peerRank[j]]) + c->remoteVoff[j];
+         peerLd[j] = c->peerNN[c->peerRank[j]];
+      }
+      std::vector<int> sendV((size_t)c->sendVptr[np]);
+      CFD_CK(cudaMemcpy(sendV.data(), c->sendVidx, sizeof(int) * sendV.size(), cudaMemcpyDeviceToHost));
+      std::vector<int> pv((size_t)NNo + 1, 0);
+      for (int t = 0; t < (int)sendV.size(); t++) pv[sendV[t] + 1]++;
+      for (int i = 0; i < NNo; i++) pv[i + 1] += pv[i];
+      std::vector<int2> dv((size_t)pv[NNo]);
+      {
+         std::vector<int> fill(pv.begin(), pv.end() - 1);
+         for (int j = 0; j < np; j++)
+            for (int t = c->sendVptr[j]; t < c->sendVptr[j + 1]; t++) dv[fill[sendV[t]]++] = make_int2(j, t - c->sendVptr[j]);
+      }
+      if ((rc = dupload(c, &c->dPeerV, peerV.data(), peerV.size()))) return rc;
+      if ((rc = dupload(c, &c->dPeerLd, peerLd.data(), peerLd.size()))) return rc;
+      if ((rc = dupload(c, &c->pushPtrV, pv.data(), pv.size()))) return rc;
+      if ((rc = dupload(c, &c->pushDstV, dv.data(), dv.size()))) return rc;
+   }
    std::vector<int> iface;
    for (int i = 0; i < NPo; i++)
       if (ptr[i + 1] > ptr[i]) iface.push_back(i);
@@ -2593,20 +2685,30 @@ int gq_step1GPU(cfd_ctx* c) {
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
-   if (parted(c)) {
+   if (parted(c) && !c->p2p) {
       int rcd = run_bicg_dist(c);
       if (rcd) return rcd;
       return halo(c, c->Uk, true);   // gathered by step 2 (G^T Uk) and, as Uk_prev, by the next step
    }
    {
+      const bool dist = parted(c);
+      const size_t N3 = 3 * (size_t)NN;
       BicgArgs a;
-      a.A = c->K; a.part = c->bicgPart; a.dynStart = c->bicgDynStart; a.dynCounter = c->bicgDynCounter; a.vidx = 2; a.n = NN; a.b = c->R1i; a.x = c->Uk; a.w = c->bw; a.dinv = c->Adinv; a.scratch = c->partials;
+      a.A = c->K; a.part = c->bicgPart; a.dynStart = c->bicgDynStart; a.dynCounter = c->bicgDynCounter; a.vidx = 2; a.n = c->NNo; a.ld = NN;
+      a.b = c->R1i; a.x = c->Uk; a.dinv = c->Adinv; a.scratch = c->partials;
+      a.r = c->bw; a.rs = c->bw + N3; a.p = c->bw + 2 * N3; a.AMp = c->bw + 3 * N3; a.AMs = c->bw + 4 * N3; a.xbest = c->bw + 5 * N3;
+      a.ph = dist ? c->bw_ph : c->bw + 6 * N3; a.shv = dist ? c->bw_shv : c->bw + 7 * N3;
       a.info = c->kinfo; a.tol = c->opt.bicg_tol; a.maxit = c->opt.bicg_maxit;
       a.halfstep = c->opt.bicg_no_halfstep ? 0 : 1; a.verify = c->opt.bicg_no_verify ? 0 : 1;
+      memset(&a.xc, 0, sizeof a.xc); memset(&a.xv, 0, sizeof a.xv);
+      if (dist) {
+         fill_xcomm(c, a.xc);
+         a.xv.peerV = c->dPeerV; a.xv.peerLd = c->dPeerLd; a.xv.pushPtr = c->pushPtrV; a.xv.pushDst = c->pushDstV;
+      }
       void* args[] = {&a};
       ProfScope ps(c, "bicgstab", 0.0);
       c->lastBicgRec = ps.idx;
-      CFD_CK(cudaLaunchCooperativeKernel((void*)k_bicgstab3, dim3(c->bicg_blocks), dim3(c->bicg_threads), args, 0, c->stream));
+      CFD_CK(cudaLaunchCooperativeKernel(dist ? (void*)k_bicgstab3<true> : (void*)k_bicgstab3<false>, dim3(c->bicg_blocks), dim3(c->bicg_threads), args, 0, c->stream));
       c->launches++;
 #ifdef CFD_BICG_PHASE_TIMERS
       {
@@ -2620,7 +2722,7 @@ int gq_step1GPU(cfd_ctx* c) {
       }
 #endif
    }
-   return CFD_OK;
+   return halo(c, c->Uk, true);   // partitioned runs: gathered by step 2 (G^T Uk) and, as Uk_prev, by the next step
 }
 
 int gq_step2GPU(cfd_ctx* c) {

@@ -116,7 +116,8 @@ struct cfd_ctx {
    double *Uk = nullptr, *Uk_prev = nullptr, *Pk = nullptr, *Pk_prev = nullptr, *Pk_prevprev = nullptr, *Pdiff = nullptr;
    double* R1i = nullptr;       // [3][NN] the three momentum right-hand sides
    double* Adinv = nullptr;     // [NN]
-   double* bw = nullptr;        // BiCGStab work: 8 x [3][NN]
+   double* bw = nullptr;        // BiCGStab work: 8 x [3][NN] (partitioned: 6, ph and shv live in the exchange window)
+   double *bw_ph = nullptr, *bw_shv = nullptr;
    // Krylov work
    double *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr, *cg_s = nullptr, *cg_pp = nullptr;   // (cg_s, cg_pp: single-reduction form only)
    int cg_variant = 1;          // 1 classical, 2 Chronopoulos-Gear (resolved from cfd_options.cg_variant at init)
@@ -162,13 +163,18 @@ struct cfd_ctx {
    bool p2p = false;
    char* win = nullptr;             // this rank's window: flags | mailboxes | p
    size_t winBytes = 0;
-   long long winOffP = 0;
+   long long winOffP = 0, winOffV = 0;   // byte offsets of the pressure vector and of ph | shv inside the window
    std::vector<char*> peerWin;      // [world] mapped peer windows (own included)
-   std::vector<long long> peerOffP; // [world]
+   std::vector<long long> peerOffP, peerOffV; // [world]
+   std::vector<int> peerNN;         // [world] local velocity-node counts (component strides) of the peers
    char** dPeerWin = nullptr;       // device copy
    double** dPeerP = nullptr;       // [nPeers] start of my block inside each peer's p ghosts
    int* dPeerRank = nullptr;
    int* pushPtrP = nullptr;         // [NPo+1] CSR of (peer, slot) pushes per owned pressure DOF
+   int* pushPtrV = nullptr;         // same for the owned velocity nodes
+   int2* pushDstV = nullptr;
+   double** dPeerV = nullptr;       // [nPeers] start of my block inside each peer's ph ghosts
+   int* dPeerLd = nullptr;          // [nPeers]
    int* ifaceP = nullptr;           // owned pressure DOFs with at least one push (done first, so the transfer overlaps the rest)
    int nIfaceP = 0;
    unsigned long long p2pTimeoutNs = 4000000000ull;
