@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(256) k_max_abs_diff3(int n, long long ld, cons
 // stored straight into the neighbours' ghost entries over NVLink, dot products are all-reduced through mailboxes in
 // the peers' windows; ordering by system-scope release/acquire flags carrying monotonically increasing epochs.
 // =================================================================================================
-enum { kWinFlagsBytes = 4096, kWinMailBytes = 12288, kWinHeader = 16384, kMaxRanks = 64 };
+// window header: 4 KiB of flags, then 3 (slots) x 64 (ranks) mailboxes of 16 words (128 B: up to 8 doubles as flag-in-data word pairs)
+enum { kWinFlagsBytes = 4096, kWinMailWords = 16, kWinMailBytes = 3 * 64 * 16 * 8, kWinHeader = 32768, kMaxRanks = 64 };
 
 struct XComm {
    int world, rank, npeers;
@@ -354,7 +355,7 @@ struct XComm {
 };
 __device__ __forceinline__ unsigned long long* win_arflag(char* w, int slot, int src) { return (unsigned long long*)w + slot * kMaxRanks + src; }
 __device__ __forceinline__ unsigned long long* win_haloflag(char* w, int src) { return (unsigned long long*)w + 3 * kMaxRanks + src; }
-__device__ __forceinline__ double* win_mail(char* w, int slot, int src) { return (double*)(w + kWinFlagsBytes) + (slot * kMaxRanks + src) * 8; }
+__device__ __forceinline__ double* win_mail(char* w, int slot, int src) { return (double*)(w + kWinFlagsBytes) + (slot * kMaxRanks + src) * kWinMailWords; }
 
 __device__ __forceinline__ void st_rel_sys(unsigned long long* p, unsigned long long v) {
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -397,7 +398,7 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
    return v;
 }
 
-// Sum N (<= 4) values over all blocks of all ranks; the result is bit-identical in every block of every rank
+// Sum N (<= 8) values over all blocks of all ranks; the result is bit-identical in every block of every rank
 // (local partials in a fixed order, then ranks in rank order), so every block takes the same branches.
 // One fused barrier instead of "local grid reduction, then exchange":
 //   * every block publishes its partial and takes a ticket; the LAST block to arrive reduces the partials and
@@ -414,6 +415,7 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 // grid-wide or cross-GPU synchronisation; every block of every rank runs into the same time-out or sees the error word).
 template <int N>
 __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* sh, const XComm& xc, unsigned long long& epoch) {
+   static_assert(2 * N <= kWinMailWords, "mailbox too small for this many values");
    __shared__ int s_last, s_fail;
    block_sum<N>(v, sh);
    epoch++;
