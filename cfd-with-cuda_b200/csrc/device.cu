@@ -1885,9 +1885,13 @@ int fetch_kinfo(cfd_ctx* c) {
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
    if (c->p2p && c->xstate) {   // a peer that never arrived: the spin-waits of k_pcg_p2p give up after 4 s and raise this word
-      unsigned long long err = 0;
-      CFD_CK(cudaMemcpy(&err, c->xstate + 2, sizeof err, cudaMemcpyDeviceToHost));
-      if (err) { set_error("peer-memory exchange timed out (a rank stopped participating)"); return CFD_ERR_STATE; }
+      unsigned long long err[6] = {0, 0, 0, 0, 0, 0};
+      CFD_CK(cudaMemcpy(err, c->xstate + 2, sizeof err, cudaMemcpyDeviceToHost));
+      if (err[0]) {
+         set_error("peer-memory exchange timed out (a rank stopped participating) [rank %d waited for %s: code %llu, epoch %llu, last value seen 0x%llx]",
+                   c->P.rank, (err[3] & 15) == 1 ? "a neighbour's halo flag" : "the all-reduce words", err[3] >> 4, err[4], err[5]);
+         return CFD_ERR_STATE;
+      }
    }
    // algorithmic bytes of the Krylov launches are known only now (iteration counts): DESIGN.md byte model
    if (c->lastPcgRec >= 0) {

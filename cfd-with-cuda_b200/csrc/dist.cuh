@@ -377,13 +377,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
    return t;
 }
 // Spin until *f >= want; false after the time-out (a peer died) or when another block already raised the error word.
+// (err[0] = error word; on the first time-out err[3..5] = what was waited for: 1 = halo flag | wanted epoch | value seen)
 __device__ __forceinline__ bool wait_flag(const unsigned long long* f, unsigned long long want, unsigned long long* err, unsigned long long timeoutNs) {
    const unsigned long long t0 = gtimer();
    unsigned spins = 0;
-   while (ld_acq_sys(f) < want) {
+   unsigned long long seen;
+   while ((seen = ld_acq_sys(f)) < want) {
       if ((++spins & 255u) == 0) {
          if (*(volatile unsigned long long*)err) return false;
-         if (gtimer() - t0 > timeoutNs) { *(volatile unsigned long long*)err = 1; return false; }
+         if (gtimer() - t0 > timeoutNs) {
+            if (atomicCAS(err, 0ull, 1ull) == 0ull) { err[3] = 1; err[4] = want; err[5] = seen; }
+            return false;
+         }
       }
    }
    return true;
@@ -468,7 +473,10 @@ __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* s
                if ((lo >> 32) == (tag >> 32) && (hi >> 32) == (tag >> 32)) break;
                if ((++spins & 255u) == 0) {
                   if (*(volatile unsigned long long*)(xc.xstate + 2)) ok = false;
-                  else if (gtimer() - t0 > xc.timeoutNs) { *(volatile unsigned long long*)(xc.xstate + 2) = 1; ok = false; }
+                  else if (gtimer() - t0 > xc.timeoutNs) {
+                     if (atomicCAS(xc.xstate + 2, 0ull, 1ull) == 0ull) { xc.xstate[5] = 2 + 16 * (unsigned long long)(N * 64 + threadIdx.x); xc.xstate[6] = epoch; xc.xstate[7] = lo; }
+                     ok = false;
+                  }
                }
             }
             mine[i] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));

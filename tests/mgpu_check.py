@@ -15,6 +15,8 @@ cases = [(dict(nx=8, NENv=27), 'explicit', 3, {}), (dict(nx=12, NENv=8), 'implic
          (dict(nx=8, NENv=27, cluster=2.0), 'implicit', 2, dict(cg_tol=1e-12, bicg_tol=1e-12, cg_maxit=5000, bicg_maxit=5000)),
          (dict(nx=12, NENv=8), 'explicit', 2, {})]
 variants = [int(v) for v in os.environ.get('CG_VARIANTS', '0').split(',')]
+if os.environ.get('CASES'):
+    cases = [cases[int(k)] for k in os.environ['CASES'].split(',')]
 for (cav, scheme, steps, kw), variant in [(cs, v) for cs in cases for v in variants]:
     opts = fracstep.options(device=lr, cg_variant=variant, **kw)
     s = fracstep.Solver(scheme=scheme, cavity=cav, opts=opts, world=world, rank=rank)
