@@ -344,7 +344,15 @@ def main():
     e2e_ms = float(t.item())
     normU2, normP2 = global_norms()
 
+    def finish():
+        if dist is not None:
+            fracstep.teardown_distributed(s, dist)
+            dist.destroy_process_group()
+        else:
+            s.close()
+
     if rank != 0:
+        finish()
         return 0
     n_rep = 1       # one partitioned job over all ranks (strong scaling: the mesh is fixed, each rank holds an element block)
     peak, peak_src = measured_peak()
@@ -393,9 +401,7 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(w, 3, 1)
     print(json.dumps(line))
-    s.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    finish()
     return 0
 
 

@@ -2476,6 +2476,17 @@ int cfd_p2p_attach(cfd_ctx* c, const char* all) {
    return p2p_agree(c);
 }
 
+int cfd_p2p_detach(cfd_ctx* c) {
+   if (!c) return CFD_ERR_ARG;
+   CFD_CK(cudaSetDevice(c->device));
+   if (c->stream) CFD_CK(cudaStreamSynchronize(c->stream));
+   for (size_t q = 0; q < c->peerWin.size(); q++)
+      if (c->peerWin[q] && c->peerWin[q] != c->win) cudaIpcCloseMemHandle(c->peerWin[q]);
+   c->peerWin.clear();
+   c->p2p = false;
+   return CFD_OK;
+}
+
 int cfd_p2p_reset(cfd_ctx* c) {
    if (!c) return CFD_ERR_ARG;
    if (!c->win) { set_error("no exchange window (context is not partitioned)"); return CFD_ERR_STATE; }

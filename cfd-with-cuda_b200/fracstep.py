@@ -122,6 +122,7 @@ def lib():
     L.cfd_csr_pcg.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, _ip, _dp]
     L.cfd_csr_pcg_variant.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp]
     L.cfd_p2p_reset.argtypes = [vp]
+    L.cfd_p2p_detach.argtypes = [vp]
     L.cfd_solver_create_from_inp.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
     L.cfd_solver_create_cavity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                            C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
@@ -530,6 +531,17 @@ def setup_distributed(solver, dist, torch, peer_memory=True):
         dist.all_gather(allb, mine)
         solver.p2p_attach(b"".join(t.cpu().numpy().tobytes() for t in allb))
         dist.barrier()
+
+
+def teardown_distributed(solver, dist):
+    """Orderly end of a partitioned run: every rank unmaps its peers' exchange windows, the ranks meet, then the solver (and with
+    it this rank's own window) is destroyed -- exported memory must not be freed while a peer still has it mapped."""
+    ch = solver.L.cfd_solver_ctx(solver.h)
+    if ch:
+        _check(solver.L.cfd_p2p_detach(C.c_void_p(ch)))
+    dist.barrier()
+    solver.close()
+    dist.barrier()
 
 
 def nccl_unique_id():

@@ -157,6 +157,11 @@ int cfd_p2p_attach(cfd_ctx* ctx, const char* all_desc /* [world][96] */);
  * default 4000): zero this rank's exchange window and epochs.  Collective in the sense that EVERY rank must call it, with a
  * host-side barrier before and after, before the contexts are used again. */
 int cfd_p2p_reset(cfd_ctx* ctx);
+/* Orderly teardown of the peer-memory path: unmaps the peers' windows (this rank's own window stays until cfd_destroy).
+ * Call on EVERY rank, then synchronise the ranks on the host (barrier), then destroy the contexts: CUDA forbids freeing
+ * exported memory while another process still has it mapped.  (cfd_destroy unmaps on its own if this was not called, which is
+ * only safe when the peers are known to be gone.) */
+int cfd_p2p_detach(cfd_ctx* ctx);
 
 /* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
  * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);

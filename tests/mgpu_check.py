@@ -41,6 +41,6 @@ for (cav, scheme, steps, kw), variant in [(cs, v) for cs in cases for v in varia
         print('   part: iter', [r['iter'] for r in reps], 'cg', [r['cg_iterations'] for r in reps], 'bicg', [r['bicg_iterations'] for r in reps], 'mon', reps[-1]['monitor'], 'maxAcc', reps[-1]['maxAcc'])
         print('   single: iter', [r['iter'] for r in gre], 'cg', [r['cg_iterations'] for r in gre], 'bicg', [r['bicg_iterations'] for r in gre], 'mon', gre[-1]['monitor'], 'maxAcc', gre[-1]['maxAcc'])
         g.close()
-    s.close()
+    fracstep.teardown_distributed(s, dist)
 dist.barrier()
 dist.destroy_process_group()
