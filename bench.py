@@ -257,6 +257,14 @@ def main():
     import numpy as np
     import torch
     import fracstep
+    if os.environ.get("BENCH_WATCHDOG_S"):   # diagnostics: dump every thread's Python stack and exit if the run takes longer than this
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG_S"]), exit=True)
+    t_start = time.time()
+
+    def stage(msg):
+        if os.environ.get("BENCH_VERBOSE"):
+            print("[bench rank %d %7.1f s] %s" % (rank, time.time() - t_start, msg), file=sys.stderr, flush=True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -285,6 +293,7 @@ def main():
         #  its neighbours through peer memory; CFD_NO_P2P=1 keeps the host-driven NCCL version)
         fracstep.setup_distributed(s, dist, torch, peer_memory=True)
     setup_s = time.time() - t0
+    stage('set-up done')
     c = s.ctx
 
     def barrier():
@@ -298,6 +307,7 @@ def main():
     # the state the timed region starts from, kept on the host so that the end-to-end leg repeats the SAME K steps
     state_names = ("Un", "Pn", "Unp1_prev") if w["scheme"] == "explicit" else ("Uk_prev", "Pk_prev", "Pk_prevprev")
     state0 = {nm: c.download(nm) for nm in state_names}
+    stage('warm-up done')
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -324,6 +334,7 @@ def main():
         return float(v[0].sqrt().item()), float(v[1].sqrt().item())
 
     normU, normP = global_norms()
+    stage('timed region done')
 
     # ---- end to end: the same K steps again, from the same state, host buffers in / host buffers out every step
     for nm in state_names:
@@ -343,6 +354,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     normU2, normP2 = global_norms()
+    stage('end-to-end leg done')
 
     def finish():
         if dist is not None:
