@@ -1884,6 +1884,11 @@ int fetch_kinfo(cfd_ctx* c) {
       c->last_bicg_restarts[d] = (int)hk[kBicgInfoRestarts + d];
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
+#ifdef CFD_PCG_PHASE_TIMERS
+   if (c->cg_variant == 2 && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      fprintf(stderr, "[rank %d] pcg (single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync + halo wait %.2f | sweep %.2f | reduction %.2f\n",
+              c->P.rank, c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
+#endif
    if (c->p2p && c->xstate) {   // a peer that never arrived: the spin-waits of k_pcg_p2p give up after 4 s and raise this word
       unsigned long long err[6] = {0, 0, 0, 0, 0, 0};
       CFD_CK(cudaMemcpy(err, c->xstate + 2, sizeof err, cudaMemcpyDeviceToHost));
