@@ -921,15 +921,19 @@ struct PcgCgArgs {
 __device__ __forceinline__ void pcgcg_slice(const Sell& Z, const double* __restrict__ val, int s, const double* u, const double* r, double* w, int lane,
                                             double& g, double& d, double& rr) {
    const int T = Z.T, sub = lane % T;
+   const int row = s * Z.R + lane / T;
+   const bool own = sub == 0 && row < Z.nrows;
+   // the row's own r and u are requested BEFORE the matrix sweep: a warp works through its slices one after the other, so a load
+   // issued after the sweep would add its full latency to every slice (measured: the sweep ran at half the classical kernel's rate)
+   double ri = 0.0, ui = 0.0;
+   if (own) { ri = r[row]; ui = u[row]; }
    double acc = 0.0;
    sell_pairs<4>(Z, s, lane, [&](long long e, int2 c2) {
       const double2 v2 = ldnc_d2(val + e);
       acc += v2.x * u[c2.x] + v2.y * u[c2.y];
    });
    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-   const int row = s * Z.R + lane / T;
-   if (sub == 0 && row < Z.nrows) {
-      const double ri = r[row], ui = u[row];
+   if (own) {
       w[row] = acc;
       g += ri * ui; d += acc * ui; rr += ri * ri;
    }
