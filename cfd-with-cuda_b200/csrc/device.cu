@@ -852,12 +852,24 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
    int it = 0;
    if (!(sqrt(rr) <= thresh || it >= a.maxit))
       if (!p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i]; })) return;
+   // phase clocks (diagnostics build: info[8..12] = ns in spmv / all-reduce 1 / update / all-reduce 2 / p update + push + flags), of
+   // block 0 and -- info[13..17] -- of the last block
+#ifdef CFD_PCG_PHASE_TIMERS
+   unsigned long long tph[5] = {0, 0, 0, 0, 0}, t0 = 0, t1;
+   const bool clk = threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+#define PCG_TICK(k) do { if (clk) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+   if (clk) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define PCG_TICK(k)
+#endif
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       double v1[1];
       v1[0] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.p, a.q, gwarp, nwarps, lane);
+      PCG_TICK(0);
       if (!xgrid_sum<1>(v1, buf1, sh, xc, epoch)) return;
       if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
+      PCG_TICK(1);
       const double alpha = rz / v1[0];
       double v2[2] = {0, 0};
       for (int i = tid; i < n; i += nthreads) {
@@ -867,14 +879,22 @@ __global__ void __launch_bounds__(512, 3) k_pcg_p2p(PcgP2PArgs pa) {
          v2[0] += ri * (a.dinv[i] * ri);
          v2[1] += ri * ri;
       }
+      PCG_TICK(2);
       if (!xgrid_sum<2>(v2, buf0, sh, xc, epoch)) return;
+      PCG_TICK(3);
       const double beta = v2[0] / rz;
       rz = v2[0];
       rr = v2[1];
       it++;
       if (sqrt(rr) <= thresh || it >= a.maxit) break;   // converged: the next search direction is never used
       if (!p_update_and_push(grid, n, a.p, xc, hepoch, tid, nthreads, [&](int i) { return a.dinv[i] * a.r[i] + beta * a.p[i]; })) return;
+      PCG_TICK(4);
    }
+#undef PCG_TICK
+#ifdef CFD_PCG_PHASE_TIMERS
+   if (clk)
+      for (int k = 0; k < 5; k++) a.info[(blockIdx.x == 0 ? 8 : 13) + k] = (double)tph[k];
+#endif
    grid.sync();
    if (tid == 0) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
@@ -1889,6 +1909,11 @@ int fetch_kinfo(cfd_ctx* c) {
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
 #ifdef CFD_PCG_PHASE_TIMERS
+   if (c->cg_variant == 1 && parted(c) && c->p2p && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      for (int b = 0; b < 2; b++)
+         fprintf(stderr, "[rank %d] pcg (classical, peer memory) phases, us / iteration, %s block (%d iterations): spmv %.2f | all-reduce 1 %.2f | update %.2f | all-reduce 2 %.2f | "
+                         "p update + push + flags %.2f\n", c->P.rank, b ? "last" : "first", c->last_cg, hk[8 + 5 * b] / c->last_cg * 1e-3, hk[9 + 5 * b] / c->last_cg * 1e-3,
+                 hk[10 + 5 * b] / c->last_cg * 1e-3, hk[11 + 5 * b] / c->last_cg * 1e-3, hk[12 + 5 * b] / c->last_cg * 1e-3);
    if (c->cg_variant == 2 && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "[rank %d] pcg (single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync + halo wait %.2f | sweep %.2f | reduction %.2f\n",
               c->P.rank, c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
