@@ -990,18 +990,22 @@ __device__ __forceinline__ void pcgcg_rows(const PcgCgArgs& a, int t0, int t1, i
       a.r[i] = ri;
       const double un = a.dinv[i] * ri;
       a.u[i] = un;
-      if (DIST)
+      if (DIST) {
+         bool pushed = false;
          for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
             const int2 dst = a.xc.pushDst[e];
             st_sys_f64(a.xc.peerP[dst.x] + dst.y, un);
+            pushed = true;
          }
+         if (pushed) __threadfence_system();   // system-scope fences are expensive: only the storing threads issue one
+      }
    }
 }
 
 // After this rank's interface values have been stored into the neighbours' windows: the last block to get here raises the halo flags.
 __device__ __forceinline__ void pcgcg_signal(const XComm& xc, unsigned long long hepoch) {
    __shared__ int s_lastI;
-   __threadfence_system();
+   __threadfence();   // (the threads that stored into a neighbour's window have fenced those stores at system scope themselves)
    __syncthreads();
    if (threadIdx.x == 0) {
       const unsigned long long G = gridDim.x;
@@ -1046,11 +1050,15 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
       const double un = a.dinv[i] * ri;
       a.u[i] = un;
       v4[3] += bi * bi;
-      if (DIST)
+      if (DIST) {
+         bool pushed = false;
          for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
             const int2 dst = a.xc.pushDst[e];
             st_sys_f64(a.xc.peerP[dst.x] + dst.y, un);
+            pushed = true;
          }
+         if (pushed) __threadfence_system();
+      }
    };
    if (DIST) {
       for (int t = tid; t < a.xc.nIface; t += nthreads) initRow(a.xc.ifaceRows[t]);
@@ -1277,10 +1285,13 @@ struct BicgScalars {
 
 // DIST: store a freshly computed entry of ph (which = 0) or shv (which = 1) into the ghost copies the neighbours hold
 __device__ __forceinline__ void bicg_push(const BicgArgs& a, int which, int c, int i, double v) {
+   bool pushed = false;
    for (int e = a.xv.pushPtr[i]; e < a.xv.pushPtr[i + 1]; e++) {
       const int2 d = a.xv.pushDst[e];
       st_sys_f64(a.xv.peerV[d.x] + (size_t)(which * 3 + c) * (size_t)a.xv.peerLd[d.x] + d.y, v);
+      pushed = true;
    }
+   if (pushed) __threadfence_system();   // only the storing threads pay for the system-scope fence
 }
 
 // DIST = true (partitioned runs): the same kernel as a fused compute + collective over peer memory.  ph and shv -- the vectors
@@ -1307,6 +1318,8 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    if (DIST) { epoch = a.xc.xstate[0]; hepoch = a.xc.xstate[1]; }
    // grid-wide (DIST: cross-GPU) sum; false = a peer timed out: leave at once
 #define BICG_SUM(NV, v, buf) (DIST ? xgrid_sum<NV>(v, buf, sh, a.xc, epoch) : (grid_sum<NV>(grid, v, buf, sh), true))
+   // ... that also hands over the peer-memory stores made in the pass before it
+#define BICG_SUM_PUBLISH(NV, v, buf) (DIST ? xgrid_sum<NV, true>(v, buf, sh, a.xc, epoch) : (grid_sum<NV>(grid, v, buf, sh), true))
    // hand-over of pushed values without a reduction: flags + local grid sync
 #define BICG_HANDOVER()                                   \
    do {                                                   \
@@ -1333,8 +1346,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
       }
       v6[c] = acc;
    }
-   if (DIST) __threadfence_system();
-   if (!BICG_SUM(6, v6, buf0)) return;
+   if (!BICG_SUM_PUBLISH(6, v6, buf0)) return;
    if (threadIdx.x == 0) {
       for (int c = 0; c < 3; c++) {
          S.bb[c] = S.rr[c] = S.rrs[c] = v6[c];
@@ -1474,9 +1486,8 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
          }
          v3[c] = acc;
       }
-      if (DIST) __threadfence_system();   // the reduction that follows publishes the pushes
       BICG_TICK(2);
-      if (!BICG_SUM(3, v3, buf0)) return;
+      if (!BICG_SUM_PUBLISH(3, v3, buf0)) return;   // publishes the shv values stored into the neighbours' windows
       BICG_TICK(3);
       if (threadIdx.x == 0)
          for (int c = 0; c < 3; c++) {   // converged at the half step (cusp::krylov::bicgstab): x += alpha M p, no iteration counted
@@ -1564,6 +1575,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
    }
 #undef BICG_TICK
 #undef BICG_SUM
+#undef BICG_SUM_PUBLISH
 #undef BICG_HANDOVER
 #ifdef CFD_BICG_PHASE_TIMERS
    if (tid == 0) {
@@ -1909,6 +1921,9 @@ int fetch_kinfo(cfd_ctx* c) {
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
 #ifdef CFD_PCG_PHASE_TIMERS
+   if (c->cg_variant == 1 && !parted(c) && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      fprintf(stderr, "pcg (classical) phases, us / iteration, block 0 (%d iterations): spmv %.2f | reduction 1 %.2f | update %.2f | reduction 2 %.2f | p update + sync %.2f\n",
+              c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3, hk[12] / c->last_cg * 1e-3);
    if (c->cg_variant == 1 && parted(c) && c->p2p && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       for (int b = 0; b < 2; b++)
          fprintf(stderr, "[rank %d] pcg (classical, peer memory) phases, us / iteration, %s block (%d iterations): spmv %.2f | all-reduce 1 %.2f | update %.2f | all-reduce 2 %.2f | "

@@ -418,7 +418,10 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 //     fences after its own poll (acquire side).
 // Returns false -- in every thread of the block -- after a time-out: the caller must leave the kernel at once (no further
 // grid-wide or cross-GPU synchronisation; every block of every rank runs into the same time-out or sees the error word).
-template <int N>
+// PUBLISH = true: peer-memory stores made before the call (each storing thread fenced them at system scope) are handed over with
+// the reduction: the delivering warp fences at system scope before it writes the words.  System-scope fences are expensive
+// (measured: one in every polling block cost ~15 us per reduction), so nothing else in here uses one.
+template <int N, bool PUBLISH = false>
 __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* sh, const XComm& xc, unsigned long long& epoch) {
    static_assert(2 * N <= kWinMailWords, "mailbox too small for this many values");
    __shared__ int s_last, s_fail;
@@ -437,7 +440,8 @@ __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* s
    }
    __syncthreads();
    if (s_last && threadIdx.x < 32) {
-      __threadfence_system();
+      __threadfence();   // acquire side of the tickets: the other blocks' partials (and whatever they published before them)
+      if (PUBLISH) __threadfence_system();
       double tot[N];
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -482,7 +486,7 @@ __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* s
             mine[i] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
          }
          if (!ok) s_fail = 1;
-         __threadfence_system();   // acquire side, in every lane that observed a word
+         __threadfence();   // acquire side, in every lane that observed a word (drops this SM's stale L1 lines before the block reads on)
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -504,15 +508,17 @@ __device__ __forceinline__ bool xgrid_sum(double (&v)[N], double* buf, double* s
 template <typename F>
 __device__ __forceinline__ bool p_update_and_push(cg::grid_group& grid, int n, double* p, const XComm& xc, unsigned long long& hepoch,
                                                   int tid, int nthreads, F value) {
+   bool pushed = false;
    for (int i = tid; i < n; i += nthreads) {
       const double pn = value(i);
       p[i] = pn;
       for (int e = xc.pushPtr[i]; e < xc.pushPtr[i + 1]; e++) {
          const int2 d = xc.pushDst[e];
          st_sys_f64(xc.peerP[d.x] + d.y, pn);
+         pushed = true;
       }
    }
-   __threadfence_system();
+   if (pushed) __threadfence_system();   // only the threads that stored into a neighbour's window pay for the system-scope fence
    grid.sync();
    hepoch++;
    if (blockIdx.x == 0 && threadIdx.x < xc.npeers) st_rel_sys(win_haloflag(xc.peerWin[xc.peerRank[threadIdx.x]], xc.rank), hepoch);
