@@ -937,47 +937,15 @@ struct PcgCgArgs {
    XComm xc;          // DIST only
 };
 
-// One slice of w = Z u by one warp, plus this lane's share of r.u, w.u and r.r over the slice's rows.
-__device__ __forceinline__ void pcgcg_slice(const Sell& Z, const double* __restrict__ val, int s, const double* u, const double* r, double* w, int lane,
-                                            double& g, double& d, double& rr) {
-   const int T = Z.T, sub = lane % T;
-   const int row = s * Z.R + lane / T;
-   const bool own = sub == 0 && row < Z.nrows;
-   // the row's own r and u are requested BEFORE the matrix sweep: a warp works through its slices one after the other, so a load
-   // issued after the sweep would add its full latency to every slice (measured: the sweep ran at half the classical kernel's rate)
-   double ri = 0.0, ui = 0.0;
-   if (own) { ri = r[row]; ui = u[row]; }
-   double acc = 0.0;
-   sell_pairs<4>(Z, s, lane, [&](long long e, int2 c2) {
-      const double2 v2 = ldnc_d2(val + e);
-      acc += v2.x * u[c2.x] + v2.y * u[c2.y];
-   });
-   for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-   if (own) {
-      w[row] = acc;
-      g += ri * ui; d += acc * ui; rr += ri * ri;
-   }
-}
-__device__ __forceinline__ void pcgcg_sweep(const PcgCgArgs& a, int gwarp, int nwarps, int lane, double& g, double& d, double& rr) {
-   const double* __restrict__ val = a.Z.vals[0];
-   const int nstatic = a.dynCounter ? a.dynStart : a.Z.nslices;
-   const SliceRange sr = slice_range(nstatic, a.part, gwarp, nwarps);
-   for (int s = sr.begin; s < sr.end; s += sr.step) pcgcg_slice(a.Z, val, s, a.u, a.r, a.w, lane, g, d, rr);
-   if (a.dynCounter) {
-      while (true) {
-         int base = 0;
-         if (lane == 0) base = atomicAdd(a.dynCounter, 2);
-         base = __shfl_sync(0xffffffffu, base, 0) + a.dynStart;
-         if (base >= a.Z.nslices) break;
-         pcgcg_slice(a.Z, val, base, a.u, a.r, a.w, lane, g, d, rr);
-         if (base + 1 < a.Z.nslices) pcgcg_slice(a.Z, val, base + 1, a.u, a.r, a.w, lane, g, d, rr);
-      }
-   }
-}
+// The sweep w = Z u with this lane's share of delta = w.u is exactly the classical kernel's q = Z p with p.q (pcg_spmv_phase):
+// gamma = r.u and |r|^2 are accumulated where r and u are produced (the vector pass) and ride along to the one reduction.  (A first
+// version read r and u again in the sweep's epilogue: two more dependent loads per slice of a warp that works through its slices
+// one after the other -- the sweep ran at 0.55 of the classical kernel's rate.)
 
 // The vector pass over rows i = f(t), t in [t0, t1): `first` = no previous search direction (beta = 0: p = u, s = w exactly).
 template <bool DIST, typename RowOf>
-__device__ __forceinline__ void pcgcg_rows(const PcgCgArgs& a, int t0, int t1, int stride, bool first, double alpha, double beta, RowOf rowOf) {
+__device__ __forceinline__ void pcgcg_rows(const PcgCgArgs& a, int t0, int t1, int stride, bool first, double alpha, double beta, RowOf rowOf,
+                                           double& g, double& rr) {
    for (int t = t0; t < t1; t += stride) {
       const int i = rowOf(t);
       if (i < 0) continue;
@@ -990,6 +958,7 @@ __device__ __forceinline__ void pcgcg_rows(const PcgCgArgs& a, int t0, int t1, i
       a.r[i] = ri;
       const double un = a.dinv[i] * ri;
       a.u[i] = un;
+      g += ri * un; rr += ri * ri;
       if (DIST) {
          bool pushed = false;
          for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
@@ -1049,7 +1018,7 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
       a.r[i] = ri;
       const double un = a.dinv[i] * ri;
       a.u[i] = un;
-      v4[3] += bi * bi;
+      v4[0] += ri * un; v4[2] += ri * ri; v4[3] += bi * bi;
       if (DIST) {
          bool pushed = false;
          for (int e = a.xc.pushPtr[i]; e < a.xc.pushPtr[i + 1]; e++) {
@@ -1071,7 +1040,7 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
    }
    grid.sync();
    if (DIST && !pcgcg_wait(a.xc, hepoch)) return;
-   pcgcg_sweep(a, gwarp, nwarps, lane, v4[0], v4[1], v4[2]);
+   v4[1] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.u, a.w, gwarp, nwarps, lane);
    if (DIST) { if (!xgrid_sum<4>(v4, a.scratch, sh, a.xc, epoch)) return; }
    else grid_sum<4>(grid, v4, a.scratch, sh);
    if (tid == 0 && a.dynCounter) *a.dynCounter = 0;
@@ -1091,21 +1060,21 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_cg(PcgCgArgs a) {
    while (true) {
       if (sqrt(rr) <= thresh || it >= a.maxit) break;
       const bool first = it == 0;
+      double v3[3] = {0, 0, 0};
       if (DIST) {
-         pcgcg_rows<true>(a, tid, a.xc.nIface, nthreads, first, alpha, beta, [&](int t) { return a.xc.ifaceRows[t]; });
+         pcgcg_rows<true>(a, tid, a.xc.nIface, nthreads, first, alpha, beta, [&](int t) { return a.xc.ifaceRows[t]; }, v3[0], v3[2]);
          hepoch++;
          pcgcg_signal(a.xc, hepoch);
-         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [&](int t) { return a.xc.pushPtr[t + 1] == a.xc.pushPtr[t] ? t : -1; });
+         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [&](int t) { return a.xc.pushPtr[t + 1] == a.xc.pushPtr[t] ? t : -1; }, v3[0], v3[2]);
       } else {
-         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [](int t) { return t; });
+         pcgcg_rows<false>(a, tid, n, nthreads, first, alpha, beta, [](int t) { return t; }, v3[0], v3[2]);
       }
       it++;
       PCG_TICK(0);
       grid.sync();   // every block's u is in place (DIST: and the neighbours' interface values, once their flags are up)
       if (DIST && !pcgcg_wait(a.xc, hepoch)) return;
       PCG_TICK(1);
-      double v3[3] = {0, 0, 0};
-      pcgcg_sweep(a, gwarp, nwarps, lane, v3[0], v3[1], v3[2]);
+      v3[1] = pcg_spmv_phase(a.Z, a.part, a.dynStart, a.dynCounter, a.u, a.w, gwarp, nwarps, lane);
       PCG_TICK(2);
       if (DIST) { if (!xgrid_sum<3>(v3, a.scratch, sh, a.xc, epoch)) return; }
       else grid_sum<3>(grid, v3, a.scratch, sh);
