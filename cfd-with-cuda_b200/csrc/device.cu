@@ -2236,7 +2236,9 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    TRY(dalloc(c, &c->cg_r, (size_t)NNp)); TRY(dalloc(c, &c->cg_p, (size_t)NNp)); TRY(dalloc(c, &c->cg_q, (size_t)NNp));
    // pressure CG recurrences (cfd_options.cg_variant): the single-reduction form where synchronisation dominates
-   c->cg_variant = o.cg_variant == 1 || o.cg_variant == 2 ? o.cg_variant : ((parted || NPo < 500000) ? 2 : 1);
+   // (default: classical.  Measured on B200, profiles/r02_cg_variants.md: the single-reduction kernel saves a synchronisation per
+   // iteration but its larger vector set falls out of L2 and its sweep runs at 32 instead of 48 warps per SM -- slower at every size tried)
+   c->cg_variant = o.cg_variant == 2 ? 2 : 1;
    if (c->cg_variant == 2) { TRY(dalloc(c, &c->cg_s, (size_t)NNp)); TRY(dalloc(c, &c->cg_pp, (size_t)NNp)); }
    TRY(dalloc(c, &c->kinfo, 64)); TRY(dalloc(c, &c->scal, 16));
    // initial state (applyBC_initial, BCH.cpp:4062-4110 / GQ.cpp:4559-4607)

@@ -118,11 +118,10 @@ typedef struct cfd_options {
                             1 = one test per iteration, where a PARALUTION-style solver (GQ.cpp:4190-4229) stops */
    int bicg_no_verify;   /* 0 (default) = a momentum solve is accepted on its TRUE residual |b - A x| <= bicg_tol |b| and restarted from it
                             otherwise (breakdowns included); 1 = trust the recurrence residual, as the reference's libraries do */
-   int cg_variant;    /* pressure CG recurrences: 1 = classical two-reduction PCG, as the reference runs it (BCH.cu:418-451);
+   int cg_variant;    /* pressure CG recurrences: 0 / 1 (default) = classical two-reduction PCG, as the reference runs it (BCH.cu:418-451);
                          2 = Chronopoulos-Gear single-reduction form (same iterates in exact arithmetic, one grid-wide / cross-GPU
-                         reduction per iteration instead of two, 16 B per row more vector traffic); 0 (default) = the library
-                         chooses: single-reduction where synchronisation dominates (partitioned runs, systems under 500 000 rows),
-                         classical otherwise */
+                         reduction per iteration instead of two, 16 B per row more vector traffic).  Both meet the parity bar; the
+                         classical form measured faster on B200 at every size tried (profiles/r02_cg_variants.md) */
    int reserved[2];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
