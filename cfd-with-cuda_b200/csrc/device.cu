@@ -586,6 +586,282 @@ __global__ void __launch_bounds__(128) k_ebe_convect_assemble(int NE, int NN, in
    }
 }
 
+// =================================================================================================
+// Matrix-free (element-by-element) operator path: K, G, G^T and the FE Laplacian applied straight from the
+// element integrals of step0 (BCH.cpp:3127-3315, GQ.cpp:3488-3500, 3677-3772) instead of streaming the
+// assembled CSR arrays -- cfd_options.operator_path = 1, bench.py --path ebe.
+// Thread per element, geometry recomputed from the 8 corners, sum-factorised: with C_k = cofactor matrix of
+// the Jacobian at Gauss point k (C = det J * J^-1, element_geometry in host_solver.cpp) and reference gradients
+// g = sum_j dN_j/dxi(k) x_j,
+//    (K x)_i   = nu  sum_k dN_i/dxi(k) . ( C_k^T C_k g / det_k )          Ke = nu int grad N_i . grad N_j
+//    (G_c p)_i = -1/rho sum_k dN_i/dxi(k) . ( C_k[c][:] p(k) )            Ge_c = -1/rho int Sp_j dN_i/dx_c   (det cancels)
+//    (G^T d)_j = -1/rho sum_k Sp_j(k) sum_c C_k[c][:] . g_c                (g_c = reference gradient of d_c)
+//    (Z p)_j   = -   sum_k dSp_j/dxi(k) . ( C_k^T C_k g / det_k )         FE Laplacian of the implicit scheme, GQ.cpp:3677-3772
+// Algorithmic bytes per element: node ids + corner coordinates + gathered and scattered nodal values only -- no matrix stream.
+// =================================================================================================
+// Cofactor matrix C (C[a][b] = det * (J^-1)[a][b], the arithmetic of element_geometry) and det of the Jacobian at Gauss point k.
+__device__ __forceinline__ double ebe_cofactor(const double (&xc)[8][3], int k, double (&C)[3][3]) {
+   double J[3][3];
+#pragma unroll
+   for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+         double s = 0;
+#pragma unroll
+         for (int m = 0; m < 8; m++) s += cdSp[a][m][k] * xc[m][d];
+         J[a][d] = s;
+      }
+   C[0][0] = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+   C[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+   C[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+   C[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+   C[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+   C[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+   C[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+   C[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+   C[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+   return J[0][0] * C[0][0] + J[0][1] * C[1][0] + J[0][2] * C[2][0];
+}
+
+// out_c[i] += sign * ( [CONV] C(Uadv) X_c + [VISC] K X_c + [PRES] G_c P )_i   for the three components, one pass over the elements.
+//   step 1 (CONV | VISC | PRES, sign -1):  R1 = -C(Un) U - K U - G Pn        (calculateMatrixA + step1, BCH.cpp:3520-3801)
+//   step 3 (PRES):                          G Pdot                             (BCH.cpp:3912-3974)
+//   K * Acc_prev (VISC):                                                        (BCH.cpp:2985-3033)
+enum { kEbeConv = 1, kEbeVisc = 2, kEbePres = 4 };
+template <int NV, int MODE>
+__global__ void __launch_bounds__(128) k_ebe_momentum_apply(int NE, int NN, int ldE, const int* __restrict__ LtoGT, const double* __restrict__ coord,
+                                                            const double* __restrict__ Uadv, const double* __restrict__ X, const double* __restrict__ Pv,
+                                                            double nu, double invRho, double sign, double* __restrict__ out) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= NE) return;
+   int nd[NV];
+#pragma unroll
+   for (int i = 0; i < NV; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
+   double xc[8][3];
+#pragma unroll
+   for (int m = 0; m < 8; m++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) xc[m][d] = __ldg(coord + 3 * (long long)nd[m] + d);
+   double pk[8];   // pressure at the Gauss points
+   if (MODE & kEbePres) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) pk[k] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+         const double v = __ldg(Pv + nd[j]);
+#pragma unroll
+         for (int k = 0; k < 8; k++) pk[k] += cSv8[k][j] * v;
+      }
+   }
+   double ug[8][3];   // advecting velocity at the Gauss points
+   if (MODE & kEbeConv) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { ug[k][0] = 0; ug[k][1] = 0; ug[k][2] = 0; }
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+         for (int i = 0; i < NV; i++) {
+            const double v = __ldg(Uadv + (long long)c * NN + nd[i]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) ug[k][c] += Tab<NV>::Sv(k, i) * v;
+         }
+   }
+#pragma unroll 1
+   for (int c = 0; c < 3; c++) {
+      double g[8][3];   // reference gradient of X_c at the Gauss points, turned into the flux h below
+      if (MODE & (kEbeConv | kEbeVisc)) {
+#pragma unroll
+         for (int k = 0; k < 8; k++) { g[k][0] = 0; g[k][1] = 0; g[k][2] = 0; }
+#pragma unroll
+         for (int j = 0; j < NV; j++) {
+            const double v = __ldg(X + (long long)c * NN + nd[j]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+               g[k][0] += Tab<NV>::dSv(0, j, k) * v;
+               g[k][1] += Tab<NV>::dSv(1, j, k) * v;
+               g[k][2] += Tab<NV>::dSv(2, j, k) * v;
+            }
+         }
+      }
+      double t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+         double C[3][3];
+         const double det = ebe_cofactor(xc, k, C);
+         double h0 = 0, h1 = 0, h2 = 0;
+         t[k] = 0.0;
+         if (MODE & (kEbeConv | kEbeVisc)) {
+            // w = C g (= det * physical gradient of X_c)
+            const double w0 = C[0][0] * g[k][0] + C[0][1] * g[k][1] + C[0][2] * g[k][2];
+            const double w1 = C[1][0] * g[k][0] + C[1][1] * g[k][1] + C[1][2] * g[k][2];
+            const double w2 = C[2][0] * g[k][0] + C[2][1] * g[k][1] + C[2][2] * g[k][2];
+            if (MODE & kEbeConv) t[k] = ug[k][0] * w0 + ug[k][1] * w1 + ug[k][2] * w2;
+            if (MODE & kEbeVisc) {
+               const double f = nu / det;
+               h0 = f * (C[0][0] * w0 + C[1][0] * w1 + C[2][0] * w2);
+               h1 = f * (C[0][1] * w0 + C[1][1] * w1 + C[2][1] * w2);
+               h2 = f * (C[0][2] * w0 + C[1][2] * w1 + C[2][2] * w2);
+            }
+         }
+         if (MODE & kEbePres) {
+            const double q = -invRho * pk[k];
+            h0 += q * C[c][0]; h1 += q * C[c][1]; h2 += q * C[c][2];
+         }
+         g[k][0] = h0; g[k][1] = h1; g[k][2] = h2;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+         double r = 0;
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            if (MODE & kEbeConv) r += Tab<NV>::Sv(k, i) * t[k];
+            if (MODE & (kEbeVisc | kEbePres))
+               r += Tab<NV>::dSv(0, i, k) * g[k][0] + Tab<NV>::dSv(1, i, k) * g[k][1] + Tab<NV>::dSv(2, i, k) * g[k][2];
+         }
+         atomicAdd(out + (long long)c * NN + nd[i], sign * r);
+      }
+   }
+}
+
+// R2[j] += sum_c (G_c^T d_c)_j on the 8 pressure nodes of every element, d formed on the fly like k_gt_rhs:
+//   mode 0 (explicit): d = scale * U - [useKAcc] MdOrigInv * KAcc        mode 1 (implicit): d = scale * U  (scale = -1/dt)
+template <int NV>
+__global__ void __launch_bounds__(128) k_ebe_gt_apply(int NE, int NN, int ldE, const int* __restrict__ LtoGT, const double* __restrict__ coord, int mode,
+                                                      const double* __restrict__ U, const double* __restrict__ KAcc, int useKAcc,
+                                                      const double* __restrict__ MdOrigInv, double scale, double invRho, double* __restrict__ R2) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= NE) return;
+   int nd[NV];
+#pragma unroll
+   for (int i = 0; i < NV; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
+   double xc[8][3];
+#pragma unroll
+   for (int m = 0; m < 8; m++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) xc[m][d] = __ldg(coord + 3 * (long long)nd[m] + d);
+   double sk[8];
+#pragma unroll
+   for (int k = 0; k < 8; k++) sk[k] = 0.0;
+#pragma unroll 1
+   for (int c = 0; c < 3; c++) {
+      double g[8][3];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { g[k][0] = 0; g[k][1] = 0; g[k][2] = 0; }
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+         const long long ix = (long long)c * NN + nd[j];
+         double v = scale * __ldg(U + ix);
+         if (mode == 0 && useKAcc) v -= __ldg(MdOrigInv + ix) * __ldg(KAcc + ix);
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            g[k][0] += Tab<NV>::dSv(0, j, k) * v;
+            g[k][1] += Tab<NV>::dSv(1, j, k) * v;
+            g[k][2] += Tab<NV>::dSv(2, j, k) * v;
+         }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+         double C[3][3];
+         ebe_cofactor(xc, k, C);
+         sk[k] += C[c][0] * g[k][0] + C[c][1] * g[k][1] + C[c][2] * g[k][2];
+      }
+   }
+#pragma unroll
+   for (int j = 0; j < 8; j++) {
+      double r = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) r += cSv8[k][j] * sk[k];
+      atomicAdd(R2 + nd[j], -invRho * r);
+   }
+}
+
+// q[j] += (Z p)_j with Z the FE Laplacian of the implicit scheme (GQ.cpp:3677-3772: Ze = - int grad Sp_i . grad Sp_j), on the corner nodes.
+template <int NV>
+__global__ void __launch_bounds__(128) k_ebe_laplace_apply(int NE, int ldE, const int* __restrict__ LtoGT, const double* __restrict__ coord,
+                                                           const double* __restrict__ pv, double* __restrict__ q) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= NE) return;
+   int nd[8];
+#pragma unroll
+   for (int i = 0; i < 8; i++) nd[i] = __ldg(LtoGT + (long long)i * ldE + e);
+   double xc[8][3], g[8][3];
+#pragma unroll
+   for (int m = 0; m < 8; m++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) xc[m][d] = __ldg(coord + 3 * (long long)nd[m] + d);
+#pragma unroll
+   for (int k = 0; k < 8; k++) { g[k][0] = 0; g[k][1] = 0; g[k][2] = 0; }
+#pragma unroll
+   for (int j = 0; j < 8; j++) {
+      const double v = __ldg(pv + nd[j]);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+         g[k][0] += cdSp[0][j][k] * v; g[k][1] += cdSp[1][j][k] * v; g[k][2] += cdSp[2][j][k] * v;
+      }
+   }
+#pragma unroll
+   for (int k = 0; k < 8; k++) {
+      double C[3][3];
+      const double det = ebe_cofactor(xc, k, C);
+      const double w0 = C[0][0] * g[k][0] + C[0][1] * g[k][1] + C[0][2] * g[k][2];
+      const double w1 = C[1][0] * g[k][0] + C[1][1] * g[k][1] + C[1][2] * g[k][2];
+      const double w2 = C[2][0] * g[k][0] + C[2][1] * g[k][1] + C[2][2] * g[k][2];
+      const double f = -1.0 / det;
+      g[k][0] = f * (C[0][0] * w0 + C[1][0] * w1 + C[2][0] * w2);
+      g[k][1] = f * (C[0][1] * w0 + C[1][1] * w1 + C[2][1] * w2);
+      g[k][2] = f * (C[0][2] * w0 + C[1][2] * w1 + C[2][2] * w2);
+   }
+#pragma unroll
+   for (int i = 0; i < 8; i++) {
+      double r = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) r += cdSp[0][i][k] * g[k][0] + cdSp[1][i][k] * g[k][1] + cdSp[2][i][k] * g[k][2];
+      atomicAdd(q + nd[i], r);
+   }
+}
+
+// The pointwise halves of step 1 and step 3 after the element pass has accumulated the operator part (matrix-free path):
+//   step 1:  R1[bc] = 0 ; UnpHalf = Un + dt * R1 * MdInv
+__global__ void __launch_bounds__(256) k_step1_finish(int NN, const int* __restrict__ bcIndex, const double* __restrict__ Un, const double* __restrict__ MdInv,
+                                                      double* __restrict__ R1, double* __restrict__ UnpHalf, double dt) {
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   if (row >= NN) return;
+   const bool bc = bcIndex[row] >= 0;
+#pragma unroll
+   for (int c = 0; c < 3; c++) {
+      const long long i = (long long)c * NN + row;
+      const double r = bc ? 0.0 : R1[i];
+      R1[i] = r;
+      UnpHalf[i] = Un[i] + dt * r * MdInv[i];
+   }
+}
+//   step 3:  R3 = -dt * (G Pdot) - [iter>1] dt * KAcc ; R3[bc] = 0 ; Acc = R3 * MdInv ; Unp1 = UnpHalf + dt * Acc ; convergence sums
+__global__ void __launch_bounds__(256) k_step3_finish(int NN, const double* __restrict__ KAcc, int useKAcc, const double* __restrict__ MdInv,
+                                                      const int* __restrict__ bcIndex, const double* __restrict__ UnpHalf, const double* __restrict__ Unp1_prev,
+                                                      double* __restrict__ R3, double* __restrict__ Acc, double* __restrict__ Unp1, double dt,
+                                                      double* __restrict__ sums) {
+   __shared__ double sh[64];
+   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+   double s[2] = {0.0, 0.0};
+   if (row < NN) {
+      const bool bc = bcIndex[row] >= 0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+         const long long i = (long long)c * NN + row;
+         double r = -dt * R3[i];   // R3 holds G_c Pdot from the element pass
+         if (useKAcc) r = r - dt * KAcc[i];
+         if (bc) r = 0.0;
+         const double a = r * MdInv[i];
+         const double u = UnpHalf[i] + dt * a;
+         R3[i] = r; Acc[i] = a; Unp1[i] = u;
+         const double d = u - Unp1_prev[i];
+         s[0] += u * u; s[1] += d * d;
+      }
+   }
+   block_sum<2>(s, sh);
+   if (threadIdx.x == 0) { atomicAdd(sums + 0, s[0]); atomicAdd(sums + 1, s[1]); }
+}
+
 // Dirichlet rows of A -> identity rows (applyVelBC_LHS, GQ.cu:478-498), on the Sell layout.
 __global__ void k_bc_rows_identity(Sell A, int vidx, int nbc, const int* __restrict__ bcNodes, const int* __restrict__ diagPos) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -629,6 +905,16 @@ __global__ void __launch_bounds__(256) k_gq_rhs(Sell MK, int mIdx, Sell G, int N
       R1[(long long)NN + m.row] = (w >= 0) ? BCstr[3 * w + 1] : a1;
       R1[2 * (long long)NN + m.row] = (w >= 0) ? BCstr[3 * w + 2] : a2;
    }
+}
+
+// y_c = G_c x (three value arrays on one pattern, rows = velocity nodes): the assembled counterpart of the matrix-free G apply
+__global__ void __launch_bounds__(256) k_g_apply(Sell G, int NN, const double* __restrict__ x, double* __restrict__ y) {
+   RowMap m;
+   if (!row_map(G, m)) return;
+   double a0 = 0, a1 = 0, a2 = 0;
+   lane_dot_g3(G, m, [x](int c) { return __ldg(x + c); }, 1.0, a0, a1, a2);
+   a0 = lanes_sum(a0, G.T); a1 = lanes_sum(a1, G.T); a2 = lanes_sum(a2, G.T);
+   if (m.owner) { y[m.row] = a0; y[(long long)NN + m.row] = a1; y[2 * (long long)NN + m.row] = a2; }
 }
 
 __global__ void k_axpy_out(long long n, const double* __restrict__ a, const double* __restrict__ b, double s, double* __restrict__ out) {
@@ -1978,6 +2264,37 @@ Bytes ebe_bytes(const cfd_ctx* c, bool assemble) {
    return per * c->P.NE;
 }
 
+// ---- matrix-free operator path (cfd_options.operator_path = 1) -------------------------------------------------------
+inline bool matrix_free(const cfd_ctx* c) { return c->opt.operator_path == 1; }
+// algorithmic bytes of one element pass: node ids + corner coordinates + `gath` gathered and `scat` scattered (read-modify-write) values
+double mf_bytes(const cfd_ctx* c, double gath, double scat) { return (4.0 * c->P.NENv + 192.0 + 8.0 * gath + 16.0 * scat) * (double)c->P.NE; }
+
+template <int MODE>
+int launch_momentum_apply(cfd_ctx* c, const double* Uadv, const double* X, const double* Pv, double sign, double* out) {
+   const int NE = c->P.NE, NN = c->P.NN;
+   const double invRho = 1.0 / c->P.density;
+   if (c->P.NENv == 27)
+      k_ebe_momentum_apply<27, MODE><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, Uadv, X, Pv, c->P.viscosity, invRho, sign, out);
+   else
+      k_ebe_momentum_apply<8, MODE><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, Uadv, X, Pv, c->P.viscosity, invRho, sign, out);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   return CFD_OK;
+}
+int launch_gt_apply(cfd_ctx* c, int mode, const double* U, const double* KAcc, int useKAcc, const double* MdOrigInv, double scale, double* R2) {
+   const int NE = c->P.NE, NN = c->P.NN;
+   const double invRho = 1.0 / c->P.density;
+   CFD_CK(cudaMemsetAsync(R2, 0, sizeof(double) * (size_t)c->P.NNp, c->stream));
+   if (c->P.NENv == 27)
+      k_ebe_gt_apply<27><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, mode, U, KAcc, useKAcc, MdOrigInv, scale, invRho, R2);
+   else
+      k_ebe_gt_apply<8><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, mode, U, KAcc, useKAcc, MdOrigInv, scale, invRho, R2);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
+   if (c->pin >= 0) CFD_CK(cudaMemsetAsync(R2 + c->pin, 0, sizeof(double), c->stream));   // applyPresBC: R2[zeroPressureNode] = 0
+   return CFD_OK;
+}
+
 }   // namespace
 
 extern "C" {
@@ -2032,6 +2349,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       return CFD_ERR_ARG;
    }
    if (P->scheme == CFD_EXPLICIT && (!P->MdInv || !P->MdOrigInv)) { set_error("explicit scheme needs MdInv and MdOrigInv"); return CFD_ERR_ARG; }
+   if (opt && opt->operator_path == 1 && P->world > 1) { set_error("operator_path = 1 (matrix-free operators) is single-GPU: interface rows would need a sum exchange"); return CFD_ERR_ARG; }
+   if (opt && opt->operator_path != 0 && opt->operator_path != 1) { set_error("operator_path must be 0 (assembled) or 1 (matrix-free)"); return CFD_ERR_ARG; }
    if (P->scheme == CFD_IMPLICIT && (!P->sparseMvalue || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
    cfd_options o;
    if (opt) o = *opt; else cfd_default_options(&o);
@@ -2572,6 +2891,13 @@ int bch_beginTimeStep(cfd_ctx* c) {
 
 int bch_calculateMatrixAGPU(cfd_ctx* c) {
    const size_t N3 = 3 * (size_t)c->P.NN;
+   if (matrix_free(c)) {
+      // the whole operator part of step 1 in ONE element pass: R1 = -C(Un) U - K U - G Pn
+      const double nv = c->P.NENv;
+      ProfScope ps(c, "ebe", mf_bytes(c, 3 * nv + 3 * nv + 8, 3 * nv));
+      CFD_CK(cudaMemsetAsync(c->R1, 0, N3 * sizeof(double), c->stream));
+      return launch_momentum_apply<kEbeConv | kEbeVisc | kEbePres>(c, c->Un, c->UnpHalf_prev, c->Pn, -1.0, c->R1);
+   }
    ProfScope ps(c, "ebe", ebe_bytes(c, false));
    CFD_CK(cudaMemsetAsync(c->R1, 0, N3 * sizeof(double), c->stream));
    if (c->P.NENv == 27) return launch_ebe_apply<27>(c, c->Un, c->UnpHalf_prev, c->R1);
@@ -2580,6 +2906,13 @@ int bch_calculateMatrixAGPU(cfd_ctx* c) {
 
 int bch_step1GPUpart(cfd_ctx* c, int /*iter*/) {
    const int NN = c->P.NN;
+   if (matrix_free(c)) {   // K U + G P went into R1 with the convective term (bch_calculateMatrixAGPU): only the pointwise half is left
+      ProfScope ps(c, "step1", 8.0 * 3 * NN * 5 + 4.0 * NN);
+      k_step1_finish<<<gridFor(NN, 256), 256, 0, c->stream>>>(NN, c->bcIndex, c->Un, c->MdInv, c->R1, c->UnpHalf, c->P.dt);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+      return CFD_OK;
+   }
    ProfScope ps(c, "step1", spmv_bytes(c->K, 1, 3, true) + spmv_bytes(c->G, 3, 1, false) + 8.0 * 3 * NN * 3);
    k_step1<<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, c->G, NN, c->UnpHalf_prev, c->Pn, c->Un, c->MdInv,
                                                                                 c->bcIndex, c->R1, c->UnpHalf, c->P.dt);
@@ -2591,7 +2924,12 @@ int bch_step1GPUpart(cfd_ctx* c, int /*iter*/) {
 int bch_step2GPU(cfd_ctx* c, int iter) {
    const int NN = c->P.NN, NNp = c->P.NNp;
    const double dt = c->P.dt;
-   {
+   if (matrix_free(c)) {
+      const double nv = c->P.NENv;
+      ProfScope ps(c, "gt_rhs", mf_bytes(c, (iter != 1 ? 9 : 3) * nv, 8));
+      int rcm = launch_gt_apply(c, 0, c->UnpHalf, c->KtimesAcc_prev, iter != 1, c->MdOrigInv, 1.0 / (dt * dt), c->R2);
+      if (rcm) return rcm;
+   } else {
       ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
       k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 0, c->UnpHalf, c->KtimesAcc_prev, iter != 1,
                                                                                     c->MdOrigInv, 1.0 / (dt * dt), c->pin, c->R2);
@@ -2613,6 +2951,21 @@ int bch_step2GPU(cfd_ctx* c, int iter) {
 
 int bch_step3GPU(cfd_ctx* c, int iter) {
    const int NN = c->P.NN;
+   if (matrix_free(c)) {
+      const double nv = c->P.NENv;
+      {
+         ProfScope ps(c, "step3", mf_bytes(c, 8, 3 * nv));
+         CFD_CK(cudaMemsetAsync(c->R3, 0, 3 * (size_t)NN * sizeof(double), c->stream));
+         int rcm = launch_momentum_apply<kEbePres>(c, nullptr, nullptr, c->Pdot, 1.0, c->R3);
+         if (rcm) return rcm;
+      }
+      ProfScope ps(c, "step3", 8.0 * 3 * NN * 8 + 4.0 * NN);
+      k_step3_finish<<<gridFor(NN, 256), 256, 0, c->stream>>>(NN, c->KtimesAcc_prev, iter != 1, c->MdInv, c->bcIndex, c->UnpHalf, c->Unp1_prev, c->R3, c->Acc,
+                                                              c->Unp1, c->P.dt, c->scal);
+      c->launches++;
+      CFD_CK(cudaGetLastError());
+      return CFD_OK;
+   }
    ProfScope ps(c, "step3", spmv_bytes(c->G, 3, 1, false) + 8.0 * 3 * NN * 7);
    k_step3<<<gridFor((long long)c->G.nslices * 32, 256), 256, 0, c->stream>>>(c->G, NN, c->Pdot, c->KtimesAcc_prev, iter != 1, c->MdInv, c->bcIndex,
                                                                                 c->UnpHalf, c->Unp1_prev, c->R3, c->Acc, c->Unp1, c->P.dt, c->scal);
@@ -2647,6 +3000,12 @@ int bch_rotateIterates(cfd_ctx* c) {
 
 int bch_calculate_KtimesAcc_prevGPU(cfd_ctx* c) {
    const int NN = c->P.NN;
+   if (matrix_free(c)) {
+      const double nv = c->P.NENv;
+      ProfScope ps(c, "spmv_k", mf_bytes(c, 3 * nv, 3 * nv));
+      CFD_CK(cudaMemsetAsync(c->KtimesAcc_prev, 0, 3 * (size_t)NN * sizeof(double), c->stream));
+      return launch_momentum_apply<kEbeVisc>(c, nullptr, c->Acc_prev, nullptr, 1.0, c->KtimesAcc_prev);
+   }
    ProfScope ps(c, "spmv_k", spmv_bytes(c->K, 1, 3, false));
    k_spmv_multi<3><<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, 0, c->Acc_prev, NN, c->KtimesAcc_prev, NN, 1.0, 0.0);
    c->launches++;
@@ -2762,7 +3121,11 @@ int gq_step1GPU(cfd_ctx* c) {
 
 int gq_step2GPU(cfd_ctx* c) {
    const int NN = c->P.NN, NNp = c->P.NNp;
-   {
+   if (matrix_free(c)) {
+      ProfScope ps(c, "gt_rhs", mf_bytes(c, 3.0 * c->P.NENv, 8));
+      int rcm = launch_gt_apply(c, 1, c->Uk, nullptr, 0, nullptr, -1.0 / c->P.dt, c->R2);
+      if (rcm) return rcm;
+   } else {
       ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
       k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 1, c->Uk, nullptr, 0, nullptr, -1.0 / c->P.dt,
                                                                                     c->pin, c->R2);
@@ -2963,6 +3326,78 @@ int cfd_matrix_stats(cfd_ctx* c, const char* name, long long* nnz, long long* st
    if (stored_values) *stored_values = m->padded;
    if (stored_indices) *stored_indices = m->nindex;
    if (lanes_per_row) *lanes_per_row = m->T;
+   return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one operator, both ways (assembled / matrix-free)
+// ------------------------------------------------------------------------------------------------
+int cfd_operator_apply(cfd_ctx* c, const char* op, int path, const double* x, double* y, int repeat, double* ms_per_call, double* bytes) {
+   if (!c || !op || !x || !y) return CFD_ERR_ARG;
+   if (parted(c)) { set_error("cfd_operator_apply: single-GPU contexts only"); return CFD_ERR_ARG; }
+   const std::string o(op);
+   const int NN = c->P.NN, NNp = c->P.NNp, NE = c->P.NE;
+   const double nv = c->P.NENv, invRho = 1.0 / c->P.density;
+   const bool toP = o == "GT" || o == "Z", fromP = o == "G" || o == "Z";
+   if (o != "K" && o != "G" && o != "GT" && o != "Z") { set_error("unknown operator %s (K, G, GT, Z)", op); return CFD_ERR_ARG; }
+   if (o == "Z" && c->P.scheme != CFD_IMPLICIT) { set_error("operator Z (FE Laplacian) needs an implicit context; the explicit Z = G^T Md^-1 G is a product of G applies"); return CFD_ERR_ARG; }
+   const size_t nx = fromP ? (size_t)NNp : 3 * (size_t)NN, ny = toP ? (size_t)NNp : 3 * (size_t)NN;
+   double *dx = nullptr, *dy = nullptr;
+   CFD_CK(cudaMalloc(&dx, sizeof(double) * nx));
+   CFD_CK(cudaMalloc(&dy, sizeof(double) * ny));
+   CFD_CK(cudaMemcpy(dx, x, sizeof(double) * nx, cudaMemcpyHostToDevice));
+   // K of an implicit context: vals[0] holds M + K, vals[1] M; the explicit layout keeps K alone
+   if (o == "K" && path == 0 && c->P.scheme == CFD_IMPLICIT) { cudaFree(dx); cudaFree(dy); set_error("assembled K alone is kept by explicit contexts only"); return CFD_ERR_ARG; }
+   Bytes nb(0.0);
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   float best = 1e30f;
+   for (int it = 0; it < std::max(1, repeat); it++) {
+      cudaEventRecord(e0, c->stream);
+      if (path == 0) {
+         if (o == "K") { k_spmv_multi<3><<<gridFor((long long)c->K.nslices * 32, 256), 256, 0, c->stream>>>(c->K, 0, dx, NN, dy, NN, 1.0, 0.0); nb = spmv_bytes(c->K, 1, 3, false); }
+         else if (o == "G") { k_g_apply<<<gridFor((long long)c->G.nslices * 32, 256), 256, 0, c->stream>>>(c->G, NN, dx, dy); nb = spmv_bytes(c->G, 3, 1, false) + Bytes(16.0 * NN); }
+         else if (o == "GT") { k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 1, dx, nullptr, 0, nullptr, 1.0, -1, dy); nb = spmv_bytes(c->GT, 3, 3, false); }
+         else { k_spmv_multi<1><<<gridFor((long long)c->Z.nslices * 32, 256), 256, 0, c->stream>>>(c->Z, 0, dx, NNp, dy, NNp, 1.0, 0.0); nb = spmv_bytes(c->Z, 1, 1, false); }
+      } else {
+         CFD_CK(cudaMemsetAsync(dy, 0, sizeof(double) * ny, c->stream));
+         if (o == "K") {
+            if (c->P.NENv == 27) k_ebe_momentum_apply<27, kEbeVisc><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, nullptr, dx, nullptr, c->P.viscosity, invRho, 1.0, dy);
+            else k_ebe_momentum_apply<8, kEbeVisc><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, nullptr, dx, nullptr, c->P.viscosity, invRho, 1.0, dy);
+            nb = Bytes(mf_bytes(c, 3 * nv, 3 * nv));
+         } else if (o == "G") {
+            if (c->P.NENv == 27) k_ebe_momentum_apply<27, kEbePres><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, nullptr, nullptr, dx, c->P.viscosity, invRho, 1.0, dy);
+            else k_ebe_momentum_apply<8, kEbePres><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, nullptr, nullptr, dx, c->P.viscosity, invRho, 1.0, dy);
+            nb = Bytes(mf_bytes(c, 8, 3 * nv));
+         } else if (o == "GT") {
+            if (c->P.NENv == 27) k_ebe_gt_apply<27><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, 1, dx, nullptr, 0, nullptr, 1.0, invRho, dy);
+            else k_ebe_gt_apply<8><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, NN, c->ldE, c->LtoGT, c->coord, 1, dx, nullptr, 0, nullptr, 1.0, invRho, dy);
+            nb = Bytes(mf_bytes(c, 3 * nv, 8));
+         } else {
+            if (c->P.NENv == 27) k_ebe_laplace_apply<27><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, c->coord, dx, dy);
+            else k_ebe_laplace_apply<8><<<gridFor(NE, 128), 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, c->coord, dx, dy);
+            nb = Bytes((4.0 * 8 + 192.0 + 8.0 * 8 + 16.0 * 8) * (double)NE);
+         }
+      }
+      cudaEventRecord(e1, c->stream);
+      CFD_CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = std::min(best, ms);
+   }
+   CFD_CK(cudaGetLastError());
+   CFD_CK(cudaMemcpy(y, dy, sizeof(double) * ny, cudaMemcpyDeviceToHost));
+   if (o == "Z" && path == 1 && c->pin >= 0) {
+      // the assembled Z carries the pin (diagonal x 1000, applyBC_Step2, GQ.cpp:4677-4693): add the same term to the matrix-free product
+      // (999 * diagonal * x[pin]); the diagonal is what the Jacobi preconditioner stores
+      double dinv = 1.0;
+      CFD_CK(cudaMemcpy(&dinv, c->Zdinv + c->pin, sizeof(double), cudaMemcpyDeviceToHost));
+      if (!c->opt.cg_no_precond) y[c->pin] += (999.0 / 1000.0) / dinv * x[c->pin];
+   }
+   if (ms_per_call) *ms_per_call = best;
+   if (bytes) *bytes = path == 0 ? nb.l : nb.a;
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(dx); cudaFree(dy);
    return CFD_OK;
 }
 

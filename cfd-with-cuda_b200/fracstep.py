@@ -55,7 +55,7 @@ class cfd_options(C.Structure):
         ("cg_tol", C.c_double), ("cg_maxit", C.c_int), ("cg_warm_start", C.c_int),
         ("bicg_tol", C.c_double), ("bicg_maxit", C.c_int), ("maxacc_rule", C.c_int),
         ("device", C.c_int), ("ebe_scatter", C.c_int), ("cg_no_precond", C.c_int), ("deterministic", C.c_int), ("bicg_no_halfstep", C.c_int), ("bicg_no_verify", C.c_int), ("cg_variant", C.c_int),
-        ("reserved", C.c_int * 2), ("cuda_stream", C.c_void_p),
+        ("operator_path", C.c_int), ("reserved", C.c_int * 1), ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -123,6 +123,7 @@ def lib():
     L.cfd_csr_pcg_variant.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp]
     L.cfd_p2p_reset.argtypes = [vp]
     L.cfd_p2p_detach.argtypes = [vp]
+    L.cfd_operator_apply.argtypes = [vp, C.c_char_p, C.c_int, _dp, _dp, C.c_int, _dp, _dp]
     L.cfd_solver_create_from_inp.argtypes = [C.c_char_p, C.c_int, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
     L.cfd_solver_create_cavity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                            C.c_int, C.c_double, C.POINTER(cfd_options), C.c_int, C.POINTER(vp)]
@@ -336,6 +337,14 @@ class Context:
         ms = C.c_double()
         _check(self.L.cfd_timeStep_host(self.h, _d(U), _d(P), C.byref(rep), C.byref(ms)))
         return self._rep(rep), ms.value
+
+    def operator_apply(self, op, x, path=0, repeat=1):
+        """y = Op x through the assembled (path 0) or the matrix-free element (path 1) kernels; returns (y, best ms, algorithmic bytes)."""
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros(self.NNp if op in ("GT", "Z") else 3 * self.NN)
+        ms, nb = C.c_double(), C.c_double()
+        _check(self.L.cfd_operator_apply(self.h, op.encode(), path, _d(x), _d(y), repeat, C.byref(ms), C.byref(nb)))
+        return y, ms.value, nb.value
 
     def profile(self, enable=True):
         _check(self.L.cfd_profile(self.h, int(enable)))

@@ -122,7 +122,11 @@ typedef struct cfd_options {
                          2 = Chronopoulos-Gear single-reduction form (same iterates in exact arithmetic, one grid-wide / cross-GPU
                          reduction per iteration instead of two, 16 B per row more vector traffic).  Both meet the parity bar; the
                          classical form measured faster on B200 at every size tried (profiles/r02_cg_variants.md) */
-   int reserved[2];
+   int operator_path; /* 0 (default) = K, G, G^T applied from the assembled CSR arrays (Sell layout); 1 = matrix-free: the explicit scheme's
+                         operator applications (step 1: -C(U)U - K U - G P in ONE element pass, step 2: G^T d, step 3: G Pdot, K Acc) are
+                         evaluated element by element from the integrals of step0 (BCH.cpp:3127-3315), no matrix stream.  Same
+                         results to rounding.  Single GPU; the pressure solve keeps its assembled Z */
+   int reserved[1];
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 
@@ -252,6 +256,12 @@ long long cfd_kernel_launches(cfd_ctx* ctx); /* kernels launched by this context
 /* layout statistics of a device matrix ("K", "G", "GT", "Z"): true non-zeros, stored value slots (padding included),
  * stored index integers (after per-slice offset compression), lanes per row */
 int cfd_matrix_stats(cfd_ctx* ctx, const char* name, long long* nnz, long long* stored_values, long long* stored_indices, int* lanes_per_row);
+
+/* One operator of the path applied both ways on a context's mesh (micro-benchmark "EBE vs CSR", parity test of the matrix-free
+ * kernels): op = "K" (x [3NN] -> y [3NN]), "G" (x [NNp] -> y [3NN]), "GT" (x [3NN] -> y [NNp]), "Z" (implicit contexts: the FE
+ * Laplacian, x [NNp] -> y [NNp]); path 0 = assembled (Sell SpMV), 1 = matrix-free element kernels.  x, y are host arrays;
+ * *ms_per_call = best CUDA-event time of `repeat` launches; *bytes = algorithmic bytes of one launch in that path's own model. */
+int cfd_operator_apply(cfd_ctx* ctx, const char* op, int path, const double* x, double* y, int repeat, double* ms_per_call, double* bytes);
 
 /* ---- stand-alone kernels on caller data (micro-benchmarks and parity tests) ------------------- */
 /* y = alpha*A*x + beta*y for `nvec` vectors sharing one CSR matrix; x is [nvec][ncols], y [nvec][nrows] host arrays */

@@ -573,3 +573,58 @@ def test_pcg_against_library_solver(mesh):
                       R2.ctypes.data_as(dp), x.ctypes.data_as(dp), 1e-6, 1000, C.byref(its), C.byref(ms)) == 0
     assert abs(its.value - its_ours) <= 1
     assert rel(x_ours, x) <= 1e-9
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matrix_free_operators_equal_the_assembled_ones(mesh, name):
+    """cfd_options.operator_path / cfd_operator_apply: K, G, G^T and the FE Laplacian applied element by element from the integrals of
+    step0 (BCH.cpp:3127-3315, GQ.cpp:3677-3772) equal the assembled (Sell SpMV) products to summation-order rounding -- and both equal
+    scipy on the oracle's CSR arrays."""
+    import scipy.sparse as sp
+    import fracstep
+    import orc
+    rng = np.random.default_rng(3)
+    for scheme in ("explicit", "implicit"):
+        o = orc.Oracle(mesh(name, **CASES[name]), scheme)
+        c = fracstep.Context(fracstep.Problem(o, scheme), None)
+        NN, NNp = o.i("NN"), o.i("NNp")
+        K = sp.csr_matrix((o.arr("sparseKvalue"), o.arr("sparseMcol"), o.arr("sparseMrowStarts")), shape=(NN, NN))
+        G = [sp.csr_matrix((o.arr("sparseG%dvalue" % d), o.arr("sparseGcol"), o.arr("sparseGrowStarts")), shape=(NN, NNp)) for d in (1, 2, 3)]
+        xv, xp = rng.standard_normal(3 * NN), rng.standard_normal(NNp)
+        ref = {"K": np.concatenate([K @ xv[d * NN:(d + 1) * NN] for d in range(3)]),
+               "G": np.concatenate([G[d] @ xp for d in range(3)]),
+               "GT": sum(G[d].T @ xv[d * NN:(d + 1) * NN] for d in range(3))}
+        ops = ["K", "G", "GT"]
+        if scheme == "implicit":
+            Z = sp.csr_matrix((o.arr("sparseZvalue"), o.arr("sparseZcol"), o.arr("sparseZrowStarts")), shape=(NNp, NNp))
+            ref["Z"] = Z @ xp
+            ops.append("Z")
+        for op in ops:
+            x = xp if op in ("G", "Z") else xv
+            y1, _, _ = c.operator_apply(op, x, path=1)
+            assert rel(y1, ref[op]) < 1e-12, (scheme, op, rel(y1, ref[op]))
+            if not (op == "K" and scheme == "implicit"):   # (implicit contexts keep M + K and M, not K alone)
+                y0, _, _ = c.operator_apply(op, x, path=0)
+                assert rel(y0, ref[op]) < 1e-13, (scheme, op, rel(y0, ref[op]))
+        c.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matrix_free_time_loop(mesh, name):
+    """The explicit time loop with operator_path = 1 (step 1 = ONE element pass for -C(U)U - K U - G P; G^T, G Pdot and K Acc element by
+    element): same fields as the oracle (1e-6), same inner iterations and CG counts, and equal to the assembled path to rounding."""
+    import fracstep
+    import orc
+    o = orc.Oracle(mesh(name, **CASES[name]), "explicit")
+    o.run(4)
+    out = {}
+    for path in (0, 1):
+        c = fracstep.Context(fracstep.Problem(o, "explicit"), fracstep.options(operator_path=path))
+        reps = c.time_loop(4)
+        out[path] = c.fields()
+        U, P = out[path]
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-5, (path, rel(U, o.U), rel(P, o.P))
+        assert [r["iter"] for r in reps] == list(o.arr("innerIters"))
+        assert abs(sum(r["cg_iterations"] for r in reps) - int(o.arr("cgIters").sum())) <= 2 * len(o.arr("cgIters"))
+        c.close()
+    assert rel(out[1][0], out[0][0]) <= 1e-9 and rel(out[1][1], out[0][1]) <= 1e-6   # (P: CG stopped at 1e-6 on both)
