@@ -27,6 +27,9 @@ WORKLOADS = {
     "cavity128_q1_implicit": dict(n=128, NENv=8, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity128_q1_explicit": dict(n=128, NENv=8, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity64_q2_explicit": dict(n=64, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity96_q2_explicit": dict(n=96, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity128_q2_explicit": dict(n=128, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    "cavity128_q2_implicit": dict(n=128, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity64_q2_implicit": dict(n=64, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     # configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (30^3 Q2/Q1, sinh clustering 2.0)
     "ne27000_explicit": dict(n=30, NENv=27, scheme="explicit", cluster=2.0, viscosity=0.01, dt=1e-3, inp=True),
@@ -227,6 +230,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cg-variant", type=int, default=0, help="cfd_options.cg_variant: 0 library default, 1 classical PCG, 2 single-reduction PCG")
     ap.add_argument("--deterministic", type=int, default=0, help="cfd_options.deterministic")
+    ap.add_argument("--path", default="csr", choices=["csr", "ebe"],
+                    help="operator path of the explicit scheme: csr = assembled matrices (Sell SpMV), ebe = matrix-free element kernels (cfd_options.operator_path)")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
     sz = sizes(w)
@@ -276,7 +281,7 @@ def main():
         fracstep.build()
     if dist is not None:
         dist.barrier()
-    opts = fracstep.options(device=local_rank, cg_variant=a.cg_variant, deterministic=a.deterministic)
+    opts = fracstep.options(device=local_rank, cg_variant=a.cg_variant, deterministic=a.deterministic, operator_path=1 if a.path == "ebe" else 0)
     t0 = time.time()
     tmp = None
     if w.get("inp"):
@@ -383,7 +388,7 @@ def main():
                        share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
     config.update(parallelism="1 GPU" if world == 1 else "%d element blocks (z-slabs), one per GPU; peer-memory Krylov kernels + NCCL halo swap / allreduce" % world,
                   l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["layout_bytes"] for v in prof.values()) / a.steps / 1e9),
-                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps), cg_variant=a.cg_variant,
+                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps), cg_variant=a.cg_variant, operator_path=a.path,
                   bicgstab_iterations_last_step=reps[-1]["bicg_iterations"])
     krylov_ok = all(r["cg_converged"] for r in reps) and all(all(r["bicg_converged"]) for r in reps)
     line = dict(metric="time steps/s", value=n_rep * a.steps / (ms_max * 1e-3), unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
