@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 
 #include <dlfcn.h>
 
@@ -161,15 +162,18 @@ int sell_upload(const SellHost& h, int nval, const double* const* csrVals, Sell&
    CFD_CK(cudaMemcpy(d.colOff, h.colOff.data(), sizeof(long long) * h.colOff.size(), cudaMemcpyHostToDevice));
    CFD_CK(cudaMalloc(&d.cols, sizeof(int) * std::max<size_t>(h.cols.size(), 2)));
    CFD_CK(cudaMemcpy(d.cols, h.cols.data(), sizeof(int) * h.cols.size(), cudaMemcpyHostToDevice));
-   std::vector<double> tmp;
+   std::unique_ptr<double[]> tmp;   // staging in layout order: allocated once, zero-filled and scattered in parallel (multi-GB arrays)
    for (int v = 0; v < nval; v++) {
       CFD_CK(cudaMalloc(&d.vals[v], sizeof(double) * std::max<size_t>((size_t)d.padded, 2)));
       if (csrVals && csrVals[v]) {
-         tmp.assign((size_t)d.padded, 0.0);
+         if (!tmp) tmp.reset(new double[std::max<size_t>((size_t)d.padded, 2)]);
+         double* t = tmp.get();
          const double* src = csrVals[v];
 #pragma omp parallel for schedule(static)
-         for (long long k = 0; k < d.nnz; k++) tmp[(size_t)h.perm[(size_t)k]] = src[k];
-         CFD_CK(cudaMemcpy(d.vals[v], tmp.data(), sizeof(double) * (size_t)d.padded, cudaMemcpyHostToDevice));
+         for (long long k = 0; k < d.padded; k++) t[k] = 0.0;
+#pragma omp parallel for schedule(static)
+         for (long long k = 0; k < d.nnz; k++) t[(size_t)h.perm[(size_t)k]] = src[k];
+         CFD_CK(cudaMemcpy(d.vals[v], t, sizeof(double) * (size_t)d.padded, cudaMemcpyHostToDevice));
       } else {
          CFD_CK(cudaMemset(d.vals[v], 0, sizeof(double) * (size_t)d.padded));
       }
@@ -1404,6 +1408,12 @@ __global__ void __launch_bounds__(1024) k_diag_sync(int iters, int mode, double*
    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = acc;
 }
 
+#ifndef CFD_BICG_UNROLL1
+#define CFD_BICG_UNROLL1 8
+#endif
+#ifndef CFD_BICG_UNROLL2
+#define CFD_BICG_UNROLL2 6
+#endif
 // peer-memory exchange of the velocity-row vectors the momentum SpMV gathers (partitioned runs)
 struct XVel {
    double* const* peerV;   // [npeers] start of MY block inside the peer's ghost range of its ph region (shv region: + 3 * peerLd)
@@ -1471,7 +1481,9 @@ __device__ __forceinline__ void bicg_spmv_na(const Sell& A, const int* part, int
       double acc[NA];
 #pragma unroll
       for (int q = 0; q < NA; q++) acc[q] = 0.0;
-      sell_pairs<4>(A, s, lane, [&](long long e, int2 c2) {
+      // a warp works through its slices one after the other, so the sweep is latency-bound per warp at 2 CTAs per SM: the fewer
+      // right-hand sides are left, the more matrix pairs are kept in flight per lane (CFD_BICG_UNROLL1 / 2: tuning override)
+      sell_pairs<(NA == 1 ? CFD_BICG_UNROLL1 : (NA == 2 ? CFD_BICG_UNROLL2 : 4))>(A, s, lane, [&](long long e, int2 c2) {
          const double2 v2 = ldnc_d2(val + e);
 #pragma unroll
          for (int q = 0; q < NA; q++) acc[q] += v2.x * in[base[q] + c2.x] + v2.y * in[base[q] + c2.y];
@@ -2407,8 +2419,11 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    // ---- matrices -> Sell.  The velocity-row matrices (K/M/A and G) share one row partition (same T).
    const int Tv = choose_Tv(NNo, P->sparseMrowStarts[NNo]);
+   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z arrive on ONE pattern (same arrays): its layout is built once and shared
+   SellHost hK;
+   const bool sameG = P->sparseGrowStarts == P->sparseMrowStarts && P->sparseGcol == P->sparseMcol && NNp == NN && NPo == NNo;
    {
-      SellHost h;
+      SellHost& h = hK;
       sell_build_host(NNo, NN, P->sparseMrowStarts, P->sparseMcol, Tv, h);
       c->hostOffK = h.sliceOff;
       if (P->scheme == CFD_EXPLICIT) {
@@ -2416,21 +2431,23 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          TRY(sell_upload(h, 1, v, c->K));
       } else {
          const long long nnzOwned = P->sparseMrowStarts[NNo];
-         std::vector<double> mk((size_t)nnzOwned);
+         std::unique_ptr<double[]> mk(new double[std::max<size_t>((size_t)nnzOwned, 1)]);
 #pragma omp parallel for schedule(static)
          for (long long k = 0; k < nnzOwned; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
-         const double* v[3] = {mk.data(), P->sparseMvalue, nullptr};
+         const double* v[3] = {mk.get(), P->sparseMvalue, nullptr};
          TRY(sell_upload(h, 3, v, c->K));
          // element -> Sell position map, transposed to [q][e]
          c->ldE = (NE + 31) & ~31;
-         std::vector<int> mt((size_t)nv * nv * c->ldE, 0);
+         const size_t nmt = (size_t)nv * nv * c->ldE;
+         std::unique_ptr<int[]> mt(new int[nmt]);   // (1 G entries at 256^3: filled in parallel, padding columns included)
 #pragma omp parallel for schedule(static)
-         for (int e = 0; e < NE; e++)
+         for (int e = 0; e < c->ldE; e++)
             for (int q = 0; q < nv * nv; q++) {
+               if (e >= NE) { mt[(size_t)q * c->ldE + e] = 0; continue; }
                const int row = P->LtoGnode[(size_t)e * nv + q / nv];
                mt[(size_t)q * c->ldE + e] = row < NNo ? (int)h.perm[(size_t)P->sparseMapM_1d[(size_t)e * nv * nv + q]] : -1;
             }
-         TRY(dupload(c, &c->mapT, mt.data(), mt.size()));
+         TRY(dupload(c, &c->mapT, mt.get(), nmt));
          std::vector<int> dp(NNo, 0);
 #pragma omp parallel for schedule(static)
          for (int r = 0; r < NNo; r++)
@@ -2441,35 +2458,64 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    IPHASE("Sell K/M/A + maps");
    {
-      SellHost h;
-      sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, h);
+      SellHost hOwn;
+      if (!sameG) sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, hOwn);
       const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
-      TRY(sell_upload(h, 3, v, c->G));
+      TRY(sell_upload(sameG ? hK : hOwn, 3, v, c->G));
    }
    IPHASE("Sell G");
    {
       // explicit transpose of the G pattern: rows = pressure nodes (instead of the reference's
-      // OPERATION_TRANSPOSE csrmv scatter, BCH.cu:1006-1009)
+      // OPERATION_TRANSPOSE csrmv scatter, BCH.cu:1006-1009).  Parallel: count, prefix sum, scatter in any order, then every
+      // transposed row is put into ascending column order (deterministic result).
       const int nnzG = P->sparseG_nnz;
-      std::vector<int> ts(NNp + 1, 0), tcol(nnzG);
-      std::vector<double> t1(nnzG), t2(nnzG), t3(nnzG);
-      for (int k = 0; k < nnzG; k++) ts[P->sparseGcol[k] + 1]++;
+      std::vector<int> ts((size_t)NNp + 1, 0), tcol((size_t)nnzG), tsrc((size_t)nnzG);
+      std::unique_ptr<double[]> t1(new double[(size_t)nnzG]), t2(new double[(size_t)nnzG]), t3(new double[(size_t)nnzG]);   // (no serial zero fill)
+#pragma omp parallel for schedule(static)
+      for (int k = 0; k < nnzG; k++) {
+#pragma omp atomic
+         ts[(size_t)P->sparseGcol[k] + 1]++;
+      }
       for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
-      std::vector<int> fill(ts.begin(), ts.end() - 1);
-      for (int r = 0; r < NN; r++)
-         for (int k = P->sparseGrowStarts[r]; k < P->sparseGrowStarts[r + 1]; k++) {
-            const int p = fill[P->sparseGcol[k]]++;
-            tcol[p] = r; t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k];
+      {
+         std::vector<int> fill(ts.begin(), ts.end() - 1);
+#pragma omp parallel for schedule(static)
+         for (int r = 0; r < NN; r++)
+            for (int k = P->sparseGrowStarts[r]; k < P->sparseGrowStarts[r + 1]; k++) {
+               int p;
+#pragma omp atomic capture
+               p = fill[P->sparseGcol[k]]++;
+               tcol[p] = r; tsrc[p] = k;
+            }
+      }
+#pragma omp parallel
+      {
+         std::vector<std::pair<int, int> > row;
+#pragma omp for schedule(static)
+         for (int j = 0; j < NNp; j++) {
+            row.clear();
+            for (int p = ts[j]; p < ts[j + 1]; p++) row.push_back(std::make_pair(tcol[p], tsrc[p]));
+            std::sort(row.begin(), row.end());
+            for (int p = ts[j], q = 0; p < ts[j + 1]; p++, q++) {
+               const int k = row[q].second;
+               tcol[p] = row[q].first;
+               t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k];
+            }
          }
+      }
+      std::vector<int>().swap(tsrc);
       SellHost h;
       sell_build_host(NPo, NN, ts.data(), tcol.data(), choose_T(NPo, ts[NPo]), h);   // rows = owned pressure DOFs, all local velocity columns
-      const double* v[3] = {t1.data(), t2.data(), t3.data()};
+      const double* v[3] = {t1.get(), t2.get(), t3.get()};
       TRY(sell_upload(h, 3, v, c->GT));
    }
    IPHASE("Sell G^T");
    {
-      SellHost h;
-      sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, choose_T(NPo, P->sparseZrowStarts[NPo]), h);
+      const int Tz = choose_T(NPo, P->sparseZrowStarts[NPo]);
+      const bool sameZ = sameG && Tz == Tv && P->sparseZrowStarts == P->sparseMrowStarts && P->sparseZcol == P->sparseMcol;
+      SellHost hOwn;
+      if (!sameZ) sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, Tz, hOwn);
+      SellHost& h = sameZ ? hK : hOwn;
       c->hostOffZ = h.sliceOff;
       const double* v[1] = {P->sparseZvalue};
       TRY(sell_upload(h, 1, v, c->Z));
