@@ -1546,7 +1546,7 @@ enum { kBicgMaxRestarts = 12 };
 struct BicgScalars {
    double bb[3], rr[3], rrs[3], thresh[3], alpha[3], omega[3], trueRR[3], bestRR[3], prevTrue[3];
    int its[3], act[3], half[3], act2[3], chk[3], brk[3], fin[3], restarts[3], hasBest[3];
-   int todo[3];   // after a check: 0 nothing, 1 restart, 3 restart + remember x as the best iterate, 2 give back the best iterate
+   int todo[3];   // after a check: 0 nothing, 1 restart, 3 restart + remember x as the best iterate, 2 give back the best iterate, 4 give back x = 0
    int passes;
 };
 
@@ -1681,7 +1681,8 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
                   // out of iterations, or restarts no longer gain (attainable accuracy reached): stop, unconverged, best iterate
                   S.act[c] = 0; S.fin[c] = 2;
                   if (!improved && S.hasBest[c]) { S.todo[c] = 2; S.trueRR[c] = S.bestRR[c]; }
-                  else if (improved) S.bestRR[c] = tr;
+                  else if (!improved) { S.todo[c] = 4; S.trueRR[c] = S.bb[c]; }   // nothing verified beats the initial guess: return x = 0
+                  else S.bestRR[c] = tr;
                } else {
                   S.todo[c] = improved ? 3 : 1;   // restart (3: and remember x as the best iterate so far)
                   if (improved) { S.bestRR[c] = tr; S.hasBest[c] = 1; }
@@ -1700,6 +1701,7 @@ __global__ void __launch_bounds__(512, 2) k_bicgstab3(BicgArgs a) {
                for (int i = tid; i < n; i += nthreads) {
                   const size_t k = (size_t)c * ld + i;
                   if (todo == 2) { a.x[k] = xbest[k]; continue; }
+                  if (todo == 4) { a.x[k] = 0.0; continue; }
                   const double ri = AMs[k];
                   r[k] = ri; rs[k] = ri; p[k] = ri;
                   const double phi = a.dinv[i] * ri;
