@@ -1096,6 +1096,99 @@ __global__ void __launch_bounds__(512, MINB) k_pcg_t(PcgArgs a) {
 // two register budgets of the same kernel: 3 CTAs/SM (40 registers) or 2 CTAs/SM (64 registers); chosen at init
 static void* pcg_kernel(int minb) { return minb == 2 ? (void*)k_pcg_t<2> : (void*)k_pcg_t<3>; }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Jacobi-PCG with the MATRIX RESIDENT IN SHARED MEMORY for the whole solve: small pressure systems (the reference's shipped
+// 30^3 input: Z = G^T Md^-1 G, 29 791 rows, 3.3 M non-zeros = 27 MB of values) fit into the 148 x 227 KB of shared memory of a
+// B200.  One CTA of 1024 threads per SM owns a contiguous range of slices (balanced by bytes, <= 32 slices = one per warp) and
+// copies their values in once; every CG iteration then reads the matrix from shared memory (LDS.128) instead of streaming it
+// from L2 -- what is left per iteration is the p gather, three vector passes and the three grid-wide synchronisations, now over
+// 148 CTAs.  Same recurrences and the same arithmetic per row as k_pcg_t; the dot-product partials are grouped by other CTAs, so the
+// iterates agree to rounding, not bitwise.  Statically scheduled: bitwise reproducible from run to run.  Column indices stay
+// where they are (compressed offset lists are a few hundred bytes per slice and live in L1).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct PcgSmemArgs {
+   PcgArgs a;            // a.part = slice range per CTA [gridDim + 1]
+};
+__global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
+   cg::grid_group grid = cg::this_grid();
+   extern __shared__ double zs[];   // this CTA's slices' values, in layout order
+   __shared__ double sh[3 * 32];
+   const PcgArgs& a = pa.a;
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int nthreads = gridDim.x * blockDim.x;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   double* buf0 = a.scratch;
+   double* buf1 = a.scratch + 3 * (size_t)gridDim.x;
+   const int n = a.n;
+   const int s0 = a.part[blockIdx.x], s1 = a.part[blockIdx.x + 1];
+   const long long e0 = a.Z.sliceOff[s0], e1 = a.Z.sliceOff[s1];
+   {
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(a.Z.vals[0] + e0);
+      double2* dst = reinterpret_cast<double2*>(zs);
+      for (long long k = threadIdx.x; k < ((e1 - e0) >> 1); k += blockDim.x) dst[k] = src[k];
+   }
+   __syncthreads();
+   // q = Z p on this CTA's slices (one per warp), matrix values from shared memory; returns this lane's share of p.q
+   auto spmv = [&](const double* p, double* q) {
+      double pq = 0.0;
+      for (int s = s0 + warp; s < s1; s += (blockDim.x >> 5)) {
+         const int T = a.Z.T, sub = lane % T;
+         double acc = 0.0;
+         sell_pairs<4>(a.Z, s, lane, [&](long long e, int2 c2) {
+            const double2 v2 = *reinterpret_cast<const double2*>(zs + (e - e0));
+            acc += v2.x * p[c2.x] + v2.y * p[c2.y];
+         });
+         for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+         const int row = s * a.Z.R + lane / T;
+         if (sub == 0 && row < a.Z.nrows) { q[row] = acc; pq += p[row] * acc; }
+      }
+      return pq;
+   };
+   if (!a.x0zero) {
+      spmv(a.x, a.q);
+      grid.sync();
+   }
+   double v3[3] = {0, 0, 0};
+   for (int i = tid; i < n; i += nthreads) {
+      const double bi = a.b[i];
+      double ri = bi;
+      if (a.x0zero) a.x[i] = 0.0; else ri = bi - a.q[i];
+      const double zi = a.dinv[i] * ri;
+      a.r[i] = ri;
+      a.p[i] = zi;
+      v3[0] += ri * zi; v3[1] += bi * bi; v3[2] += ri * ri;
+   }
+   grid_sum<3>(grid, v3, buf0, sh);
+   double rz = v3[0];
+   const double bb = v3[1];
+   double rr = v3[2];
+   const double thresh = a.tol * sqrt(bb);
+   int it = 0;
+   while (true) {
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;
+      double v1[1];
+      v1[0] = spmv(a.p, a.q);
+      grid_sum<1>(grid, v1, buf1, sh);
+      const double alpha = rz / v1[0];
+      double v2[2] = {0, 0};
+      for (int i = tid; i < n; i += nthreads) {
+         a.x[i] += alpha * a.p[i];
+         const double ri = a.r[i] - alpha * a.q[i];
+         a.r[i] = ri;
+         v2[0] += ri * (a.dinv[i] * ri);
+         v2[1] += ri * ri;
+      }
+      grid_sum<2>(grid, v2, buf0, sh);
+      const double beta = v2[0] / rz;
+      rz = v2[0];
+      rr = v2[1];
+      for (int i = tid; i < n; i += nthreads) a.p[i] = a.dinv[i] * a.r[i] + beta * a.p[i];
+      it++;
+      grid.sync();
+   }
+   if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
+}
+
 struct PcgP2PArgs {
    PcgArgs a;   // a.p lives in this rank's exchange window
    XComm xc;
@@ -2166,6 +2259,17 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
+   if (c->pcgSmemBytes > 0) {   // small system: matrix resident in shared memory, one CTA per SM
+      PcgSmemArgs pa;
+      pa.a = a;
+      pa.a.part = c->pcgSmemPart; pa.a.dynCounter = nullptr; pa.a.dynStart = c->Z.nslices;
+      void* sargs[] = {&pa};
+      ProfScope ps(c, "pcg", x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false));
+      c->lastPcgRec = ps.idx;
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_smem, dim3(c->numSMs), dim3(1024), sargs, c->pcgSmemBytes, c->stream));
+      c->launches++;
+      return CFD_OK;
+   }
    void* args[] = {&a};
    ProfScope ps(c, "pcg", x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false));
    c->lastPcgRec = ps.idx;
@@ -2712,6 +2816,40 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          c->pcgcgPart = c->pcgPart; c->pcgcg_blocks = c->pcg_blocks;
          c->pcgDynStart = dynStart;
          if (useDyn) TRY(dalloc(c, &c->pcgDynCounter, 4));
+         // Shared-memory-resident matrix (k_pcg_smem): one CTA per SM takes a contiguous slice range of at most 32 slices (one per
+         // warp) whose values fit into its shared memory.  Greedy fill in slice order with an even byte target; not eligible if the
+         // ranges do not cover the matrix (too large, or too many slices) -- then the streaming kernel above runs.
+         if (!parted && c->cg_variant != 2 && getenv("CFD_NO_PCG_SMEM") == nullptr) {
+            int maxOptin = 0;
+            CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+            const long long cap = (long long)maxOptin - 1024 - 3 * 32 * 8;   // static shared memory of the kernel + slack
+            const long long total = c->hostOffZ[nsZ] * 8;
+            if (nsZ <= 32 * c->numSMs && total <= cap * c->numSMs) {
+               std::vector<int> ps(c->numSMs + 1, nsZ);
+               long long maxBytes = 0;
+               int s = 0;
+               bool ok = true;
+               for (int b = 0; b < c->numSMs; b++) {
+                  ps[b] = s;
+                  const long long target = (long long)((double)c->hostOffZ[nsZ] * (b + 1) / c->numSMs);   // even share, in entries
+                  const int sBegin = s;
+                  while (s < nsZ && s - sBegin < 32 && (c->hostOffZ[s + 1] - c->hostOffZ[sBegin]) * 8 <= cap &&
+                         (c->hostOffZ[s + 1] <= target || s == sBegin)) s++;
+                  maxBytes = std::max(maxBytes, (c->hostOffZ[s] - c->hostOffZ[sBegin]) * 8);
+               }
+               ps[c->numSMs] = s;
+               ok = s == nsZ;
+               if (ok) {
+                  CFD_CK(cudaFuncSetAttribute(k_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
+                  int occS = 0;
+                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_pcg_smem, 1024, (size_t)maxBytes));
+                  if (occS >= 1) {
+                     TRY(dupload(c, &c->pcgSmemPart, ps.data(), ps.size()));
+                     c->pcgSmemBytes = (size_t)maxBytes;
+                  }
+               }
+            }
+         }
       }
       if (P->scheme == CFD_IMPLICIT) {
          // large matrices: static share (contiguous chunk per CTA, its gathered window stays in L1) + dynamic tail as for Z;

@@ -134,6 +134,8 @@ struct cfd_ctx {
    int* bicgDynCounter = nullptr;
    int *pcgPart = nullptr, *bicgPart = nullptr;   // [blocks+1] slice ranges per block, balanced by stored entries
    int* pcgcgPart = nullptr;                      // (= pcgPart: the context runs one of the two PCG kernels)
+   int* pcgSmemPart = nullptr;                    // [numSMs+1] slice ranges of the shared-memory-resident PCG (small systems)
+   size_t pcgSmemBytes = 0;                       // its dynamic shared memory per CTA; 0 = not eligible
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
    int timeN = 0;

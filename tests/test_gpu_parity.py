@@ -628,3 +628,28 @@ def test_matrix_free_time_loop(mesh, name):
         assert abs(sum(r["cg_iterations"] for r in reps) - int(o.arr("cgIters").sum())) <= 2 * len(o.arr("cgIters"))
         c.close()
     assert rel(out[1][0], out[0][0]) <= 1e-9 and rel(out[1][1], out[0][1]) <= 1e-6   # (P: CG stopped at 1e-6 on both)
+
+
+def test_shared_memory_resident_pcg_equals_the_streaming_kernel(mesh, monkeypatch):
+    """Small pressure systems run k_pcg_smem (matrix values resident in shared memory for the whole solve, one CTA per SM); larger ones
+    the streaming kernel k_pcg_t.  Same recurrences: on the same system both give the same iteration count and the same solution to
+    rounding -- checked through the explicit time loop of a mesh small enough for the resident kernel, with and without it."""
+    import fracstep
+    import orc
+    path = mesh("q2_c6_smem", n=6, cluster=2.0)
+    o = orc.Oracle(path, "explicit")
+    o.run(3)
+    out = {}
+    for resident in (True, False):
+        if resident:
+            monkeypatch.delenv("CFD_NO_PCG_SMEM", raising=False)
+        else:
+            monkeypatch.setenv("CFD_NO_PCG_SMEM", "1")
+        c = fracstep.Context(fracstep.Problem(o, "explicit"), None)
+        reps = c.time_loop(3)
+        out[resident] = (c.fields(), [r["cg_iterations"] for r in reps])
+        U, P = out[resident][0]
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-5
+        c.close()
+    assert out[True][1] == out[False][1]
+    assert rel(out[True][0][0], out[False][0][0]) <= 1e-12 and rel(out[True][0][1], out[False][0][1]) <= 1e-9
