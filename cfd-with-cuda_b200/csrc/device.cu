@@ -1099,7 +1099,7 @@ static void* pcg_kernel(int minb) { return minb == 2 ? (void*)k_pcg_t<2> : (void
 // ---------------------------------------------------------------------------------------------------------------------------
 // Jacobi-PCG with the MATRIX RESIDENT IN SHARED MEMORY for the whole solve: small pressure systems (the reference's shipped
 // 30^3 input: Z = G^T Md^-1 G, 29 791 rows, 3.3 M non-zeros = 27 MB of values) fit into the 148 x 227 KB of shared memory of a
-// B200.  One CTA of 1024 threads per SM owns a contiguous range of slices (balanced by bytes, <= 32 slices = one per warp) and
+// B200.  One CTA of 1024 threads per SM owns a contiguous range of slices (balanced by bytes, dealt to its 32 warps) and
 // copies their values in once; every CG iteration then reads the matrix from shared memory (LDS.128) instead of streaming it
 // from L2 -- what is left per iteration is the p gather, three vector passes and the three grid-wide synchronisations, now over
 // 148 CTAs.  Same recurrences and the same arithmetic per row as k_pcg_t; the dot-product partials are grouped by other CTAs, so the
@@ -2816,15 +2816,15 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          c->pcgcgPart = c->pcgPart; c->pcgcg_blocks = c->pcg_blocks;
          c->pcgDynStart = dynStart;
          if (useDyn) TRY(dalloc(c, &c->pcgDynCounter, 4));
-         // Shared-memory-resident matrix (k_pcg_smem): one CTA per SM takes a contiguous slice range of at most 32 slices (one per
-         // warp) whose values fit into its shared memory.  Greedy fill in slice order with an even byte target; not eligible if the
-         // ranges do not cover the matrix (too large, or too many slices) -- then the streaming kernel above runs.
+         // Shared-memory-resident matrix (k_pcg_smem): one CTA per SM takes a contiguous slice range whose values fit into its
+         // shared memory (its 32 warps deal the slices among themselves).  Greedy fill in slice order with an even byte target; not
+         // eligible if the ranges do not cover the matrix (too large) -- then the streaming kernel above runs.
          if (!parted && c->cg_variant != 2 && getenv("CFD_NO_PCG_SMEM") == nullptr) {
             int maxOptin = 0;
             CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
             const long long cap = (long long)maxOptin - 1024 - 3 * 32 * 8;   // static shared memory of the kernel + slack
             const long long total = c->hostOffZ[nsZ] * 8;
-            if (nsZ <= 32 * c->numSMs && total <= cap * c->numSMs) {
+            if (total <= cap * c->numSMs) {
                std::vector<int> ps(c->numSMs + 1, nsZ);
                long long maxBytes = 0;
                int s = 0;
@@ -2833,7 +2833,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                   ps[b] = s;
                   const long long target = (long long)((double)c->hostOffZ[nsZ] * (b + 1) / c->numSMs);   // even share, in entries
                   const int sBegin = s;
-                  while (s < nsZ && s - sBegin < 32 && (c->hostOffZ[s + 1] - c->hostOffZ[sBegin]) * 8 <= cap &&
+                  while (s < nsZ && (c->hostOffZ[s + 1] - c->hostOffZ[sBegin]) * 8 <= cap &&
                          (c->hostOffZ[s + 1] <= target || s == sBegin)) s++;
                   maxBytes = std::max(maxBytes, (c->hostOffZ[s] - c->hostOffZ[sBegin]) * 8);
                }
@@ -2851,6 +2851,10 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             }
          }
       }
+      if (verb)
+         fprintf(stderr, "[cfdb200 init] pressure CG: %s, Z %d rows, %d slices (T = %d), %.1f MB of values%s\n",
+                 c->pcgSmemBytes ? "k_pcg_smem (matrix resident in shared memory)" : (c->cg_variant == 2 ? "k_pcg_cg (single reduction)" : "k_pcg_t (streaming)"),
+                 c->Z.nrows, c->Z.nslices, c->Z.T, 8e-6 * (double)c->Z.padded, c->pcgSmemBytes ? "" : "");
       if (P->scheme == CFD_IMPLICIT) {
          // large matrices: static share (contiguous chunk per CTA, its gathered window stays in L1) + dynamic tail as for Z;
          // fewer than 4 slices per warp: everything through the counter (slice order = node order, long corner rows first)
