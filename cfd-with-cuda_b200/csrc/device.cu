@@ -1108,17 +1108,23 @@ static void* pcg_kernel(int minb) { return minb == 2 ? (void*)k_pcg_t<2> : (void
 // ---------------------------------------------------------------------------------------------------------------------------
 struct PcgSmemArgs {
    PcgArgs a;            // a.part = slice range per CTA [gridDim + 1]
+   double *s, *pp;       // single-reduction form only: s = Z p, and the search direction (a.p then holds u = M^-1 r, a.q holds w = Z u)
 };
+// SINGLE = true: the single-reduction (Chronopoulos-Gear) recurrences of k_pcg_cg -- TWO grid-wide synchronisations per iteration
+// instead of three.  Here everything but the synchronisations is cheap (matrix in shared memory, vectors in L2, 64 registers at one
+// CTA per SM anyway), so the form that loses on large streamed systems wins: measured on the shipped 30^3 input, us per CG
+// iteration: streaming classical 21.8, resident classical 16.4, resident single-reduction -> profiles/r02_cg_variants.md.
+template <bool SINGLE>
 __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
    cg::grid_group grid = cg::this_grid();
    extern __shared__ double zs[];   // this CTA's slices' values, in layout order
-   __shared__ double sh[3 * 32];
+   __shared__ double sh[4 * 32];
    const PcgArgs& a = pa.a;
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
    const int nthreads = gridDim.x * blockDim.x;
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    double* buf0 = a.scratch;
-   double* buf1 = a.scratch + 3 * (size_t)gridDim.x;
+   double* buf1 = a.scratch + 4 * (size_t)gridDim.x;
    const int n = a.n;
    const int s0 = a.part[blockIdx.x], s1 = a.part[blockIdx.x + 1];
    const long long e0 = a.Z.sliceOff[s0], e1 = a.Z.sliceOff[s1];
@@ -1128,7 +1134,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
       for (long long k = threadIdx.x; k < ((e1 - e0) >> 1); k += blockDim.x) dst[k] = src[k];
    }
    __syncthreads();
-   // q = Z p on this CTA's slices (one per warp), matrix values from shared memory; returns this lane's share of p.q
+   // q = Z p on this CTA's slices, matrix values from shared memory; returns this lane's share of p.q
    auto spmv = [&](const double* p, double* q) {
       double pq = 0.0;
       for (int s = s0 + warp; s < s1; s += (blockDim.x >> 5)) {
@@ -1147,6 +1153,54 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
    if (!a.x0zero) {
       spmv(a.x, a.q);
       grid.sync();
+   }
+   if (SINGLE) {
+      double* u = a.p; double* w = a.q; double* p = pa.pp; double* sv = pa.s;
+      double v4[4] = {0, 0, 0, 0};
+      for (int i = tid; i < n; i += nthreads) {
+         const double bi = a.b[i];
+         double ri = bi;
+         if (a.x0zero) a.x[i] = 0.0; else ri = bi - w[i];
+         a.r[i] = ri;
+         const double un = a.dinv[i] * ri;
+         u[i] = un;
+         v4[0] += ri * un; v4[2] += ri * ri; v4[3] += bi * bi;
+      }
+      grid.sync();
+      v4[1] = spmv(u, w);
+      grid_sum<4>(grid, v4, buf0, sh);
+      double gamma = v4[0], rr = v4[2];
+      const double bb = v4[3];
+      const double thresh = a.tol * sqrt(bb);
+      double alpha = gamma / v4[1], beta = 0.0;
+      int it = 0;
+      while (true) {
+         if (sqrt(rr) <= thresh || it >= a.maxit) break;
+         const bool first = it == 0;
+         double v3[3] = {0, 0, 0};
+         for (int i = tid; i < n; i += nthreads) {
+            const double ui = u[i], wi = w[i];
+            const double pi = first ? ui : ui + beta * p[i];
+            const double si = first ? wi : wi + beta * sv[i];
+            p[i] = pi; sv[i] = si;
+            a.x[i] += alpha * pi;
+            const double ri = a.r[i] - alpha * si;
+            a.r[i] = ri;
+            const double un = a.dinv[i] * ri;
+            u[i] = un;
+            v3[0] += ri * un; v3[2] += ri * ri;
+         }
+         it++;
+         grid.sync();
+         v3[1] = spmv(u, w);
+         grid_sum<3>(grid, v3, buf0, sh);
+         beta = v3[0] / gamma;
+         alpha = v3[0] / (v3[1] - beta * v3[0] / alpha);
+         gamma = v3[0];
+         rr = v3[2];
+      }
+      if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
+      return;
    }
    double v3[3] = {0, 0, 0};
    for (int i = tid; i < n; i += nthreads) {
@@ -2254,7 +2308,7 @@ int run_pcg_cg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
 
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (parted(c) && !c->p2p) return run_pcg_dist(c, b, x, x0zero);
-   if (c->cg_variant == 2) return run_pcg_cg(c, b, x, x0zero);
+   if (c->cg_variant == 2 && !c->pcgSmemBytes) return run_pcg_cg(c, b, x, x0zero);
    if (parted(c)) return run_pcg_p2p(c, b, x, x0zero);
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
@@ -2263,10 +2317,12 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
       PcgSmemArgs pa;
       pa.a = a;
       pa.a.part = c->pcgSmemPart; pa.a.dynCounter = nullptr; pa.a.dynStart = c->Z.nslices;
+      pa.s = c->cg_s; pa.pp = c->cg_pp;
       void* sargs[] = {&pa};
       ProfScope ps(c, "pcg", x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false));
       c->lastPcgRec = ps.idx;
-      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_smem, dim3(c->numSMs), dim3(1024), sargs, c->pcgSmemBytes, c->stream));
+      CFD_CK(cudaLaunchCooperativeKernel(c->pcgSmemSingle ? (void*)k_pcg_smem<true> : (void*)k_pcg_smem<false>, dim3(c->numSMs), dim3(1024), sargs,
+                                         c->pcgSmemBytes, c->stream));
       c->launches++;
       return CFD_OK;
    }
@@ -2819,7 +2875,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          // Shared-memory-resident matrix (k_pcg_smem): one CTA per SM takes a contiguous slice range whose values fit into its
          // shared memory (its 32 warps deal the slices among themselves).  Greedy fill in slice order with an even byte target; not
          // eligible if the ranges do not cover the matrix (too large) -- then the streaming kernel above runs.
-         if (!parted && c->cg_variant != 2 && getenv("CFD_NO_PCG_SMEM") == nullptr) {
+         if (!parted && getenv("CFD_NO_PCG_SMEM") == nullptr) {
             int maxOptin = 0;
             CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
             const long long cap = (long long)maxOptin - 1024 - 3 * 32 * 8;   // static shared memory of the kernel + slack
@@ -2840,12 +2896,18 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                ps[c->numSMs] = s;
                ok = s == nsZ;
                if (ok) {
-                  CFD_CK(cudaFuncSetAttribute(k_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
+                  // recurrences inside the resident kernel: cfd_options.cg_variant 1 = classical, 2 = single reduction, 0 = the library's
+                  // choice = single reduction (two synchronisations per iteration; here nothing else costs anything)
+                  c->pcgSmemSingle = o.cg_variant != 1;
+                  const void* kk = c->pcgSmemSingle ? (const void*)k_pcg_smem<true> : (const void*)k_pcg_smem<false>;
+                  CFD_CK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
                   int occS = 0;
-                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_pcg_smem, 1024, (size_t)maxBytes));
+                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, kk, 1024, (size_t)maxBytes));
                   if (occS >= 1) {
                      TRY(dupload(c, &c->pcgSmemPart, ps.data(), ps.size()));
                      c->pcgSmemBytes = (size_t)maxBytes;
+                     if (c->pcgSmemSingle && !c->cg_s) { TRY(dalloc(c, &c->cg_s, (size_t)NNp)); TRY(dalloc(c, &c->cg_pp, (size_t)NNp)); }
+                     c->cg_variant = c->pcgSmemSingle ? 2 : 1;   // (byte model of the iteration)
                   }
                }
             }
@@ -2853,7 +2915,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       }
       if (verb)
          fprintf(stderr, "[cfdb200 init] pressure CG: %s, Z %d rows, %d slices (T = %d), %.1f MB of values%s\n",
-                 c->pcgSmemBytes ? "k_pcg_smem (matrix resident in shared memory)" : (c->cg_variant == 2 ? "k_pcg_cg (single reduction)" : "k_pcg_t (streaming)"),
+                 c->pcgSmemBytes ? (c->pcgSmemSingle ? "k_pcg_smem<single reduction> (matrix resident in shared memory)" : "k_pcg_smem<classical> (matrix resident in shared memory)") : (c->cg_variant == 2 ? "k_pcg_cg (single reduction)" : "k_pcg_t (streaming)"),
                  c->Z.nrows, c->Z.nslices, c->Z.T, 8e-6 * (double)c->Z.padded, c->pcgSmemBytes ? "" : "");
       if (P->scheme == CFD_IMPLICIT) {
          // large matrices: static share (contiguous chunk per CTA, its gathered window stays in L1) + dynamic tail as for Z;

@@ -136,6 +136,7 @@ struct cfd_ctx {
    int* pcgcgPart = nullptr;                      // (= pcgPart: the context runs one of the two PCG kernels)
    int* pcgSmemPart = nullptr;                    // [numSMs+1] slice ranges of the shared-memory-resident PCG (small systems)
    size_t pcgSmemBytes = 0;                       // its dynamic shared memory per CTA; 0 = not eligible
+   bool pcgSmemSingle = false;                    // resident kernel runs the single-reduction recurrences
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
    int timeN = 0;
