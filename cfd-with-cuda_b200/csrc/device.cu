@@ -1174,6 +1174,13 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
       const double thresh = a.tol * sqrt(bb);
       double alpha = gamma / v4[1], beta = 0.0;
       int it = 0;
+#ifdef CFD_PCG_PHASE_TIMERS
+      unsigned long long tph[4] = {0, 0, 0, 0}, t0 = 0, t1;
+#define PCG_TICK(k) do { if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+      if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define PCG_TICK(k)
+#endif
       while (true) {
          if (sqrt(rr) <= thresh || it >= a.maxit) break;
          const bool first = it == 0;
@@ -1191,14 +1198,23 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
             v3[0] += ri * un; v3[2] += ri * ri;
          }
          it++;
+         PCG_TICK(0);
          grid.sync();
+         PCG_TICK(1);
          v3[1] = spmv(u, w);
+         PCG_TICK(2);
          grid_sum<3>(grid, v3, buf0, sh);
+         PCG_TICK(3);
          beta = v3[0] / gamma;
          alpha = v3[0] / (v3[1] - beta * v3[0] / alpha);
          gamma = v3[0];
          rr = v3[2];
       }
+#undef PCG_TICK
+#ifdef CFD_PCG_PHASE_TIMERS
+      if (tid == 0)
+         for (int k = 0; k < 4; k++) a.info[8 + k] = (double)tph[k];
+#endif
       if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
       return;
    }
@@ -2350,7 +2366,7 @@ int fetch_kinfo(cfd_ctx* c) {
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
 #ifdef CFD_PCG_PHASE_TIMERS
-   if (c->cg_variant == 1 && !parted(c) && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+   if (c->cg_variant == 1 && !parted(c) && !c->pcgSmemBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "pcg (classical) phases, us / iteration, block 0 (%d iterations): spmv %.2f | reduction 1 %.2f | update %.2f | reduction 2 %.2f | p update + sync %.2f\n",
               c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3, hk[12] / c->last_cg * 1e-3);
    if (c->cg_variant == 1 && parted(c) && c->p2p && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
@@ -2358,7 +2374,10 @@ int fetch_kinfo(cfd_ctx* c) {
          fprintf(stderr, "[rank %d] pcg (classical, peer memory) phases, us / iteration, %s block (%d iterations): spmv %.2f | all-reduce 1 %.2f | update %.2f | all-reduce 2 %.2f | "
                          "p update + push + flags %.2f\n", c->P.rank, b ? "last" : "first", c->last_cg, hk[8 + 5 * b] / c->last_cg * 1e-3, hk[9 + 5 * b] / c->last_cg * 1e-3,
                  hk[10 + 5 * b] / c->last_cg * 1e-3, hk[11 + 5 * b] / c->last_cg * 1e-3, hk[12 + 5 * b] / c->last_cg * 1e-3);
-   if (c->cg_variant == 2 && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+   if (c->pcgSmemBytes && c->pcgSmemSingle && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      fprintf(stderr, "pcg (resident, single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync %.2f | sweep %.2f | reduction %.2f\n",
+              c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
+   else if (c->cg_variant == 2 && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "[rank %d] pcg (single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync + halo wait %.2f | sweep %.2f | reduction %.2f\n",
               c->P.rank, c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
 #endif
