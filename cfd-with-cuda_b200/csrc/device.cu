@@ -1259,6 +1259,149 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_smem(PcgSmemArgs pa) {
    if (tid == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_pcg_res: the resident PCG of small pressure systems, second form.  Phase clocks of k_pcg_smem on the shipped 30^3 input
+// (profiles/r02_pcg_resident_phases.txt): 5.9 us of the 17 us iteration went into the sweep and 8.3 us into the reduction that waits
+// for the slowest sweep -- with the matrix in shared memory the sweep is bound by its p GATHERS: L1 is carved down to ~30 KB and is
+// invalidated by every grid-wide fence, so 3.3 M eight-byte gathers per iteration travel as 32-byte sectors from L2.  Here each CTA
+// owns a block of ROWS outright:
+//   * matrix values of its rows in shared memory, in a private layout (groups of 32/T rows, T lanes per row, entries in pairs),
+//   * the columns its rows touch form a short list (a few planes of the pressure lattice); per sweep the CTA copies exactly those
+//     vector entries into shared memory with coalesced loads -- the gathers become LDS; column ids are 16-bit positions in that list,
+//   * x, r, p, s, u, w, 1/diag of a row live in the REGISTERS of one thread for the whole solve: the vector pass costs no memory
+//     traffic but the 8-byte store of u.
+// Single-reduction (Chronopoulos-Gear) recurrences: one grid.sync (u visible) + one grid-wide reduction per iteration.  Static
+// assignment, fixed summation orders: bitwise reproducible from run to run; iterates agree with k_pcg_t to rounding.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct ResCta {
+   long long valOff;   // first entry of this CTA in vals / idx
+   long long grpOff;   // first of its ngroups + 1 group offsets in grp
+   long long colOff;   // first of its ncols staged columns in cols
+   int row0, nrows, ngroups, ncols;
+};
+struct PcgResArgs {
+   const ResCta* cta;
+   const double* vals;           // per CTA: groups of R = 32/T rows; entry (slot j, row rl, lane-in-row t) at grp[g] + (j/2)*64 + 2*(rl*T + t) + (j&1)
+   const unsigned short* idx;    // same layout: position of the entry's column in the CTA's staged list
+   const int* cols;              // per CTA: the global columns it stages, ascending
+   const int* grp;               // per CTA: ngroups + 1 entry offsets (multiples of 64)
+   int T;
+   int n;
+   const double* b;
+   double* x;
+   double* u;                    // the one vector other CTAs read: u = M^-1 r
+   const double* dinv;
+   double* scratch;
+   double* info;
+   double tol;
+   int maxit, x0zero;
+};
+__global__ void __launch_bounds__(1024, 1) k_pcg_res(PcgResArgs a) {
+   cg::grid_group grid = cg::this_grid();
+   extern __shared__ double zs[];   // values | staged vector entries | this CTA's rows of w = Z u
+   __shared__ double sh[4 * 32];
+   const ResCta c = a.cta[blockIdx.x];
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int* __restrict__ grp = a.grp + c.grpOff;
+   const int nvals = grp[c.ngroups];
+   double* win = zs + nvals;
+   double* wrow = win + ((c.ncols + 1) & ~1);
+   {
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(a.vals + c.valOff);
+      double2* dst = reinterpret_cast<double2*>(zs);
+      for (int k = threadIdx.x; k < (nvals >> 1); k += blockDim.x) dst[k] = src[k];
+   }
+   const unsigned short* __restrict__ idx = a.idx + c.valOff;
+   const int* __restrict__ cols = a.cols + c.colOff;
+   const int T = a.T, R = 32 / T;
+   double* buf0 = a.scratch;
+   // wrow = (Z src) on this CTA's rows
+   auto sweep = [&](const double* src) {
+      for (int k = threadIdx.x; k < c.ncols; k += blockDim.x) win[k] = __ldcg(src + __ldg(cols + k));
+      __syncthreads();
+      for (int g = warp; g < c.ngroups; g += 32) {
+         const int off = grp[g];
+         const int np = (grp[g + 1] - off) >> 6;
+         const double2* vp = reinterpret_cast<const double2*>(zs + off) + lane;
+         const unsigned* __restrict__ ip = reinterpret_cast<const unsigned*>(idx + off) + lane;
+         double acc = 0.0;
+#pragma unroll 8
+         for (int jp = 0; jp < np; jp++) {
+            const unsigned i2 = __ldg(ip + jp * 32);
+            const double2 v2 = vp[jp * 32];
+            acc += v2.x * win[i2 & 0xffffu] + v2.y * win[i2 >> 16];
+         }
+         for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+         const int r = g * R + lane / T;
+         if ((lane % T) == 0 && r < c.nrows) wrow[r] = acc;
+      }
+      __syncthreads();
+   };
+   const bool own = (int)threadIdx.x < c.nrows;
+   const int row = c.row0 + (int)threadIdx.x;
+   double xi = 0.0, ri = 0.0, pi = 0.0, si = 0.0, ui = 0.0, wi = 0.0, di = 0.0, bi = 0.0;
+   if (own) { bi = a.b[row]; di = a.dinv[row]; }
+   if (!a.x0zero) {   // warm start: r = b - Z x
+      if (own) xi = a.x[row];
+      sweep(a.x);
+      if (own) ri = bi - wrow[threadIdx.x];
+   } else {
+      ri = bi;
+   }
+   ui = di * ri;
+   if (own) a.u[row] = ui;
+   double v4[4] = {ri * ui, 0.0, ri * ri, bi * bi};
+   grid.sync();
+   sweep(a.u);
+   if (own) wi = wrow[threadIdx.x];
+   v4[1] = ui * wi;
+   grid_sum<4>(grid, v4, buf0, sh);
+   double gamma = v4[0], rr = v4[2];
+   const double bb = v4[3];
+   const double thresh = a.tol * sqrt(bb);
+   double alpha = gamma / v4[1], beta = 0.0;
+   int it = 0;
+#ifdef CFD_PCG_PHASE_TIMERS
+   unsigned long long tph[4] = {0, 0, 0, 0}, t0 = 0, t1;
+#define PCG_TICK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); tph[k] += t1 - t0; t0 = t1; } } while (0)
+   if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#else
+#define PCG_TICK(k)
+#endif
+   while (true) {
+      if (sqrt(rr) <= thresh || it >= a.maxit) break;
+      pi = ui + beta * pi;
+      si = wi + beta * si;
+      xi += alpha * pi;
+      ri -= alpha * si;
+      ui = di * ri;
+      if (own) a.u[row] = ui;
+      double v3[3] = {ri * ui, 0.0, ri * ri};
+      it++;
+      PCG_TICK(0);
+      grid.sync();
+      PCG_TICK(1);
+      sweep(a.u);
+      if (own) wi = wrow[threadIdx.x];
+      v3[1] = ui * wi;
+      PCG_TICK(2);
+      grid_sum<3>(grid, v3, buf0, sh);
+      PCG_TICK(3);
+      beta = v3[0] / gamma;
+      alpha = v3[0] / (v3[1] - beta * v3[0] / alpha);
+      gamma = v3[0];
+      rr = v3[2];
+   }
+#undef PCG_TICK
+   if (own) a.x[row] = xi;
+   if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
+#ifdef CFD_PCG_PHASE_TIMERS
+      for (int k = 0; k < 4; k++) a.info[8 + k] = (double)tph[k];
+#endif
+   }
+}
+
 struct PcgP2PArgs {
    PcgArgs a;   // a.p lives in this rank's exchange window
    XComm xc;
@@ -2324,11 +2467,23 @@ int run_pcg_cg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
 
 int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (parted(c) && !c->p2p) return run_pcg_dist(c, b, x, x0zero);
-   if (c->cg_variant == 2 && !c->pcgSmemBytes) return run_pcg_cg(c, b, x, x0zero);
+   if (c->cg_variant == 2 && !c->pcgSmemBytes && !c->resBytes) return run_pcg_cg(c, b, x, x0zero);
    if (parted(c)) return run_pcg_p2p(c, b, x, x0zero);
    PcgArgs a;
    a.Z = c->Z; a.part = c->pcgPart; a.dynStart = c->pcgDynStart; a.dynCounter = c->pcgDynCounter; a.n = c->P.NNp; a.b = b; a.x = x; a.r = c->cg_r; a.p = c->cg_p; a.q = c->cg_q; a.dinv = c->Zdinv;
    a.scratch = c->partials; a.info = c->kinfo; a.tol = c->opt.cg_tol; a.maxit = c->opt.cg_maxit; a.x0zero = x0zero ? 1 : 0;
+   if (c->resBytes > 0) {   // small system: row blocks resident per CTA (values in shared memory, vectors in registers)
+      PcgResArgs ra;
+      ra.cta = (const ResCta*)c->resCta; ra.vals = c->resVals; ra.idx = c->resIdx; ra.cols = c->resCols; ra.grp = c->resGrp; ra.T = c->resT;
+      ra.n = c->P.NNp; ra.b = b; ra.x = x; ra.u = c->cg_p; ra.dinv = c->Zdinv; ra.scratch = c->partials; ra.info = c->kinfo;
+      ra.tol = c->opt.cg_tol; ra.maxit = c->opt.cg_maxit; ra.x0zero = x0zero ? 1 : 0;
+      void* rargs[] = {&ra};
+      ProfScope ps(c, "pcg", spmv_bytes(c->Z, 1, 1, false) + (x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false)));
+      c->lastPcgRec = ps.idx;
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_res, dim3(c->numSMs), dim3(1024), rargs, c->resBytes, c->stream));
+      c->launches++;
+      return CFD_OK;
+   }
    if (c->pcgSmemBytes > 0) {   // small system: matrix resident in shared memory, one CTA per SM
       PcgSmemArgs pa;
       pa.a = a;
@@ -2366,7 +2521,7 @@ int fetch_kinfo(cfd_ctx* c) {
    }
    c->last_bicg_passes = (int)hk[kBicgInfoPasses];
 #ifdef CFD_PCG_PHASE_TIMERS
-   if (c->cg_variant == 1 && !parted(c) && !c->pcgSmemBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+   if (c->cg_variant == 1 && !parted(c) && !c->pcgSmemBytes && !c->resBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "pcg (classical) phases, us / iteration, block 0 (%d iterations): spmv %.2f | reduction 1 %.2f | update %.2f | reduction 2 %.2f | p update + sync %.2f\n",
               c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3, hk[12] / c->last_cg * 1e-3);
    if (c->cg_variant == 1 && parted(c) && c->p2p && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
@@ -2374,7 +2529,10 @@ int fetch_kinfo(cfd_ctx* c) {
          fprintf(stderr, "[rank %d] pcg (classical, peer memory) phases, us / iteration, %s block (%d iterations): spmv %.2f | all-reduce 1 %.2f | update %.2f | all-reduce 2 %.2f | "
                          "p update + push + flags %.2f\n", c->P.rank, b ? "last" : "first", c->last_cg, hk[8 + 5 * b] / c->last_cg * 1e-3, hk[9 + 5 * b] / c->last_cg * 1e-3,
                  hk[10 + 5 * b] / c->last_cg * 1e-3, hk[11 + 5 * b] / c->last_cg * 1e-3, hk[12 + 5 * b] / c->last_cg * 1e-3);
-   if (c->pcgSmemBytes && c->pcgSmemSingle && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+   if (c->resBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      fprintf(stderr, "pcg (k_pcg_res) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync %.2f | sweep %.2f | reduction %.2f\n",
+              c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
+   else if (c->pcgSmemBytes && c->pcgSmemSingle && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "pcg (resident, single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync %.2f | sweep %.2f | reduction %.2f\n",
               c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
    else if (c->cg_variant == 2 && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
@@ -2894,7 +3052,104 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          // Shared-memory-resident matrix (k_pcg_smem): one CTA per SM takes a contiguous slice range whose values fit into its
          // shared memory (its 32 warps deal the slices among themselves).  Greedy fill in slice order with an even byte target; not
          // eligible if the ranges do not cover the matrix (too large) -- then the streaming kernel above runs.
-         if (!parted && getenv("CFD_NO_PCG_SMEM") == nullptr) {
+         // k_pcg_res: row blocks resident per CTA (see the kernel).  Built from the CSR arrays of Z; eligible when every CTA's block
+         // (values + staged vector entries + its rows of w) fits into its shared memory.  cfd_options.cg_variant = 1 (classical
+         // recurrences asked for explicitly) keeps k_pcg_smem<classical> / k_pcg_t.
+         if (!parted && o.cg_variant != 1 && getenv("CFD_NO_PCG_SMEM") == nullptr && getenv("CFD_NO_PCG_RES") == nullptr && NPo > 0) {
+            int maxOptin = 0;
+            CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+            const long long cap = (long long)maxOptin - 4 * 32 * 8 - 256;   // static shared memory of the kernel + slack
+            const int* rs = P->sparseZrowStarts; const int* cl = P->sparseZcol; const double* zv = P->sparseZvalue;
+            const int nC = c->numSMs, n = NPo;
+            const long long nnzZ = rs[n];
+            if (nnzZ * 8 <= cap * nC) {
+               // lanes per row: fewest sequential entry pairs per warp (groups dealt round-robin to the 32 warps of a CTA)
+               const double avgLen = (double)nnzZ / n, rowsPer = std::max(1.0, (double)n / nC);
+               int bestT = 8; double bestCost = 1e300;
+               for (int T = 2; T <= 32; T *= 2) {
+                  const double groups = std::ceil(rowsPer / (32 / T)), rounds = std::ceil(groups / 32.0);
+                  const double cost = rounds * (std::ceil(std::ceil(avgLen / T) / 2.0) + 0.25 * std::log2((double)T));
+                  if (cost < bestCost) { bestCost = cost; bestT = T; }
+               }
+               if (const char* e = getenv("CFD_PCG_RES_T")) { const int t = atoi(e); if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) bestT = t; }
+               const int T = bestT, R = 32 / T;
+               std::vector<ResCta> cta(nC);
+               std::vector<int> grp, cols;
+               std::vector<std::vector<int> > ctaCols(nC);
+               long long totalEntries = 0, maxBytes = 0;
+               bool ok = true;
+               int r = 0;
+               for (int b = 0; b < nC; b++) {
+                  ResCta& k = cta[b];
+                  k.row0 = r;
+                  const long long target = (long long)((double)nnzZ * (b + 1) / nC);
+                  while (r < n && (rs[r + 1] <= target || b == nC - 1)) r++;
+                  k.nrows = r - k.row0;
+                  k.ngroups = (k.nrows + R - 1) / R;
+                  k.valOff = totalEntries; k.grpOff = (long long)grp.size(); k.colOff = (long long)cols.size();
+                  std::vector<int>& u = ctaCols[b];
+                  for (int q = rs[k.row0]; q < rs[r]; q++) u.push_back(cl[q]);
+                  std::sort(u.begin(), u.end());
+                  u.erase(std::unique(u.begin(), u.end()), u.end());
+                  k.ncols = (int)u.size();
+                  cols.insert(cols.end(), u.begin(), u.end());
+                  int off = 0;
+                  for (int g = 0; g < k.ngroups; g++) {
+                     grp.push_back(off);
+                     int w = 0;
+                     for (int rl = 0; rl < R && k.row0 + g * R + rl < r; rl++) {
+                        const int rr2 = k.row0 + g * R + rl;
+                        w = std::max(w, (rs[rr2 + 1] - rs[rr2] + T - 1) / T);
+                     }
+                     off += ((w + 1) & ~1) * 32;
+                  }
+                  grp.push_back(off);
+                  totalEntries += off;
+                  const long long bytes = 8LL * off + 8LL * ((k.ncols + 1) & ~1) + 8LL * k.nrows;
+                  maxBytes = std::max(maxBytes, bytes);
+                  if (k.nrows > 1024 || k.ncols > 65535) ok = false;
+               }
+               if (ok && maxBytes <= cap && r == n) {
+                  std::vector<double> vals((size_t)std::max<long long>(totalEntries, 2), 0.0);
+                  std::vector<unsigned short> idx((size_t)std::max<long long>(totalEntries, 2), 0);
+#pragma omp parallel for schedule(dynamic, 1)
+                  for (int b = 0; b < nC; b++) {
+                     const ResCta& k = cta[b];
+                     const std::vector<int>& u = ctaCols[b];
+                     for (int lr = 0; lr < k.nrows; lr++) {
+                        const int g = lr / R, rl = lr % R, row = k.row0 + lr;
+                        const long long base = k.valOff + grp[(size_t)k.grpOff + g];
+                        for (int q = rs[row], e = 0; q < rs[row + 1]; q++, e++) {
+                           const int t = e % T, j = e / T;
+                           const long long pos = base + (long long)(j >> 1) * 64 + 2 * (rl * T + t) + (j & 1);
+                           vals[(size_t)pos] = zv[q];
+                           idx[(size_t)pos] = (unsigned short)(std::lower_bound(u.begin(), u.end(), cl[q]) - u.begin());
+                        }
+                     }
+                  }
+                  CFD_CK(cudaFuncSetAttribute((const void*)k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
+                  int occR = 0;
+                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, (const void*)k_pcg_res, 1024, (size_t)maxBytes));
+                  if (occR >= 1) {
+                     ResCta* dcta = nullptr;
+                     TRY(dupload(c, &dcta, cta.data(), cta.size()));
+                     c->resCta = dcta;
+                     TRY(dupload(c, &c->resVals, vals.data(), vals.size()));
+                     TRY(dupload(c, &c->resIdx, idx.data(), idx.size()));
+                     if (cols.empty()) cols.push_back(0);
+                     TRY(dupload(c, &c->resCols, cols.data(), cols.size()));
+                     TRY(dupload(c, &c->resGrp, grp.data(), grp.size()));
+                     c->resT = T;
+                     c->resBytes = (size_t)maxBytes;
+                     c->cg_variant = 2;   // (byte model of the iteration)
+                     if (verb)
+                        fprintf(stderr, "[cfdb200 init] k_pcg_res: %d rows in %d row blocks, T = %d lanes per row, %.1f MB of values, at most %.1f KB of shared memory per CTA\n",
+                                n, nC, T, 8e-6 * (double)totalEntries, maxBytes / 1024.0);
+                  }
+               }
+            }
+         }
+         if (!parted && !c->resBytes && getenv("CFD_NO_PCG_SMEM") == nullptr) {
             int maxOptin = 0;
             CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
             const long long cap = (long long)maxOptin - 1024 - 3 * 32 * 8;   // static shared memory of the kernel + slack
@@ -2934,7 +3189,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       }
       if (verb)
          fprintf(stderr, "[cfdb200 init] pressure CG: %s, Z %d rows, %d slices (T = %d), %.1f MB of values%s\n",
-                 c->pcgSmemBytes ? (c->pcgSmemSingle ? "k_pcg_smem<single reduction> (matrix resident in shared memory)" : "k_pcg_smem<classical> (matrix resident in shared memory)") : (c->cg_variant == 2 ? "k_pcg_cg (single reduction)" : "k_pcg_t (streaming)"),
+                 c->resBytes ? "k_pcg_res (row blocks resident per CTA: values in shared memory, staged vector window, vectors in registers)" : c->pcgSmemBytes ? (c->pcgSmemSingle ? "k_pcg_smem<single reduction> (matrix resident in shared memory)" : "k_pcg_smem<classical> (matrix resident in shared memory)") : (c->cg_variant == 2 ? "k_pcg_cg (single reduction)" : "k_pcg_t (streaming)"),
                  c->Z.nrows, c->Z.nslices, c->Z.T, 8e-6 * (double)c->Z.padded, c->pcgSmemBytes ? "" : "");
       if (P->scheme == CFD_IMPLICIT) {
          // large matrices: static share (contiguous chunk per CTA, its gathered window stays in L1) + dynamic tail as for Z;

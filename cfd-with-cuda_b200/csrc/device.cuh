@@ -137,6 +137,13 @@ struct cfd_ctx {
    int* pcgSmemPart = nullptr;                    // [numSMs+1] slice ranges of the shared-memory-resident PCG (small systems)
    size_t pcgSmemBytes = 0;                       // its dynamic shared memory per CTA; 0 = not eligible
    bool pcgSmemSingle = false;                    // resident kernel runs the single-reduction recurrences
+   // k_pcg_res (row blocks resident per CTA, staged vector window): device arrays of its private layout; resBytes = 0: not eligible
+   void* resCta = nullptr;
+   double* resVals = nullptr;
+   unsigned short* resIdx = nullptr;
+   int *resCols = nullptr, *resGrp = nullptr;
+   int resT = 0;
+   size_t resBytes = 0;
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
    int timeN = 0;
