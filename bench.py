@@ -232,6 +232,8 @@ def main():
     ap.add_argument("--deterministic", type=int, default=0, help="cfd_options.deterministic")
     ap.add_argument("--path", default="csr", choices=["csr", "ebe"],
                     help="operator path of the explicit scheme: csr = assembled matrices (Sell SpMV), ebe = matrix-free element kernels (cfd_options.operator_path)")
+    ap.add_argument("--step0", default="host", choices=["host", "device"],
+                    help="set-up: host = step0 (element integrals, Z) on the host cores; device = on the GPU (cfd_options.step0_device)")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
     sz = sizes(w)
@@ -281,7 +283,8 @@ def main():
         fracstep.build()
     if dist is not None:
         dist.barrier()
-    opts = fracstep.options(device=local_rank, cg_variant=a.cg_variant, deterministic=a.deterministic, operator_path=1 if a.path == "ebe" else 0)
+    opts = fracstep.options(device=local_rank, cg_variant=a.cg_variant, deterministic=a.deterministic, operator_path=1 if a.path == "ebe" else 0,
+                            step0_device=1 if a.step0 == "device" and world == 1 else 0)
     t0 = time.time()
     tmp = None
     if w.get("inp"):
@@ -388,7 +391,7 @@ def main():
                        share=round(v["ms"] / total_ms, 4) if total_ms else 0.0) for k, v in prof.items() if v["launches"]}
     config.update(parallelism="1 GPU" if world == 1 else "%d element blocks (z-slabs), one per GPU; peer-memory Krylov kernels + NCCL halo swap / allreduce" % world,
                   l2="matrix streams %.2f GB per step >> 126 MB L2 (no flush needed)" % (sum(v["layout_bytes"] for v in prof.values()) / a.steps / 1e9),
-                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps), cg_variant=a.cg_variant, operator_path=a.path,
+                  setup_s=round(setup_s, 1), cg_iterations_per_step=cg_its / float(a.steps), cg_variant=a.cg_variant, operator_path=a.path, step0=a.step0 if world == 1 else "host",
                   bicgstab_iterations_last_step=reps[-1]["bicg_iterations"])
     krylov_ok = all(r["cg_converged"] for r in reps) and all(all(r["bicg_converged"]) for r in reps)
     line = dict(metric="time steps/s", value=n_rep * a.steps / (ms_max * 1e-3), unit="steps/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,

@@ -826,6 +826,158 @@ __global__ void __launch_bounds__(128) k_ebe_laplace_apply(int NE, int ldE, cons
 
 // The pointwise halves of step 1 and step 3 after the element pass has accumulated the operator part (matrix-free path):
 //   step 1:  R1[bc] = 0 ; UnpHalf = Un + dt * R1 * MdInv
+// =================================================================================================
+// step0 on the device (cfd_options.step0_device = 1): the element integrals of step0
+// (BCH.cpp:3127-3315, GQ.cpp:3425-3572, 3677-3772) evaluated by the GPU and summed straight into CSR-ordered value arrays, the
+// lumped mass, the explicit pressure matrix Z = sum_c G_c^T Md^-1 G_c (calculateZ, BCH.cpp:3322-3479 / BCH.cu:281-411) as a row-wise
+// sparse product, the pin -- then one permutation pass per matrix into the Sell layout.  Same formulas and the same order of the
+// Gauss-point sums as the host path (assemble_step0, host_solver.cpp); the element contributions of an entry arrive through FP64
+// atomics, i.e. in any order: equal to the host arrays to rounding.  Set-up only, not on the time-loop path.
+// =================================================================================================
+// position of column c in CSR row `row` (ascending columns); -1 if absent
+__device__ __forceinline__ int csr_find(const int* __restrict__ rs, const int* __restrict__ col, int row, int c) {
+   int lo = __ldg(rs + row), hi = __ldg(rs + row + 1) - 1;
+   if (hi < lo) return -1;
+   while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(col + mid) < c) lo = mid + 1; else hi = mid;
+   }
+   return __ldg(col + lo) == c ? lo : -1;
+}
+
+// one thread per (element, local row i): rows i of Me, Ke, Ge_1..3 and (implicit, i < 8) of the FE-Laplacian element matrix
+template <int NV>
+__global__ void __launch_bounds__(128) k_step0_elements(int NE, int ldE, const int* __restrict__ LtoGT, const double* __restrict__ coord,
+                                                        const int* __restrict__ Mrs, const int* __restrict__ Mcol,
+                                                        const int* __restrict__ Grs, const int* __restrict__ Gcol,
+                                                        const int* __restrict__ Zrs, const int* __restrict__ Zcol,
+                                                        double mscale, double visc, double invDens,
+                                                        double* __restrict__ M, double* __restrict__ K, double* __restrict__ G1,
+                                                        double* __restrict__ G2, double* __restrict__ G3, double* __restrict__ Z) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+   if (e >= NE) return;
+   double xc[8][3];
+#pragma unroll
+   for (int m = 0; m < 8; m++) {
+      const long long nd = __ldg(LtoGT + (long long)m * ldE + e);
+#pragma unroll
+      for (int d = 0; d < 3; d++) xc[m][d] = __ldg(coord + 3 * nd + d);
+   }
+   // inverse Jacobian and quadrature factor at the 8 Gauss points (calcJacob, BCH.cpp:2495-2711: unit weights, fac = det J)
+   double I[8][9], fac[8], gi[8][3];
+#pragma unroll
+   for (int k = 0; k < 8; k++) {
+      double C[3][3];
+      const double det = ebe_cofactor(xc, k, C);
+      const double id = 1.0 / det;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+         for (int b = 0; b < 3; b++) I[k][3 * a + b] = C[a][b] * id;
+      fac[k] = det;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+         gi[k][a] = I[k][3 * a] * Tab<NV>::dSv(0, i, k) + I[k][3 * a + 1] * Tab<NV>::dSv(1, i, k) + I[k][3 * a + 2] * Tab<NV>::dSv(2, i, k);
+   }
+   const int row = __ldg(LtoGT + (long long)i * ldE + e);
+   for (int j = 0; j < NV; j++) {
+      double me = 0.0, ke = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+         double gj[3];
+#pragma unroll
+         for (int a = 0; a < 3; a++)
+            gj[a] = I[k][3 * a] * Tab<NV>::dSv(0, j, k) + I[k][3 * a + 1] * Tab<NV>::dSv(1, j, k) + I[k][3 * a + 2] * Tab<NV>::dSv(2, j, k);
+         me += Tab<NV>::Sv(k, i) * Tab<NV>::Sv(k, j) * fac[k];
+         ke += (gi[k][0] * gj[0] + gi[k][1] * gj[1] + gi[k][2] * gj[2]) * fac[k];
+      }
+      const int pos = csr_find(Mrs, Mcol, row, __ldg(LtoGT + (long long)j * ldE + e));
+      if (pos >= 0) { atomicAdd(M + pos, mscale * me); atomicAdd(K + pos, visc * ke); }
+   }
+   for (int j = 0; j < 8; j++) {
+      double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+         const double w = cSv8[k][j] * fac[k];
+         g1 += w * gi[k][0]; g2 += w * gi[k][1]; g3 += w * gi[k][2];
+      }
+      const int pos = csr_find(Grs, Gcol, row, __ldg(LtoGT + (long long)j * ldE + e));
+      if (pos >= 0) { atomicAdd(G1 + pos, -invDens * g1); atomicAdd(G2 + pos, -invDens * g2); atomicAdd(G3 + pos, -invDens * g3); }
+   }
+   if (Z != nullptr && i < 8) {   // FE Laplacian on the pressure basis (implicit Z, GQ.cpp:3677-3772)
+      double gp[8][3];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+#pragma unroll
+         for (int a = 0; a < 3; a++) gp[k][a] = I[k][3 * a] * cdSp[0][i][k] + I[k][3 * a + 1] * cdSp[1][i][k] + I[k][3 * a + 2] * cdSp[2][i][k];
+      for (int j = 0; j < 8; j++) {
+         double z = 0.0;
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            double gj[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) gj[a] = I[k][3 * a] * cdSp[0][j][k] + I[k][3 * a + 1] * cdSp[1][j][k] + I[k][3 * a + 2] * cdSp[2][j][k];
+            z += (gp[k][0] * gj[0] + gp[k][1] * gj[1] + gp[k][2] * gj[2]) * fac[k];
+         }
+         const int pos = csr_find(Zrs, Zcol, row, __ldg(LtoGT + (long long)j * ldE + e));
+         if (pos >= 0) atomicAdd(Z + pos, -z);
+      }
+   }
+}
+
+// lumped mass = row sums of M in CSR order (BCH.cpp:3254-3292); MdOrigInv = 1/md, MdInv = 1/md with Dirichlet rows set to 1
+__global__ void __launch_bounds__(256) k_step0_lump(int NN, const int* __restrict__ rs, const double* __restrict__ M, const int* __restrict__ bcIndex,
+                                                    double* __restrict__ md, double* __restrict__ MdOrigInv, double* __restrict__ MdInv) {
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= NN) return;
+   double s = 0.0;
+   for (int k = rs[r]; k < rs[r + 1]; k++) s += M[k];
+   md[r] = s;
+   const double inv = 1.0 / s, invBC = bcIndex[r] >= 0 ? 1.0 : inv;
+#pragma unroll
+   for (int c = 0; c < 3; c++) { MdOrigInv[(size_t)c * NN + r] = inv; MdInv[(size_t)c * NN + r] = invBC; }
+}
+
+// Z = sum_c G_c^T diag(1/md) G_c, one warp per pressure row i through the transposed pattern of G (ts / trow / tpos): for every
+// velocity node r coupled to i (ascending), the lanes take the entries of row r of G and add w . G[r][j] to Z[i][j]
+// -- the accumulation order of the host product (assemble_step0).  Z must be zero on entry.
+__global__ void __launch_bounds__(256) k_step0_spgemm_z(int NNp, const int* __restrict__ ts, const int* __restrict__ trow, const int* __restrict__ tpos,
+                                                        const int* __restrict__ Grs, const int* __restrict__ Gcol, const double* __restrict__ G1,
+                                                        const double* __restrict__ G2, const double* __restrict__ G3, const double* __restrict__ md,
+                                                        const int* __restrict__ Zrs, const int* __restrict__ Zcol, double* Z) {
+   const int i = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+   if (i >= NNp) return;
+   for (int t = ts[i]; t < ts[i + 1]; t++) {
+      const int r = trow[t], q = tpos[t];
+      const double d = md[r];
+      const double w1 = G1[q] / d, w2 = G2[q] / d, w3 = G3[q] / d;
+      for (int k = Grs[r] + lane; k < Grs[r + 1]; k += 32) {
+         const int pos = csr_find(Zrs, Zcol, i, Gcol[k]);
+         if (pos >= 0) Z[pos] += w1 * G1[k] + w2 * G2[k] + w3 * G3[k];
+      }
+      __syncwarp();   // the next r may touch the same Z entries from other lanes
+   }
+}
+
+// dst[perm[k]] = a[k] (+ b[k]): CSR order -> Sell layout;  dst[k] = src[idx[k]]: transposed values;  1/diag of a CSR matrix
+__global__ void __launch_bounds__(256) k_step0_scatter(long long n, const long long* __restrict__ perm, const double* __restrict__ a,
+                                                       const double* __restrict__ b, double* __restrict__ dst) {
+   const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+   if (k < n) dst[perm[k]] = b ? a[k] + b[k] : a[k];
+}
+__global__ void __launch_bounds__(256) k_step0_gather(long long n, const int* __restrict__ idx, const double* __restrict__ src, double* __restrict__ dst) {
+   const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+   if (k < n) dst[k] = src[idx[k]];
+}
+__global__ void __launch_bounds__(256) k_step0_diag(int n, const int* __restrict__ rs, const int* __restrict__ col, double* val, int pin, int noPrecond,
+                                                    double* __restrict__ dinv) {
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= n) return;
+   const int pos = csr_find(rs, col, r, r);
+   if (pos >= 0 && r == pin) val[pos] *= 1000.0;   // pressure pin: diagonal x 1000 (applyBC_Step2, BCH.cpp:4167-4180)
+   dinv[r] = (noPrecond || pos < 0) ? 1.0 : 1.0 / val[pos];
+}
+
 __global__ void __launch_bounds__(256) k_step1_finish(int NN, const int* __restrict__ bcIndex, const double* __restrict__ Un, const double* __restrict__ MdInv,
                                                       double* __restrict__ R1, double* __restrict__ UnpHalf, double dt) {
    const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1296,7 +1448,9 @@ struct PcgResArgs {
    double tol;
    int maxit, x0zero;
 };
-__global__ void __launch_bounds__(1024, 1) k_pcg_res(PcgResArgs a) {
+constexpr int kResThreads = 512;   // 16 warps, 128 registers per thread: room for the cached column ids
+constexpr int kResWarps = kResThreads / 32;
+__global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
    cg::grid_group grid = cg::this_grid();
    extern __shared__ double zs[];   // values | staged vector entries | this CTA's rows of w = Z u
    __shared__ double sh[4 * 32];
@@ -1316,26 +1470,72 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_res(PcgResArgs a) {
    const int T = a.T, R = 32 / T;
    double* buf0 = a.scratch;
    // wrow = (Z src) on this CTA's rows
+#ifdef CFD_PCG_PHASE_TIMERS
+   unsigned long long tsw[3] = {0, 0, 0}, u0 = 0, u1;
+#define SWEEP_TICK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(u1)); tsw[k] += u1 - u0; u0 = u1; } } while (0)
+#define SWEEP_T0() do { if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(u0)); } while (0)
+#else
+#define SWEEP_TICK(k)
+#define SWEEP_T0()
+#endif
+   // Column ids of this warp's FIRST row group stay in registers for the whole solve (they never change, and every grid-wide fence
+   // invalidates L1: re-reading them costs an L2 round trip per dependent load -- measured 4.3 of the 5.2 us of a sweep).  Further
+   // groups of the warp (more than 16 groups per CTA) and pairs beyond kResCache are requested per sweep, a whole chunk at a time.
+   constexpr int kResCache = 32;
+   unsigned ireg[kResCache];
+   int off0 = 0, np0 = 0;
+   if (warp < c.ngroups) { off0 = grp[warp]; np0 = (grp[warp + 1] - off0) >> 6; }
+#pragma unroll
+   for (int q = 0; q < kResCache; q++) ireg[q] = q < np0 ? __ldg(reinterpret_cast<const unsigned*>(idx + off0) + lane + q * 32) : 0u;
+   // the staged columns likewise: up to kResCols per thread in registers (one L2 round trip per sweep instead of two)
+   constexpr int kResCols = 8;
+   int creg[kResCols];
+   const bool colsCached = c.ncols <= kResCols * kResThreads;
+#pragma unroll
+   for (int q = 0; q < kResCols; q++) { const int k = (int)threadIdx.x + q * kResThreads; creg[q] = (colsCached && k < c.ncols) ? __ldg(cols + k) : -1; }
    auto sweep = [&](const double* src) {
-      for (int k = threadIdx.x; k < c.ncols; k += blockDim.x) win[k] = __ldcg(src + __ldg(cols + k));
+      SWEEP_T0();
+      if (colsCached) {
+         double v[kResCols];
+#pragma unroll
+         for (int q = 0; q < kResCols; q++) v[q] = creg[q] >= 0 ? __ldcg(src + creg[q]) : 0.0;
+#pragma unroll
+         for (int q = 0; q < kResCols; q++) if (creg[q] >= 0) win[threadIdx.x + q * kResThreads] = v[q];
+      } else {
+         for (int k = threadIdx.x; k < c.ncols; k += blockDim.x) win[k] = __ldcg(src + __ldg(cols + k));
+      }
       __syncthreads();
-      for (int g = warp; g < c.ngroups; g += 32) {
-         const int off = grp[g];
-         const int np = (grp[g + 1] - off) >> 6;
+      SWEEP_TICK(0);
+      for (int g = warp; g < c.ngroups; g += kResWarps) {
+         const bool first = g == warp;
+         const int off = first ? off0 : grp[g];
+         const int np = first ? np0 : (grp[g + 1] - off) >> 6;
          const double2* vp = reinterpret_cast<const double2*>(zs + off) + lane;
          const unsigned* __restrict__ ip = reinterpret_cast<const unsigned*>(idx + off) + lane;
          double acc = 0.0;
-#pragma unroll 8
-         for (int jp = 0; jp < np; jp++) {
-            const unsigned i2 = __ldg(ip + jp * 32);
-            const double2 v2 = vp[jp * 32];
-            acc += v2.x * win[i2 & 0xffffu] + v2.y * win[i2 >> 16];
+         for (int base = 0; base < np; base += kResCache) {
+            unsigned iq[kResCache];
+            if (first && base == 0) {
+#pragma unroll
+               for (int q = 0; q < kResCache; q++) iq[q] = ireg[q];
+            } else {
+#pragma unroll
+               for (int q = 0; q < kResCache; q++) iq[q] = base + q < np ? __ldg(ip + (base + q) * 32) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < kResCache; q++)
+               if (base + q < np) {
+                  const double2 v2 = vp[(base + q) * 32];
+                  acc += v2.x * win[iq[q] & 0xffffu] + v2.y * win[iq[q] >> 16];
+               }
          }
          for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
          const int r = g * R + lane / T;
          if ((lane % T) == 0 && r < c.nrows) wrow[r] = acc;
       }
+      SWEEP_TICK(1);
       __syncthreads();
+      SWEEP_TICK(2);
    };
    const bool own = (int)threadIdx.x < c.nrows;
    const int row = c.row0 + (int)threadIdx.x;
@@ -1398,6 +1598,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_res(PcgResArgs a) {
       a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb;
 #ifdef CFD_PCG_PHASE_TIMERS
       for (int k = 0; k < 4; k++) a.info[8 + k] = (double)tph[k];
+      for (int k = 0; k < 3; k++) a.info[24 + k] = (double)tsw[k];   // inside the sweep: staging | warp 0's groups | wait for the CTA's other warps
 #endif
    }
 }
@@ -2234,6 +2435,32 @@ int dupload(cfd_ctx* c, T** p, const T* host, size_t count) {
    return CFD_OK;
 }
 
+// set-up scratch on the device, released on every exit path (device step0)
+// Uploads and zero fills are issued on the context's stream (created non-blocking: work on the legacy stream is NOT ordered with it),
+// so they are ordered with the step0 kernels that consume them.
+struct DevScratch {
+   std::vector<void*> v;
+   cudaStream_t st = nullptr;
+   ~DevScratch() { for (void* q : v) cudaFree(q); }
+   int alloc(void** q, size_t bytes) {
+      CFD_CK(cudaMalloc(q, std::max<size_t>(bytes, 16)));
+      v.push_back(*q);
+      return CFD_OK;
+   }
+   template <class T> int up(T** q, const T* host, size_t n) {
+      int rc = alloc((void**)q, sizeof(T) * n);
+      if (rc) return rc;
+      CFD_CK(cudaMemcpyAsync(*q, host, sizeof(T) * n, cudaMemcpyHostToDevice, st));   // (pageable source: returns once it is staged)
+      return CFD_OK;
+   }
+   int zeros(double** q, size_t n) {
+      int rc = alloc((void**)q, sizeof(double) * n);
+      if (rc) return rc;
+      CFD_CK(cudaMemsetAsync(*q, 0, sizeof(double) * std::max<size_t>(n, 2), st));
+      return CFD_OK;
+   }
+};
+
 int regvec(cfd_ctx* c, const char* name, double** p, long long n) {
    int rc = dalloc(c, p, (size_t)n);
    if (rc) return rc;
@@ -2480,7 +2707,7 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
       void* rargs[] = {&ra};
       ProfScope ps(c, "pcg", spmv_bytes(c->Z, 1, 1, false) + (x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false)));
       c->lastPcgRec = ps.idx;
-      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_res, dim3(c->numSMs), dim3(1024), rargs, c->resBytes, c->stream));
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_res, dim3(c->numSMs), dim3(kResThreads), rargs, c->resBytes, c->stream));
       c->launches++;
       return CFD_OK;
    }
@@ -2532,6 +2759,9 @@ int fetch_kinfo(cfd_ctx* c) {
    if (c->resBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "pcg (k_pcg_res) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync %.2f | sweep %.2f | reduction %.2f\n",
               c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
+   if (c->resBytes && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
+      fprintf(stderr, "   inside the sweep (block 0, %d sweeps): staging %.2f | warp 0's row groups %.2f | wait for the other warps %.2f\n",
+              c->last_cg + 1, hk[24] / (c->last_cg + 1) * 1e-3, hk[25] / (c->last_cg + 1) * 1e-3, hk[26] / (c->last_cg + 1) * 1e-3);
    else if (c->pcgSmemBytes && c->pcgSmemSingle && c->last_cg > 0 && getenv("CFD_PCG_PHASES"))
       fprintf(stderr, "pcg (resident, single-reduction) phases, us / iteration, block 0 (%d iterations): vector pass %.2f | grid sync %.2f | sweep %.2f | reduction %.2f\n",
               c->last_cg, hk[8] / c->last_cg * 1e-3, hk[9] / c->last_cg * 1e-3, hk[10] / c->last_cg * 1e-3, hk[11] / c->last_cg * 1e-3);
@@ -2693,16 +2923,23 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       set_error("unsupported element: NENv=%d NENp=%d NGP=%d (supported: 27/8/8 and 8/8/8)", P->NENv, P->NENp, P->NGP);
       return CFD_ERR_ARG;
    }
-   if (!P->coord || !P->LtoGnode || !P->sparseMrowStarts || !P->sparseMcol || !P->sparseKvalue || !P->sparseGrowStarts ||
-       !P->sparseGcol || !P->sparseG1value || !P->sparseG2value || !P->sparseG3value || !P->sparseZrowStarts || !P->sparseZcol ||
-       !P->sparseZvalue || (P->BCnVelNodes > 0 && (!P->BCvelNodes || !P->BCstr))) {
+   // step0_device = 1: the value arrays (K, M, G1..3, Z, MdInv, MdOrigInv) are computed on the device from the mesh and the patterns
+   const bool dev0 = opt && opt->step0_device == 1;
+   if (opt && opt->step0_device != 0 && opt->step0_device != 1) { set_error("step0_device must be 0 (value arrays from the host) or 1 (computed on the device)"); return CFD_ERR_ARG; }
+   if (dev0 && P->world > 1) { set_error("step0_device = 1 is single-GPU (partitioned sub-meshes number their pressure DOFs separately)"); return CFD_ERR_ARG; }
+   if (!P->coord || !P->LtoGnode || !P->sparseMrowStarts || !P->sparseMcol || !P->sparseGrowStarts || !P->sparseGcol || !P->sparseZrowStarts ||
+       !P->sparseZcol || (P->BCnVelNodes > 0 && (!P->BCvelNodes || !P->BCstr))) {
       set_error("cfd_problem: a required array is NULL");
       return CFD_ERR_ARG;
    }
-   if (P->scheme == CFD_EXPLICIT && (!P->MdInv || !P->MdOrigInv)) { set_error("explicit scheme needs MdInv and MdOrigInv"); return CFD_ERR_ARG; }
+   if (!dev0 && (!P->sparseKvalue || !P->sparseG1value || !P->sparseG2value || !P->sparseG3value || !P->sparseZvalue)) {
+      set_error("cfd_problem: a matrix value array is NULL (cfd_options.step0_device = 1 computes them on the device)");
+      return CFD_ERR_ARG;
+   }
+   if (!dev0 && P->scheme == CFD_EXPLICIT && (!P->MdInv || !P->MdOrigInv)) { set_error("explicit scheme needs MdInv and MdOrigInv"); return CFD_ERR_ARG; }
    if (opt && opt->operator_path == 1 && P->world > 1) { set_error("operator_path = 1 (matrix-free operators) is single-GPU: interface rows would need a sum exchange"); return CFD_ERR_ARG; }
    if (opt && opt->operator_path != 0 && opt->operator_path != 1) { set_error("operator_path must be 0 (assembled) or 1 (matrix-free)"); return CFD_ERR_ARG; }
-   if (P->scheme == CFD_IMPLICIT && (!P->sparseMvalue || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
+   if (P->scheme == CFD_IMPLICIT && ((!dev0 && !P->sparseMvalue) || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
    cfd_options o;
    if (opt) o = *opt; else cfd_default_options(&o);
    int ndev = 0;
@@ -2759,21 +2996,25 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    // ---- matrices -> Sell.  The velocity-row matrices (K/M/A and G) share one row partition (same T).
    const int Tv = choose_Tv(NNo, P->sparseMrowStarts[NNo]);
    // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z arrive on ONE pattern (same arrays): its layout is built once and shared
-   SellHost hK;
+   SellHost hK, hG, hGT, hZ;   // (hG / hZ stay empty when they share hK)
+   std::vector<int> gtSrc, gtRs, gtRow;   // device step0: transposed pattern of G (row starts, velocity node and G position of every entry)
    const bool sameG = P->sparseGrowStarts == P->sparseMrowStarts && P->sparseGcol == P->sparseMcol && NNp == NN && NPo == NNo;
    {
       SellHost& h = hK;
       sell_build_host(NNo, NN, P->sparseMrowStarts, P->sparseMcol, Tv, h);
       c->hostOffK = h.sliceOff;
       if (P->scheme == CFD_EXPLICIT) {
-         const double* v[1] = {P->sparseKvalue};
+         const double* v[1] = {dev0 ? nullptr : P->sparseKvalue};
          TRY(sell_upload(h, 1, v, c->K));
       } else {
          const long long nnzOwned = P->sparseMrowStarts[NNo];
-         std::unique_ptr<double[]> mk(new double[std::max<size_t>((size_t)nnzOwned, 1)]);
+         std::unique_ptr<double[]> mk;
+         if (!dev0) {
+            mk.reset(new double[std::max<size_t>((size_t)nnzOwned, 1)]);
 #pragma omp parallel for schedule(static)
-         for (long long k = 0; k < nnzOwned; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
-         const double* v[3] = {mk.get(), P->sparseMvalue, nullptr};
+            for (long long k = 0; k < nnzOwned; k++) mk[k] = P->sparseMvalue[k] + P->sparseKvalue[k];   // calculate_MplusK, GQ.cu:537-547 (constant: done once)
+         }
+         const double* v[3] = {mk.get(), dev0 ? nullptr : P->sparseMvalue, nullptr};
          TRY(sell_upload(h, 3, v, c->K));
          // element -> Sell position map, transposed to [q][e]
          c->ldE = (NE + 31) & ~31;
@@ -2797,10 +3038,10 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    }
    IPHASE("Sell K/M/A + maps");
    {
-      SellHost hOwn;
-      if (!sameG) sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, hOwn);
-      const double* v[3] = {P->sparseG1value, P->sparseG2value, P->sparseG3value};
-      TRY(sell_upload(sameG ? hK : hOwn, 3, v, c->G));
+      if (!sameG) sell_build_host(NNo, NNp, P->sparseGrowStarts, P->sparseGcol, Tv, hG);
+      const double* v[3] = {dev0 ? nullptr : P->sparseG1value, dev0 ? nullptr : P->sparseG2value, dev0 ? nullptr : P->sparseG3value};
+      TRY(sell_upload(sameG ? hK : hG, 3, v, c->G));
+      if (!sameG && !dev0) hG = SellHost();
    }
    IPHASE("Sell G");
    {
@@ -2808,8 +3049,36 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       // OPERATION_TRANSPOSE csrmv scatter, BCH.cu:1006-1009).  Parallel: count, prefix sum, scatter in any order, then every
       // transposed row is put into ascending column order (deterministic result).
       const int nnzG = P->sparseG_nnz;
-      std::vector<int> ts((size_t)NNp + 1, 0), tcol((size_t)nnzG), tsrc((size_t)nnzG);
-      std::unique_ptr<double[]> t1(new double[(size_t)nnzG]), t2(new double[(size_t)nnzG]), t3(new double[(size_t)nnzG]);   // (no serial zero fill)
+      std::vector<int> ts, tcol, tsrc((size_t)nnzG);
+      std::unique_ptr<double[]> t1, t2, t3;
+      if (!dev0) { t1.reset(new double[(size_t)nnzG]); t2.reset(new double[(size_t)nnzG]); t3.reset(new double[(size_t)nnzG]); }   // (no serial zero fill)
+      // Q1/Q1 on a whole mesh: G lives on the (structurally symmetric) K / M pattern, so G^T has the SAME pattern and -- with the
+      // same lanes per row -- the same device layout; only the values move: entry (i, j) of G^T = entry (j, i) of G, found by
+      // bisection in row j.  (Any miss -- an unsymmetric or unsorted pattern from a caller -- falls back to the general transpose.)
+      bool gtShared = false;
+      if (sameG && choose_T(NPo, P->sparseGrowStarts[NPo]) == Tv && getenv("CFD_NO_GT_SHARED") == nullptr) {
+         const int* rs = P->sparseGrowStarts; const int* cl = P->sparseGcol;
+         int miss = 0;
+#pragma omp parallel for schedule(static) reduction(+ : miss)
+         for (int r = 0; r < NN; r++)
+            for (int k = rs[r]; k < rs[r + 1]; k++) {
+               if (k > rs[r] && cl[k] <= cl[k - 1]) miss++;
+               const int j = cl[k];
+               const int* q = std::lower_bound(cl + rs[j], cl + rs[j + 1], r);
+               if (q == cl + rs[j + 1] || *q != r) { miss++; tsrc[k] = 0; } else tsrc[k] = (int)(q - cl);
+            }
+         gtShared = miss == 0;
+      }
+      if (gtShared) {
+         if (!dev0) {
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < nnzG; k++) { t1[k] = P->sparseG1value[tsrc[k]]; t2[k] = P->sparseG2value[tsrc[k]]; t3[k] = P->sparseG3value[tsrc[k]]; }
+         }
+         const double* v[3] = {t1.get(), t2.get(), t3.get()};
+         TRY(sell_upload(hK, 3, v, c->GT));
+         if (dev0) { gtSrc.swap(tsrc); gtRs.assign(P->sparseGrowStarts, P->sparseGrowStarts + NNp + 1); gtRow.assign(P->sparseGcol, P->sparseGcol + nnzG); }
+      } else {
+      ts.assign((size_t)NNp + 1, 0); tcol.resize((size_t)nnzG);
 #pragma omp parallel for schedule(static)
       for (int k = 0; k < nnzG; k++) {
 #pragma omp atomic
@@ -2838,32 +3107,38 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             for (int p = ts[j], q = 0; p < ts[j + 1]; p++, q++) {
                const int k = row[q].second;
                tcol[p] = row[q].first;
-               t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k];
+               tsrc[p] = k;
+               if (!dev0) { t1[p] = P->sparseG1value[k]; t2[p] = P->sparseG2value[k]; t3[p] = P->sparseG3value[k]; }
             }
          }
       }
-      std::vector<int>().swap(tsrc);
-      SellHost h;
+      SellHost& h = hGT;
       sell_build_host(NPo, NN, ts.data(), tcol.data(), choose_T(NPo, ts[NPo]), h);   // rows = owned pressure DOFs, all local velocity columns
       const double* v[3] = {t1.get(), t2.get(), t3.get()};
       TRY(sell_upload(h, 3, v, c->GT));
+      if (dev0) { gtSrc.swap(tsrc); gtRs.swap(ts); gtRow.swap(tcol); } else hGT = SellHost();
+      }
    }
    IPHASE("Sell G^T");
    {
       const int Tz = choose_T(NPo, P->sparseZrowStarts[NPo]);
       const bool sameZ = sameG && Tz == Tv && P->sparseZrowStarts == P->sparseMrowStarts && P->sparseZcol == P->sparseMcol;
-      SellHost hOwn;
-      if (!sameZ) sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, Tz, hOwn);
-      SellHost& h = sameZ ? hK : hOwn;
+      if (!sameZ) sell_build_host(NPo, NNp, P->sparseZrowStarts, P->sparseZcol, Tz, hZ);
+      SellHost& h = sameZ ? hK : hZ;
       c->hostOffZ = h.sliceOff;
-      const double* v[1] = {P->sparseZvalue};
+      const double* v[1] = {dev0 ? nullptr : P->sparseZvalue};
       TRY(sell_upload(h, 1, v, c->Z));
-      std::vector<double> dinv(NPo, 1.0);
+      if (dev0) {
+         TRY(dalloc(c, &c->Zdinv, (size_t)NPo));   // filled by the device step0 below
+      } else {
+         std::vector<double> dinv(NPo, 1.0);
 #pragma omp parallel for schedule(static)
-      for (int r = 0; r < NPo; r++)
-         for (int k = P->sparseZrowStarts[r]; !o.cg_no_precond && k < P->sparseZrowStarts[r + 1]; k++)
-            if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
-      TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
+         for (int r = 0; r < NPo; r++)
+            for (int k = P->sparseZrowStarts[r]; !o.cg_no_precond && k < P->sparseZrowStarts[r + 1]; k++)
+               if (P->sparseZcol[k] == r) { dinv[r] = 1.0 / P->sparseZvalue[k]; break; }
+         TRY(dupload(c, &c->Zdinv, dinv.data(), dinv.size()));
+         if (!sameZ) hZ = SellHost();
+      }
    }
    IPHASE("Sell Z");
    // ---- mesh tables
@@ -2923,8 +3198,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    // ---- vectors
    const long long N3 = 3LL * NN;
    if (P->scheme == CFD_EXPLICIT) {
-      TRY(dupload(c, &c->MdInv, P->MdInv, (size_t)N3));
-      TRY(dupload(c, &c->MdOrigInv, P->MdOrigInv, (size_t)N3));
+      if (dev0) { TRY(dalloc(c, &c->MdInv, (size_t)N3)); TRY(dalloc(c, &c->MdOrigInv, (size_t)N3)); }
+      else { TRY(dupload(c, &c->MdInv, P->MdInv, (size_t)N3)); TRY(dupload(c, &c->MdOrigInv, P->MdOrigInv, (size_t)N3)); }
       TRY(regvec(c, "Un", &c->Un, N3)); TRY(regvec(c, "Unp1", &c->Unp1, N3)); TRY(regvec(c, "Unp1_prev", &c->Unp1_prev, N3));
       TRY(regvec(c, "UnpHalf", &c->UnpHalf, N3)); TRY(regvec(c, "UnpHalf_prev", &c->UnpHalf_prev, N3));
       TRY(regvec(c, "Acc", &c->Acc, N3)); TRY(regvec(c, "Acc_prev", &c->Acc_prev, N3));
@@ -2960,6 +3235,101 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       if (P->P0) CFD_CK(cudaMemcpy(Pd, P->P0, sizeof(double) * NNp, cudaMemcpyHostToDevice));
    }
    IPHASE("tables + vectors");
+   // ---- step0 on the device (cfd_options.step0_device = 1): the value arrays are computed here from the mesh and the patterns
+   std::vector<double> zHost;   // host copy of Z's values for the resident-PCG builder below (small systems only)
+   if (dev0) {
+      DevScratch tmp;
+      tmp.st = c->stream;
+      CFD_CK(cudaDeviceSynchronize());   // the zero fills and uploads above ran on the legacy stream; the kernels below run on c->stream
+      const size_t nnzM = (size_t)P->sparseMrowStarts[NN], nnzG = (size_t)P->sparseGrowStarts[NN], nnzZ = (size_t)P->sparseZrowStarts[NNp];
+      const bool sameZp = P->sparseZrowStarts == P->sparseMrowStarts && P->sparseZcol == P->sparseMcol;
+      {
+         // the position search is a bisection: columns must ascend within every row (the product's own patterns do)
+         auto sorted = [](int nrows, const int* rs, const int* col) {
+            int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+            for (int r = 0; r < nrows; r++)
+               for (int k = rs[r] + 1; k < rs[r + 1]; k++) bad += col[k] <= col[k - 1];
+            return bad == 0;
+         };
+         if (!sorted(NN, P->sparseMrowStarts, P->sparseMcol) || (!sameG && !sorted(NN, P->sparseGrowStarts, P->sparseGcol)) ||
+             (!sameZp && !sorted(NNp, P->sparseZrowStarts, P->sparseZcol))) {
+            set_error("step0_device = 1 needs ascending column indices within every CSR row");
+            cfd_destroy(c);
+            return CFD_ERR_ARG;
+         }
+      }
+      int *dMrs = nullptr, *dMcol = nullptr, *dGrs = nullptr, *dGcol = nullptr, *dZrs = nullptr, *dZcol = nullptr;
+      TRY(tmp.up(&dMrs, P->sparseMrowStarts, (size_t)NN + 1)); TRY(tmp.up(&dMcol, P->sparseMcol, nnzM));
+      if (sameG) { dGrs = dMrs; dGcol = dMcol; } else { TRY(tmp.up(&dGrs, P->sparseGrowStarts, (size_t)NN + 1)); TRY(tmp.up(&dGcol, P->sparseGcol, nnzG)); }
+      if (sameZp) { dZrs = dMrs; dZcol = dMcol; } else { TRY(tmp.up(&dZrs, P->sparseZrowStarts, (size_t)NNp + 1)); TRY(tmp.up(&dZcol, P->sparseZcol, nnzZ)); }
+      double *dM = nullptr, *dK = nullptr, *dG[3] = {nullptr, nullptr, nullptr}, *dZ = nullptr, *dmd = nullptr;
+      TRY(tmp.zeros(&dM, nnzM)); TRY(tmp.zeros(&dK, nnzM));
+      for (int d = 0; d < 3; d++) TRY(tmp.zeros(&dG[d], nnzG));
+      TRY(tmp.zeros(&dZ, nnzZ));
+      const bool imp = P->scheme == CFD_IMPLICIT;
+      const double mscale = imp ? 1.0 / P->dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
+      {
+         const dim3 grid((unsigned)gridFor(NE, 128), (unsigned)nv);
+         if (nv == 27)
+            k_step0_elements<27><<<grid, 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, c->coord, dMrs, dMcol, dGrs, dGcol, dZrs, dZcol, mscale, P->viscosity,
+                                                              1.0 / P->density, dM, dK, dG[0], dG[1], dG[2], imp ? dZ : nullptr);
+         else
+            k_step0_elements<8><<<grid, 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, c->coord, dMrs, dMcol, dGrs, dGcol, dZrs, dZcol, mscale, P->viscosity,
+                                                             1.0 / P->density, dM, dK, dG[0], dG[1], dG[2], imp ? dZ : nullptr);
+         c->launches++;
+         CFD_CK(cudaGetLastError());
+      }
+      int* dGtSrc = nullptr;
+      TRY(tmp.up(&dGtSrc, gtSrc.data(), nnzG));
+      if (!imp) {
+         TRY(tmp.zeros(&dmd, (size_t)NN));
+         k_step0_lump<<<gridFor(NN, 256), 256, 0, c->stream>>>(NN, dMrs, dM, c->bcIndex, dmd, c->MdOrigInv, c->MdInv);
+         int *dTs = nullptr, *dTrow = nullptr;
+         TRY(tmp.up(&dTs, gtRs.data(), (size_t)NNp + 1)); TRY(tmp.up(&dTrow, gtRow.data(), nnzG));
+         k_step0_spgemm_z<<<gridFor((long long)NNp * 32, 256), 256, 0, c->stream>>>(NNp, dTs, dTrow, dGtSrc, dGrs, dGcol, dG[0], dG[1], dG[2], dmd, dZrs, dZcol, dZ);
+         c->launches += 2;
+         CFD_CK(cudaGetLastError());
+      }
+      k_step0_diag<<<gridFor(NPo, 256), 256, 0, c->stream>>>(NPo, dZrs, dZcol, dZ, c->pin, o.cg_no_precond ? 1 : 0, c->Zdinv);
+      c->launches++;
+      // CSR order -> Sell layout (padding entries stay zero)
+      auto scatter = [&](const std::vector<long long>& perm, long long** dperm, size_t n, const double* a, const double* b, double* dst) -> int {
+         if (!*dperm) { int rc2 = tmp.up(dperm, perm.data(), n); if (rc2) return rc2; }
+         k_step0_scatter<<<gridFor((long long)n, 256), 256, 0, c->stream>>>((long long)n, *dperm, a, b, dst);
+         c->launches++;
+         CFD_CK(cudaGetLastError());
+         return CFD_OK;
+      };
+      long long *dPermK = nullptr, *dPermG = nullptr, *dPermGT = nullptr, *dPermZ = nullptr;
+      if (imp) {
+         TRY(scatter(hK.perm, &dPermK, nnzM, dM, dK, c->K.vals[0]));    // M + K (calculate_MplusK, GQ.cu:537-547)
+         TRY(scatter(hK.perm, &dPermK, nnzM, dM, nullptr, c->K.vals[1]));
+      } else {
+         TRY(scatter(hK.perm, &dPermK, nnzM, dK, nullptr, c->K.vals[0]));
+      }
+      if (sameG) dPermG = dPermK;
+      for (int d = 0; d < 3; d++) TRY(scatter(hG.perm, &dPermG, nnzG, dG[d], nullptr, c->G.vals[d]));
+      {
+         double* dT = nullptr;
+         TRY(tmp.alloc((void**)&dT, sizeof(double) * nnzG));
+         for (int d = 0; d < 3; d++) {
+            k_step0_gather<<<gridFor((long long)nnzG, 256), 256, 0, c->stream>>>((long long)nnzG, dGtSrc, dG[d], dT);
+            c->launches++;
+            if (hGT.perm.empty()) dPermGT = dPermK;   // G^T shares the K / M / A layout (Q1/Q1 on a whole mesh)
+            TRY(scatter(hGT.perm, &dPermGT, nnzG, dT, nullptr, c->GT.vals[d]));
+         }
+      }
+      if (hZ.perm.empty()) dPermZ = dPermK;   // Z shares the K / M / A layout (Q1/Q1 on a whole mesh)
+      TRY(scatter(hZ.perm, &dPermZ, nnzZ, dZ, nullptr, c->Z.vals[0]));
+      CFD_CK(cudaStreamSynchronize(c->stream));
+      if ((long long)nnzZ * 8 <= 232448LL * c->numSMs) {
+         zHost.resize(nnzZ);
+         CFD_CK(cudaMemcpy(zHost.data(), dZ, sizeof(double) * nnzZ, cudaMemcpyDeviceToHost));
+      }
+      hG = SellHost(); hGT = SellHost(); hZ = SellHost();
+      IPHASE("step0 on the device");
+   }
    // ---- partition plan
    if (parted) {
       const int np = P->nPeers;
@@ -3059,19 +3429,21 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             int maxOptin = 0;
             CFD_CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
             const long long cap = (long long)maxOptin - 4 * 32 * 8 - 256;   // static shared memory of the kernel + slack
-            const int* rs = P->sparseZrowStarts; const int* cl = P->sparseZcol; const double* zv = P->sparseZvalue;
+            const int* rs = P->sparseZrowStarts; const int* cl = P->sparseZcol; const double* zv = dev0 ? zHost.data() : P->sparseZvalue;
             const int nC = c->numSMs, n = NPo;
             const long long nnzZ = rs[n];
-            if (nnzZ * 8 <= cap * nC) {
+            if (nnzZ * 8 <= cap * nC && (!dev0 || (long long)zHost.size() == nnzZ)) {
                // lanes per row: fewest sequential entry pairs per warp (groups dealt round-robin to the 32 warps of a CTA)
                const double avgLen = (double)nnzZ / n, rowsPer = std::max(1.0, (double)n / nC);
                int bestT = 8; double bestCost = 1e300;
-               for (int T = 2; T <= 32; T *= 2) {
-                  const double groups = std::ceil(rowsPer / (32 / T)), rounds = std::ceil(groups / 32.0);
-                  const double cost = rounds * (std::ceil(std::ceil(avgLen / T) / 2.0) + 0.25 * std::log2((double)T));
+               for (int T = 1; T <= 32; T *= 2) {
+                  const double groups = std::ceil(rowsPer / (32 / T)), rounds = std::ceil(groups / (double)kResWarps);
+                  const double pairs = std::ceil(std::ceil(avgLen / T) / 2.0);
+                  // a warp's first group keeps up to 32 column-id pairs in registers; anything beyond is re-requested from L2 every sweep
+                  const double cost = rounds * (pairs + 0.25 * std::log2((double)T)) + (rounds > 1.0 || pairs > 32.0 ? 24.0 : 0.0);
                   if (cost < bestCost) { bestCost = cost; bestT = T; }
                }
-               if (const char* e = getenv("CFD_PCG_RES_T")) { const int t = atoi(e); if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) bestT = t; }
+               if (const char* e = getenv("CFD_PCG_RES_T")) { const int t = atoi(e); if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32) bestT = t; }
                const int T = bestT, R = 32 / T;
                std::vector<ResCta> cta(nC);
                std::vector<int> grp, cols;
@@ -3079,35 +3451,47 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                long long totalEntries = 0, maxBytes = 0;
                bool ok = true;
                int r = 0;
-               for (int b = 0; b < nC; b++) {
-                  ResCta& k = cta[b];
-                  k.row0 = r;
-                  const long long target = (long long)((double)nnzZ * (b + 1) / nC);
-                  while (r < n && (rs[r + 1] <= target || b == nC - 1)) r++;
-                  k.nrows = r - k.row0;
-                  k.ngroups = (k.nrows + R - 1) / R;
-                  k.valOff = totalEntries; k.grpOff = (long long)grp.size(); k.colOff = (long long)cols.size();
-                  std::vector<int>& u = ctaCols[b];
-                  for (int q = rs[k.row0]; q < rs[r]; q++) u.push_back(cl[q]);
-                  std::sort(u.begin(), u.end());
-                  u.erase(std::unique(u.begin(), u.end()), u.end());
-                  k.ncols = (int)u.size();
-                  cols.insert(cols.end(), u.begin(), u.end());
-                  int off = 0;
-                  for (int g = 0; g < k.ngroups; g++) {
-                     grp.push_back(off);
-                     int w = 0;
-                     for (int rl = 0; rl < R && k.row0 + g * R + rl < r; rl++) {
-                        const int rr2 = k.row0 + g * R + rl;
-                        w = std::max(w, (rs[rr2 + 1] - rs[rr2] + T - 1) / T);
+               // Row blocks: contiguous, an even share of the STORED entries each -- shared-memory traffic is what a sweep costs.  (Capping
+               // the rows of a block at one row group per warp, so that all column ids stay in registers, does not work out: blocks of
+               // short boundary rows then take less than their share and the last block overflows its shared memory.)
+               {
+                  const int rowCap = kResThreads;
+                  auto rowEntries = [&](int row) { return (long long)((((rs[row + 1] - rs[row] + T - 1) / T) + 1) & ~1) * T; };   // (estimate: the row's own padded width)
+                  long long remaining = 0;
+                  for (int row = 0; row < n; row++) remaining += rowEntries(row);
+                  for (int b = 0; b < nC; b++) {
+                     ResCta& k = cta[b];
+                     k.row0 = r;
+                     const long long target = remaining / (nC - b);
+                     long long took = 0;
+                     while (r < n && (b == nC - 1 || (r - k.row0 < rowCap && took + rowEntries(r) <= target + rowEntries(r) / 2))) { took += rowEntries(r); r++; }
+                     remaining -= took;
+                     k.nrows = r - k.row0;
+                     k.ngroups = (k.nrows + R - 1) / R;
+                     k.valOff = totalEntries; k.grpOff = (long long)grp.size(); k.colOff = (long long)cols.size();
+                     std::vector<int>& u = ctaCols[b];
+                     u.clear();
+                     for (int q = rs[k.row0]; q < rs[r]; q++) u.push_back(cl[q]);
+                     std::sort(u.begin(), u.end());
+                     u.erase(std::unique(u.begin(), u.end()), u.end());
+                     k.ncols = (int)u.size();
+                     cols.insert(cols.end(), u.begin(), u.end());
+                     int off = 0;
+                     for (int g = 0; g < k.ngroups; g++) {
+                        grp.push_back(off);
+                        int w = 0;
+                        for (int rl = 0; rl < R && k.row0 + g * R + rl < r; rl++) {
+                           const int rr2 = k.row0 + g * R + rl;
+                           w = std::max(w, (rs[rr2 + 1] - rs[rr2] + T - 1) / T);
+                        }
+                        off += ((w + 1) & ~1) * 32;
                      }
-                     off += ((w + 1) & ~1) * 32;
+                     grp.push_back(off);
+                     totalEntries += off;
+                     const long long bytes = 8LL * off + 8LL * ((k.ncols + 1) & ~1) + 8LL * k.nrows;
+                     maxBytes = std::max(maxBytes, bytes);
+                     if (k.nrows > kResThreads || k.ncols > 65535) ok = false;
                   }
-                  grp.push_back(off);
-                  totalEntries += off;
-                  const long long bytes = 8LL * off + 8LL * ((k.ncols + 1) & ~1) + 8LL * k.nrows;
-                  maxBytes = std::max(maxBytes, bytes);
-                  if (k.nrows > 1024 || k.ncols > 65535) ok = false;
                }
                if (ok && maxBytes <= cap && r == n) {
                   std::vector<double> vals((size_t)std::max<long long>(totalEntries, 2), 0.0);
@@ -3129,7 +3513,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                   }
                   CFD_CK(cudaFuncSetAttribute((const void*)k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
                   int occR = 0;
-                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, (const void*)k_pcg_res, 1024, (size_t)maxBytes));
+                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, (const void*)k_pcg_res, kResThreads, (size_t)maxBytes));
                   if (occR >= 1) {
                      ResCta* dcta = nullptr;
                      TRY(dupload(c, &dcta, cta.data(), cta.size()));

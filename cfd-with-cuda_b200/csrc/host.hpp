@@ -85,7 +85,7 @@ void find_monitor(Mesh& m);
 void color_mesh(Mesh& m);
 void build_pattern(const Mesh& m, int nRowLoc, int nColLoc, int nrows, int ncols, CsrPattern& P, std::vector<int>* map,
                    const std::vector<int>* rowIndex = nullptr, const std::vector<int>* colIndex = nullptr);
-void assemble_step0(const Mesh& m, int scheme, Assembled& A);
+void assemble_step0(const Mesh& m, int scheme, Assembled& A, bool patternsOnly = false);
 bool write_tecplot(const Mesh& m, const double* U, const double* P, const std::string& path, const std::string& title);
 bool read_restart(const Mesh& m, const std::string& path, double* U, double* P);
 

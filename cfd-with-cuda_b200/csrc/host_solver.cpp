@@ -88,27 +88,73 @@ static double wall_s() {
 static bool verbose() { return getenv("CFD_VERBOSE") != nullptr; }
 #define PHASE(msg) do { if (verbose()) { double t_ = wall_s(); fprintf(stderr, "[cfdb200 host] %-28s %8.2f s\n", msg, t_ - tph); tph = t_; } } while (0)
 
-void assemble_step0(const Mesh& m, int scheme, Assembled& A) {
+void assemble_step0(const Mesh& m, int scheme, Assembled& A, bool patternsOnly) {
    const int NE = m.NE, nv = m.NENv, NN = m.NN, NNp = m.NNp;
    double tph = wall_s();
    FeTables T;
    build_fe_tables(nv, T);
    const std::vector<int>* pidx = m.presIndex.empty() ? nullptr : &m.presIndex;
-   build_pattern(m, nv, nv, NN, NN, A.Mp, &A.mapM);
+   // patternsOnly (cfd_options.step0_device = 1): the device evaluates the element integrals and finds the entries by bisection, so
+   // only the patterns are built here -- plus the element -> entry map of the K / M / A pattern where the implicit scheme needs it
+   // for its per-step assembly
+   build_pattern(m, nv, nv, NN, NN, A.Mp, (patternsOnly && scheme == CFD_EXPLICIT) ? nullptr : &A.mapM);
    const bool samePattern = (nv == 8 && !pidx);   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z share one pattern
    A.sharedG = samePattern;
-   if (!samePattern) build_pattern(m, nv, 8, NN, NNp, A.GpOwn, &A.mapGOwn, nullptr, pidx);
+   if (!samePattern) build_pattern(m, nv, 8, NN, NNp, A.GpOwn, patternsOnly ? nullptr : &A.mapGOwn, nullptr, pidx);
    PHASE("patterns M, G");
    const size_t nnzM = (size_t)A.Mp.nnz(), nnzG = (size_t)A.Gp().nnz();
-   par_zero(A.Mval, nnzM); par_zero(A.Kval, nnzM);
-   par_zero(A.G1, nnzG); par_zero(A.G2, nnzG); par_zero(A.G3, nnzG);
+   if (!patternsOnly) {
+      par_zero(A.Mval, nnzM); par_zero(A.Kval, nnzM);
+      par_zero(A.G1, nnzG); par_zero(A.G2, nnzG); par_zero(A.G3, nnzG);
+   }
    const double invDens = 1.0 / m.density;
    const double mscale = scheme == CFD_IMPLICIT ? 1.0 / m.dt : 1.0;   // implicit M carries 1/dt (GQ.cpp:3495)
    if (scheme == CFD_IMPLICIT) {
       A.sharedZ = samePattern;
-      if (!samePattern) build_pattern(m, 8, 8, NNp, NNp, A.ZpOwn, &A.mapZOwn, pidx, pidx);
-      par_zero(A.Zval, (size_t)A.Zp().nnz());
+      if (!samePattern) build_pattern(m, 8, 8, NNp, NNp, A.ZpOwn, patternsOnly ? nullptr : &A.mapZOwn, pidx, pidx);
+      if (!patternsOnly) par_zero(A.Zval, (size_t)A.Zp().nnz());
       PHASE("pattern Z");
+   }
+   if (patternsOnly) {
+      if (scheme == CFD_EXPLICIT) {
+         // pattern of Z = sum_c G_c^T Md^-1 G_c: row i = union of the rows of G over the velocity nodes coupled to pressure node i
+         const CsrPattern& G = A.Gp();
+         std::vector<int> ts((size_t)NNp + 1, 0), trow(nnzG);
+         for (size_t k = 0; k < nnzG; k++) ts[G.col[k] + 1]++;
+         for (int i = 0; i < NNp; i++) ts[i + 1] += ts[i];
+         {
+            std::vector<int> fill(ts.begin(), ts.end() - 1);
+            for (int r = 0; r < NN; r++)
+               for (int k = G.rowStarts[r]; k < G.rowStarts[r + 1]; k++) trow[fill[G.col[k]]++] = r;
+         }
+         CsrPattern& Z = A.Zp();
+         Z.nrows = Z.ncols = NNp;
+         Z.rowStarts.assign((size_t)NNp + 1, 0);
+         std::vector<std::vector<int> > zc(NNp);
+#pragma omp parallel
+         {
+            std::vector<int> mark((size_t)NNp, -1), list;
+#pragma omp for schedule(dynamic, 256)
+            for (int i = 0; i < NNp; i++) {
+               list.clear();
+               for (int t = ts[i]; t < ts[i + 1]; t++) {
+                  const int r = trow[t];
+                  for (int k = G.rowStarts[r]; k < G.rowStarts[r + 1]; k++) {
+                     const int j = G.col[k];
+                     if (mark[j] != i) { mark[j] = i; list.push_back(j); }
+                  }
+               }
+               std::sort(list.begin(), list.end());
+               zc[i] = list;
+            }
+         }
+         for (int i = 0; i < NNp; i++) Z.rowStarts[i + 1] = Z.rowStarts[i] + (int)zc[i].size();
+         Z.col.resize((size_t)Z.rowStarts[NNp]);
+#pragma omp parallel for schedule(static)
+         for (int i = 0; i < NNp; i++) std::copy(zc[i].begin(), zc[i].end(), Z.col.begin() + Z.rowStarts[i]);
+         PHASE("pattern Z (symbolic product)");
+      }
+      return;
    }
    // Deterministic assembly: every CSR entry receives its element contributions in ASCENDING ELEMENT ORDER -- the order of the
    // reference's serial element loop (BCH.cpp:3127-3315) -- whatever the number of threads, so K, M, G and Z are bitwise the same
@@ -491,7 +537,9 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
       s->partitioned = true;
    }
    Mesh& m = s->mesh;
-   assemble_step0(m, scheme, s->A);
+   const bool dev0 = s->opt.step0_device == 1;
+   if (dev0 && world > 1) { set_error("step0_device = 1 is single-GPU"); return CFD_ERR_ARG; }
+   assemble_step0(m, scheme, s->A, dev0);
    cfd_problem& P = s->prob;
    memset(&P, 0, sizeof P);
    P.scheme = scheme; P.NE = m.NE; P.NN = m.NN; P.NNp = m.NNp; P.NENv = m.NENv; P.NENp = m.NENp; P.NGP = m.NGP;
@@ -499,12 +547,12 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    P.convergenceCriteria = m.converge;
    P.coord = m.coord.data(); P.LtoGnode = m.LtoGnode.data();
    P.sparseM_nnz = (int)s->A.Mp.nnz(); P.sparseMrowStarts = s->A.Mp.rowStarts.data(); P.sparseMcol = s->A.Mp.col.data();
-   P.sparseKvalue = s->A.Kval.data(); P.sparseMvalue = s->A.Mval.data();
+   P.sparseKvalue = dev0 ? nullptr : s->A.Kval.data(); P.sparseMvalue = dev0 ? nullptr : s->A.Mval.data();
    P.sparseG_nnz = (int)s->A.Gp().nnz(); P.sparseGrowStarts = s->A.Gp().rowStarts.data(); P.sparseGcol = s->A.Gp().col.data();
-   P.sparseG1value = s->A.G1.data(); P.sparseG2value = s->A.G2.data(); P.sparseG3value = s->A.G3.data();
+   P.sparseG1value = dev0 ? nullptr : s->A.G1.data(); P.sparseG2value = dev0 ? nullptr : s->A.G2.data(); P.sparseG3value = dev0 ? nullptr : s->A.G3.data();
    P.sparseZ_nnz = (int)s->A.Zp().nnz(); P.sparseZrowStarts = s->A.Zp().rowStarts.data(); P.sparseZcol = s->A.Zp().col.data();
-   P.sparseZvalue = s->A.Zval.data();
-   P.sparseMapM_1d = s->A.mapM.data();
+   P.sparseZvalue = dev0 ? nullptr : s->A.Zval.data();
+   P.sparseMapM_1d = s->A.mapM.empty() ? nullptr : s->A.mapM.data();
    P.MdInv = s->A.MdInv.empty() ? nullptr : s->A.MdInv.data();
    P.MdOrigInv = s->A.MdOrigInv.empty() ? nullptr : s->A.MdOrigInv.data();
    P.BCnVelNodes = m.BCnVelNodes; P.BCvelNodes = m.BCvelNodes.data(); P.nBC = m.nBC; P.BCstr = m.BCstr.data();

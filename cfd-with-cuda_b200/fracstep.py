@@ -55,7 +55,7 @@ class cfd_options(C.Structure):
         ("cg_tol", C.c_double), ("cg_maxit", C.c_int), ("cg_warm_start", C.c_int),
         ("bicg_tol", C.c_double), ("bicg_maxit", C.c_int), ("maxacc_rule", C.c_int),
         ("device", C.c_int), ("ebe_scatter", C.c_int), ("cg_no_precond", C.c_int), ("deterministic", C.c_int), ("bicg_no_halfstep", C.c_int), ("bicg_no_verify", C.c_int), ("cg_variant", C.c_int),
-        ("operator_path", C.c_int), ("reserved", C.c_int * 1), ("cuda_stream", C.c_void_p),
+        ("operator_path", C.c_int), ("step0_device", C.c_int), ("cuda_stream", C.c_void_p),
     ]
 
 

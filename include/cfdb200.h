@@ -126,7 +126,11 @@ typedef struct cfd_options {
                          operator applications (step 1: -C(U)U - K U - G P in ONE element pass, step 2: G^T d, step 3: G Pdot, K Acc) are
                          evaluated element by element from the integrals of step0 (BCH.cpp:3127-3315), no matrix stream.  Same
                          results to rounding.  Single GPU; the pressure solve keeps its assembled Z */
-   int reserved[1];
+   int step0_device;  /* 0 (default) = the matrix value arrays of cfd_problem (K, M, G1..3, Z, MdInv, MdOrigInv) come from the host, as the
+                         reference's step0 / calculateZ leave them (BCH.cpp:3127-3479, GQ.cpp:3425-3772); 1 = those pointers may be NULL: the
+                         element integrals, the lumped mass, Z (explicit: G^T Md^-1 G as a device sparse product; implicit: FE Laplacian)
+                         and the pin are evaluated on the GPU from coord / LtoGnode and the three CSR patterns (columns ascending within
+                         each row).  Equal to the host arrays to rounding.  Single GPU */
    void* cuda_stream; /* cudaStream_t to launch on (e.g. torch's current stream); NULL = own stream */
 } cfd_options;
 

@@ -631,25 +631,84 @@ def test_matrix_free_time_loop(mesh, name):
 
 
 def test_shared_memory_resident_pcg_equals_the_streaming_kernel(mesh, monkeypatch):
-    """Small pressure systems run k_pcg_smem (matrix values resident in shared memory for the whole solve, one CTA per SM); larger ones
-    the streaming kernel k_pcg_t.  Same recurrences: on the same system both give the same iteration count and the same solution to
-    rounding -- checked through the explicit time loop of a mesh small enough for the resident kernel, with and without it."""
+    """Small pressure systems run a RESIDENT kernel (one CTA per SM for the whole solve): k_pcg_res (row blocks per CTA: values in
+    shared memory, the vector entries a block touches staged per sweep, vectors in registers) or, if a block does not fit, k_pcg_smem
+    (values in shared memory only); larger ones the streaming kernel k_pcg_t.  Same Jacobi-PCG: on the same system all give the same
+    iteration counts and the same solution to rounding -- checked through the explicit time loop of a mesh small enough for the resident
+    kernels, with each of the three, cold and warm started."""
     import fracstep
     import orc
     path = mesh("q2_c6_smem", n=6, cluster=2.0)
     o = orc.Oracle(path, "explicit")
     o.run(3)
     out = {}
-    for resident in (True, False):
-        if resident:
-            monkeypatch.delenv("CFD_NO_PCG_SMEM", raising=False)
-        else:
+    for kernel in ("res", "smem", "stream"):
+        monkeypatch.delenv("CFD_NO_PCG_SMEM", raising=False)
+        monkeypatch.delenv("CFD_NO_PCG_RES", raising=False)
+        if kernel == "smem":
+            monkeypatch.setenv("CFD_NO_PCG_RES", "1")
+        if kernel == "stream":
             monkeypatch.setenv("CFD_NO_PCG_SMEM", "1")
         c = fracstep.Context(fracstep.Problem(o, "explicit"), None)
         reps = c.time_loop(3)
-        out[resident] = (c.fields(), [r["cg_iterations"] for r in reps])
-        U, P = out[resident][0]
-        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-5
+        out[kernel] = (c.fields(), [r["cg_iterations"] for r in reps])
+        U, P = out[kernel][0]
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-5, kernel
+        assert all(r["cg_converged"] for r in reps)
         c.close()
-    assert out[True][1] == out[False][1]
-    assert rel(out[True][0][0], out[False][0][0]) <= 1e-12 and rel(out[True][0][1], out[False][0][1]) <= 1e-9
+        # warm start (the reference's GPU build keeps the previous Pdot, BCH.cu:418-451): r = b - Z x through the same sweep
+        c = fracstep.Context(fracstep.Problem(o, "explicit"), fracstep.options(cg_warm_start=1))
+        reps = c.time_loop(3)
+        out[kernel + "_warm"] = (c.fields(), [r["cg_iterations"] for r in reps])
+        assert all(r["cg_converged"] for r in reps)
+        c.close()
+    for kernel in ("res", "smem"):
+        for sfx in ("", "_warm"):
+            a, b = out[kernel + sfx], out["stream" + sfx]
+            assert max(abs(x - y) for x, y in zip(a[1], b[1])) <= 1, (kernel, sfx, a[1], b[1])
+            assert rel(a[0][0], b[0][0]) <= 1e-9 and rel(a[0][1], b[0][1]) <= 2e-6, (kernel, sfx)   # (P: CG stopped at 1e-6 on both)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("scheme", ["explicit", "implicit"])
+def test_step0_on_the_device(mesh, name, scheme):
+    """cfd_options.step0_device = 1: the host builds the patterns only; element integrals, lumped mass,
+    Z (explicit: G^T Md^-1 G as a device sparse product, implicit: FE Laplacian), pin and the conversion into the device layout
+    run on the GPU.  Checked three ways: (1) the assembled operators K, G, G^T (and the implicit Z) applied to random vectors equal the
+    oracle's (= the reference's) CSR arrays to rounding; (2) the time loop gives the fields of the host-step0 context to rounding
+    (this covers M, the lumped masses and the explicit Z); (3) and the oracle's fields to the parity bar."""
+    import scipy.sparse as sp
+    import fracstep
+    import orc
+    kw = TIGHT if scheme == "implicit" else {}
+    path = mesh(name, **CASES[name])
+    o = orc.Oracle(path, scheme, 1, **kw)
+    rng = np.random.default_rng(7)
+    NN, NNp = o.i("NN"), o.i("NNp")
+    xv, xp = rng.standard_normal(3 * NN), rng.standard_normal(NNp)
+    G = [sp.csr_matrix((o.arr("sparseG%dvalue" % d), o.arr("sparseGcol"), o.arr("sparseGrowStarts")), shape=(NN, NNp)) for d in (1, 2, 3)]
+    ref = {"G": np.concatenate([G[d] @ xp for d in range(3)]), "GT": sum(G[d].T @ xv[d * NN:(d + 1) * NN] for d in range(3))}
+    if scheme == "explicit":
+        K = sp.csr_matrix((o.arr("sparseKvalue"), o.arr("sparseMcol"), o.arr("sparseMrowStarts")), shape=(NN, NN))
+        ref["K"] = np.concatenate([K @ xv[d * NN:(d + 1) * NN] for d in range(3)])
+    else:
+        Z = sp.csr_matrix((o.arr("sparseZvalue"), o.arr("sparseZcol"), o.arr("sparseZrowStarts")), shape=(NNp, NNp))
+        ref["Z"] = Z @ xp
+    n = 3
+    o.run(n)
+    out = {}
+    for dev in (1, 0):
+        s = fracstep.Solver(path, scheme, opts=fracstep.options(step0_device=dev, ebe_scatter=1, deterministic=1, **kw))
+        if dev:
+            assert len(s.arr("sparseKvalue")) == 0 and len(s.arr("sparseZvalue")) == 0 and len(s.arr("sparseG1value")) == 0   # nothing assembled on the host
+            for op in ref:
+                y, _, _ = s.ctx.operator_apply(op, xp if op in ("G", "Z") else xv, path=0)
+                assert rel(y, ref[op]) < 1e-12, (scheme, op, rel(y, ref[op]))
+        reps = s.ctx.time_loop(n)
+        out[dev] = s.ctx.fields()
+        assert all(r["cg_converged"] for r in reps)
+        U, P = out[dev]
+        assert rel(U, o.U) <= 1e-6 and rel(P, o.P) <= 1e-6, (dev, rel(U, o.U), rel(P, o.P))
+        s.close()
+    assert rel(out[1][0], out[0][0]) <= 1e-7 and rel(out[1][1], out[0][1]) <= 1e-6, (rel(out[1][0], out[0][0]), rel(out[1][1], out[0][1]))
