@@ -430,9 +430,11 @@ __global__ void __launch_bounds__(256) k_max_abs_diff(long long n, const double*
 __global__ void __launch_bounds__(256) k_gt_rhs(Sell GT, int NN, int mode, const double* __restrict__ U,
                                                 const double* __restrict__ KAcc, int useKAcc,
                                                 const double* __restrict__ MdOrigInv, double scale, int pinNode,
-                                                double* __restrict__ R2) {
+                                                double* __restrict__ R2, double* __restrict__ zero4 = nullptr) {
    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
    const int slice = gthread >> 5, lane = gthread & 31;
+   // the four convergence sums k_pressure_update / k_step3 accumulate later in this inner iteration start from zero (was a memset launch)
+   if (zero4 != nullptr && gthread < 4) zero4[gthread] = 0.0;
    if (slice >= GT.nslices) return;
    double acc = 0.0;
    sell_pairs<1>(GT, slice, lane, [&](long long e, int2 c2) {
@@ -839,7 +841,7 @@ __device__ __forceinline__ int csr_find(const int* __restrict__ rs, const int* _
    int lo = __ldg(rs + row), hi = __ldg(rs + row + 1) - 1;
    if (hi < lo) return -1;
    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
+      const int mid = lo + ((hi - lo) >> 1);   // (lo + hi overflows an int on the 128^3 Q2/Q1 mesh: 1.08e9 entries)
       if (__ldg(col + mid) < c) lo = mid + 1; else hi = mid;
    }
    return __ldg(col + lo) == c ? lo : -1;
@@ -957,6 +959,28 @@ __global__ void __launch_bounds__(256) k_step0_spgemm_z(int NNp, const int* __re
       }
       __syncwarp();   // the next r may touch the same Z entries from other lanes
    }
+}
+
+// implicit scheme: element -> device-layout position map of the K / M / A pattern ([i*NV+j][e], what k_ebe_convect_assemble scatters
+// through) and the positions of the diagonal, found by bisection instead of being marshalled from the host's sparseMapM_1d
+template <int NV>
+__global__ void __launch_bounds__(128) k_step0_map(int NE, int ldE, const int* __restrict__ LtoGT, const int* __restrict__ Mrs, const int* __restrict__ Mcol,
+                                                   const long long* __restrict__ perm, int* __restrict__ mapT) {
+   const int e = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+   if (e >= ldE) return;
+   int out = 0;
+   if (e < NE) {
+      const int pos = csr_find(Mrs, Mcol, __ldg(LtoGT + (long long)(q / NV) * ldE + e), __ldg(LtoGT + (long long)(q % NV) * ldE + e));
+      out = pos >= 0 ? (int)perm[pos] : -1;
+   }
+   mapT[(long long)q * ldE + e] = out;
+}
+__global__ void __launch_bounds__(256) k_step0_diagpos(int n, const int* __restrict__ rs, const int* __restrict__ col, const long long* __restrict__ perm,
+                                                       int* __restrict__ diagPos) {
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= n) return;
+   const int pos = csr_find(rs, col, r, r);
+   diagPos[r] = pos >= 0 ? (int)perm[pos] : 0;
 }
 
 // dst[perm[k]] = a[k] (+ b[k]): CSR order -> Sell layout;  dst[k] = src[idx[k]]: transposed values;  1/diag of a CSR matrix
@@ -1442,6 +1466,7 @@ struct PcgResArgs {
    const double* b;
    double* x;
    double* u;                    // the one vector other CTAs read: u = M^-1 r
+   double* u2;                   // pipelined form: second buffer for it (m = M^-1 w alternates between the two)
    const double* dinv;
    double* scratch;
    double* info;
@@ -1450,6 +1475,12 @@ struct PcgResArgs {
 };
 constexpr int kResThreads = 512;   // 16 warps, 128 registers per thread: room for the cached column ids
 constexpr int kResWarps = kResThreads / 32;
+// PIPE = true: pipelined recurrences (Ghysels-Vanroose): the dot products (r,u), (w,u), (r,r) use vectors that exist BEFORE the sweep of
+// the iteration, so their partials ride on the same grid-wide barrier that publishes m = M^-1 w for the sweep n = Z m -- ONE barrier per
+// iteration instead of two.  Same iterates as classical PCG in exact arithmetic (x, r, u = M^-1 r, w = Z u, and the search directions
+// p, s = Z p, q = M^-1 s, z = Z q are all advanced by recurrences in registers); the stopping test sees |r_i| after i updates, like
+// the classical kernel, so the iteration counts agree.
+template <bool PIPE>
 __global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
    cg::grid_group grid = cg::this_grid();
    extern __shared__ double zs[];   // values | staged vector entries | this CTA's rows of w = Z u
@@ -1488,7 +1519,7 @@ __global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
 #pragma unroll
    for (int q = 0; q < kResCache; q++) ireg[q] = q < np0 ? __ldg(reinterpret_cast<const unsigned*>(idx + off0) + lane + q * 32) : 0u;
    // the staged columns likewise: up to kResCols per thread in registers (one L2 round trip per sweep instead of two)
-   constexpr int kResCols = 8;
+   constexpr int kResCols = 6;
    int creg[kResCols];
    const bool colsCached = c.ncols <= kResCols * kResThreads;
 #pragma unroll
@@ -1550,6 +1581,37 @@ __global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
    }
    ui = di * ri;
    if (own) a.u[row] = ui;
+   if (PIPE) {
+      grid.sync();
+      sweep(a.u);
+      if (own) wi = wrow[threadIdx.x];
+      double zi = 0.0, qi = 0.0, gammaOld = 1.0, alpha = 1.0, rr = 0.0, bb = 0.0, thresh = 0.0;
+      int it = 0;
+      while (true) {
+         // (iteration 0 writes m into u2: a slower CTA may still be staging u for its first sweep; from then on the barrier of
+         //  iteration i-1 guarantees that nobody reads the buffer iteration i writes)
+         double* mb = (it & 1) ? a.u : a.u2;
+         const double mi = di * wi;
+         if (own) mb[row] = mi;
+         double v4[4] = {ri * ui, wi * ui, ri * ri, bi * bi};
+         grid_sum<4>(grid, v4, (it & 1) ? buf0 + 4 * (size_t)gridDim.x : buf0, sh);   // the one barrier: publishes m as well
+         const double gamma = v4[0], delta = v4[1];
+         rr = v4[2];
+         if (it == 0) { bb = v4[3]; thresh = a.tol * sqrt(bb); }
+         if (sqrt(rr) <= thresh || it >= a.maxit) break;
+         sweep(mb);
+         const double ni = own ? wrow[threadIdx.x] : 0.0;
+         double beta = 0.0;
+         if (it > 0) { beta = gamma / gammaOld; alpha = gamma / (delta - beta * gamma / alpha); } else alpha = gamma / delta;
+         zi = ni + beta * zi; qi = mi + beta * qi; si = wi + beta * si; pi = ui + beta * pi;
+         xi += alpha * pi; ri -= alpha * si; ui -= alpha * qi; wi -= alpha * zi;
+         gammaOld = gamma;
+         it++;
+      }
+      if (own) a.x[row] = xi;
+      if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
+      return;
+   }
    double v4[4] = {ri * ui, 0.0, ri * ri, bi * bi};
    grid.sync();
    sweep(a.u);
@@ -2702,12 +2764,13 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (c->resBytes > 0) {   // small system: row blocks resident per CTA (values in shared memory, vectors in registers)
       PcgResArgs ra;
       ra.cta = (const ResCta*)c->resCta; ra.vals = c->resVals; ra.idx = c->resIdx; ra.cols = c->resCols; ra.grp = c->resGrp; ra.T = c->resT;
-      ra.n = c->P.NNp; ra.b = b; ra.x = x; ra.u = c->cg_p; ra.dinv = c->Zdinv; ra.scratch = c->partials; ra.info = c->kinfo;
+      ra.n = c->P.NNp; ra.b = b; ra.x = x; ra.u = c->cg_p; ra.u2 = c->cg_q; ra.dinv = c->Zdinv; ra.scratch = c->partials; ra.info = c->kinfo;
       ra.tol = c->opt.cg_tol; ra.maxit = c->opt.cg_maxit; ra.x0zero = x0zero ? 1 : 0;
       void* rargs[] = {&ra};
       ProfScope ps(c, "pcg", spmv_bytes(c->Z, 1, 1, false) + (x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false)));
       c->lastPcgRec = ps.idx;
-      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_res, dim3(c->numSMs), dim3(kResThreads), rargs, c->resBytes, c->stream));
+      CFD_CK(cudaLaunchCooperativeKernel(c->resPipe ? (void*)k_pcg_res<true> : (void*)k_pcg_res<false>, dim3(c->numSMs), dim3(kResThreads), rargs,
+                                         c->resBytes, c->stream));
       c->launches++;
       return CFD_OK;
    }
@@ -2939,7 +3002,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    if (!dev0 && P->scheme == CFD_EXPLICIT && (!P->MdInv || !P->MdOrigInv)) { set_error("explicit scheme needs MdInv and MdOrigInv"); return CFD_ERR_ARG; }
    if (opt && opt->operator_path == 1 && P->world > 1) { set_error("operator_path = 1 (matrix-free operators) is single-GPU: interface rows would need a sum exchange"); return CFD_ERR_ARG; }
    if (opt && opt->operator_path != 0 && opt->operator_path != 1) { set_error("operator_path must be 0 (assembled) or 1 (matrix-free)"); return CFD_ERR_ARG; }
-   if (P->scheme == CFD_IMPLICIT && ((!dev0 && !P->sparseMvalue) || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
+   if (P->scheme == CFD_IMPLICIT && !dev0 && (!P->sparseMvalue || !P->sparseMapM_1d)) { set_error("implicit scheme needs sparseMvalue and sparseMapM_1d"); return CFD_ERR_ARG; }
    cfd_options o;
    if (opt) o = *opt; else cfd_default_options(&o);
    int ndev = 0;
@@ -2948,13 +3011,15 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    if (o.device >= 0) CFD_CK(cudaSetDevice(o.device));
    cfd_ctx* c = new cfd_ctx();
    *out = nullptr;
+   // every early return below (CFD_CK, TRY, argument errors) releases what the context holds so far
+   struct InitGuard { cfd_ctx* c; ~InitGuard() { if (c) cfd_destroy(c); } } guard{c};
    c->P = *P;
    c->opt = o;
    CFD_CK(cudaGetDevice(&c->device));
    cudaDeviceProp prop;
    CFD_CK(cudaGetDeviceProperties(&prop, c->device));
    c->numSMs = prop.multiProcessorCount;
-   if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); delete c; return CFD_ERR_CUDA; }
+   if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); return CFD_ERR_CUDA; }
    if (o.cuda_stream) { c->stream = (cudaStream_t)o.cuda_stream; c->ownStream = false; }
    else CFD_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
    CFD_CK(cudaEventCreate(&c->ev0));
@@ -2971,7 +3036,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    c->pin = parted ? P->pinLocal : (P->zeroPressureNode > 0 ? P->zeroPressureNode : -1);   // `node > 0` rule, BCH.cpp:4172
    c->monOwned = parted ? (P->monOwned != 0) : true;
    int rc;
-#define TRY(x) do { rc = (x); if (rc) { cfd_destroy(c); return rc; } } while (0)
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
 
    const bool verb = getenv("CFD_VERBOSE") != nullptr;
    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
@@ -3019,6 +3084,10 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          // element -> Sell position map, transposed to [q][e]
          c->ldE = (NE + 31) & ~31;
          const size_t nmt = (size_t)nv * nv * c->ldE;
+         if (dev0 && !P->sparseMapM_1d) {   // built on the device by the step0 block below
+            TRY(dalloc(c, &c->mapT, nmt));
+            TRY(dalloc(c, &c->diagPosA, (size_t)NNo));
+         } else {
          std::unique_ptr<int[]> mt(new int[nmt]);   // (1 G entries at 256^3: filled in parallel, padding columns included)
 #pragma omp parallel for schedule(static)
          for (int e = 0; e < c->ldE; e++)
@@ -3034,6 +3103,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
             for (int k = P->sparseMrowStarts[r]; k < P->sparseMrowStarts[r + 1]; k++)
                if (P->sparseMcol[k] == r) { dp[r] = (int)h.perm[k]; break; }
          TRY(dupload(c, &c->diagPosA, dp.data(), dp.size()));
+         }
       }
    }
    IPHASE("Sell K/M/A + maps");
@@ -3255,7 +3325,6 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          if (!sorted(NN, P->sparseMrowStarts, P->sparseMcol) || (!sameG && !sorted(NN, P->sparseGrowStarts, P->sparseGcol)) ||
              (!sameZp && !sorted(NNp, P->sparseZrowStarts, P->sparseZcol))) {
             set_error("step0_device = 1 needs ascending column indices within every CSR row");
-            cfd_destroy(c);
             return CFD_ERR_ARG;
          }
       }
@@ -3302,6 +3371,15 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
          return CFD_OK;
       };
       long long *dPermK = nullptr, *dPermG = nullptr, *dPermGT = nullptr, *dPermZ = nullptr;
+      if (imp && !P->sparseMapM_1d) {
+         TRY(tmp.up(&dPermK, hK.perm.data(), nnzM));
+         const dim3 grid((unsigned)gridFor(c->ldE, 128), (unsigned)(nv * nv));
+         if (nv == 27) k_step0_map<27><<<grid, 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, dMrs, dMcol, dPermK, c->mapT);
+         else k_step0_map<8><<<grid, 128, 0, c->stream>>>(NE, c->ldE, c->LtoGT, dMrs, dMcol, dPermK, c->mapT);
+         k_step0_diagpos<<<gridFor(NNo, 256), 256, 0, c->stream>>>(NNo, dMrs, dMcol, dPermK, c->diagPosA);
+         c->launches += 2;
+         CFD_CK(cudaGetLastError());
+      }
       if (imp) {
          TRY(scatter(hK.perm, &dPermK, nnzM, dM, dK, c->K.vals[0]));    // M + K (calculate_MplusK, GQ.cu:537-547)
          TRY(scatter(hK.perm, &dPermK, nnzM, dM, nullptr, c->K.vals[1]));
@@ -3373,7 +3451,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       if (const char* e = getenv("CFD_PCG_OCC")) c->pcg_minb = atoi(e) == 2 ? 2 : 3;
       const void* pcgK = c->cg_variant == 2 ? pcgcg_kernel(parted, c->pcg_minb) : (parted ? (const void*)k_pcg_p2p : (const void*)pcg_kernel(c->pcg_minb));
       CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcgK, c->pcg_threads, 0));
-      if (occ < 1) { set_error("k_pcg does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
+      if (occ < 1) { set_error("k_pcg does not fit on an SM"); return CFD_ERR_CUDA; }
       const long long wantWarps = std::max<long long>(c->Z.nslices, ((long long)NNp + 31) / 32);
       int blocks = c->numSMs * occ;
       const int needed = (int)std::max<long long>(1, (wantWarps * 32 + c->pcg_threads - 1) / c->pcg_threads);
@@ -3382,7 +3460,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
       if (const char* e = getenv("CFD_PCG_BLOCKS")) c->pcg_blocks = std::max(1, std::min(atoi(e), c->numSMs * occ));
       int occ2 = 0;
       CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, parted ? k_bicgstab3<true> : k_bicgstab3<false>, c->bicg_threads, 0));
-      if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); cfd_destroy(c); return CFD_ERR_CUDA; }
+      if (occ2 < 1) { set_error("k_bicgstab3 does not fit on an SM"); return CFD_ERR_CUDA; }
       const int needed2 = (int)std::max<long long>(1, ((long long)c->K.nslices * 32 + c->bicg_threads - 1) / c->bicg_threads);
       int blocks2 = c->numSMs * occ2;
       if (needed2 < blocks2) blocks2 = std::max(c->numSMs, ((needed2 + c->numSMs - 1) / c->numSMs) * c->numSMs);
@@ -3511,9 +3589,12 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                         }
                      }
                   }
-                  CFD_CK(cudaFuncSetAttribute((const void*)k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
+                  // recurrences: pipelined (one grid-wide barrier per iteration) unless CFD_PCG_RES_PIPE=0 asks for the single-reduction form (two)
+                  c->resPipe = !(getenv("CFD_PCG_RES_PIPE") && atoi(getenv("CFD_PCG_RES_PIPE")) == 0);
+                  const void* kres = c->resPipe ? (const void*)k_pcg_res<true> : (const void*)k_pcg_res<false>;
+                  CFD_CK(cudaFuncSetAttribute(kres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
                   int occR = 0;
-                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, (const void*)k_pcg_res, kResThreads, (size_t)maxBytes));
+                  CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, kres, kResThreads, (size_t)maxBytes));
                   if (occR >= 1) {
                      ResCta* dcta = nullptr;
                      TRY(dupload(c, &dcta, cta.data(), cta.size()));
@@ -3527,8 +3608,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                      c->resBytes = (size_t)maxBytes;
                      c->cg_variant = 2;   // (byte model of the iteration)
                      if (verb)
-                        fprintf(stderr, "[cfdb200 init] k_pcg_res: %d rows in %d row blocks, T = %d lanes per row, %.1f MB of values, at most %.1f KB of shared memory per CTA\n",
-                                n, nC, T, 8e-6 * (double)totalEntries, maxBytes / 1024.0);
+                        fprintf(stderr, "[cfdb200 init] k_pcg_res<%s>: %d rows in %d row blocks, T = %d lanes per row, %.1f MB of values, at most %.1f KB of shared memory per CTA\n",
+                                c->resPipe ? "pipelined" : "single reduction", n, nC, T, 8e-6 * (double)totalEntries, maxBytes / 1024.0);
                   }
                }
             }
@@ -3607,6 +3688,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
    c->P.sparseZrowStarts = nullptr; c->P.sparseZcol = nullptr; c->P.sparseZvalue = nullptr; c->P.sparseMapM_1d = nullptr;
    c->P.MdInv = c->P.MdOrigInv = nullptr; c->P.BCvelNodes = nullptr; c->P.BCstr = nullptr; c->P.U0 = c->P.P0 = nullptr;
    CFD_CK(cudaDeviceSynchronize());
+   guard.c = nullptr;
    *out = c;
    return CFD_OK;
 }
@@ -3791,11 +3873,21 @@ int cfd_get_fields(cfd_ctx* c, double* U, double* P) {
 // ------------------------------------------------------------------------------------------------
 // explicit seam
 // ------------------------------------------------------------------------------------------------
+// UnpHalf_prev <- Un, Pnp1_prev <- Pn, Acc_prev <- 0 (BCH.cpp:2866-2869) in one launch
+__global__ void __launch_bounds__(256) k_begin_step(long long n3, long long np, const double* __restrict__ Un, const double* __restrict__ Pn,
+                                                    double* __restrict__ UnpHalf_prev, double* __restrict__ Pnp1_prev, double* __restrict__ Acc_prev) {
+   const long long stride = (long long)gridDim.x * blockDim.x;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3; i += stride) {
+      UnpHalf_prev[i] = Un[i];
+      Acc_prev[i] = 0.0;
+      if (i < np) Pnp1_prev[i] = Pn[i];
+   }
+}
 int bch_beginTimeStep(cfd_ctx* c) {
-   const size_t N3 = 3 * (size_t)c->P.NN;
-   CFD_CK(cudaMemcpyAsync(c->UnpHalf_prev, c->Un, N3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-   CFD_CK(cudaMemcpyAsync(c->Pnp1_prev, c->Pn, c->P.NNp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-   CFD_CK(cudaMemsetAsync(c->Acc_prev, 0, N3 * sizeof(double), c->stream));
+   const long long N3 = 3LL * c->P.NN;
+   k_begin_step<<<std::min(gridFor(N3, 256), 8 * c->numSMs), 256, 0, c->stream>>>(N3, c->P.NNp, c->Un, c->Pn, c->UnpHalf_prev, c->Pnp1_prev, c->Acc_prev);
+   c->launches++;
+   CFD_CK(cudaGetLastError());
    return CFD_OK;
 }
 
@@ -3842,7 +3934,7 @@ int bch_step2GPU(cfd_ctx* c, int iter) {
    } else {
       ProfScope ps(c, "gt_rhs", spmv_bytes(c->GT, 3, 3, false));
       k_gt_rhs<<<gridFor((long long)c->GT.nslices * 32, 256), 256, 0, c->stream>>>(c->GT, NN, 0, c->UnpHalf, c->KtimesAcc_prev, iter != 1,
-                                                                                    c->MdOrigInv, 1.0 / (dt * dt), c->pin, c->R2);
+                                                                                    c->MdOrigInv, 1.0 / (dt * dt), c->pin, c->R2, c->scal);
       c->launches++;
       CFD_CK(cudaGetLastError());
    }
@@ -3850,7 +3942,7 @@ int bch_step2GPU(cfd_ctx* c, int iter) {
    if (rc) return rc;
    {
       ProfScope ps(c, "update", 40.0 * NNp);
-      CFD_CK(cudaMemsetAsync(c->scal, 0, 4 * sizeof(double), c->stream));
+      if (matrix_free(c)) CFD_CK(cudaMemsetAsync(c->scal, 0, 4 * sizeof(double), c->stream));   // (assembled path: zeroed by k_gt_rhs)
       k_pressure_update<<<std::min(gridFor(c->NPo, 256), 4 * c->numSMs), 256, 0, c->stream>>>(c->NPo, c->Pn, c->Pdot, c->Pnp1_prev, c->Pnp1, dt, c->scal);
       c->launches++;
       CFD_CK(cudaGetLastError());
@@ -3906,6 +3998,20 @@ int bch_rotateIterates(cfd_ctx* c) {
    CFD_CK(cudaMemcpyAsync(c->Acc_prev, c->Acc, N3, cudaMemcpyDeviceToDevice, c->stream));
    CFD_CK(cudaMemcpyAsync(c->Pnp1_prev, c->Pnp1, c->P.NNp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
    return CFD_OK;
+}
+
+// What cfd_timeLoop runs instead of the copies: the iterates rotate by exchanging buffers (every "current" array is rewritten
+// completely by the next inner iteration before anything reads it).  Not for callers that hold raw device pointers.
+static void rotate_iterates_by_swap(cfd_ctx* c) {
+   std::swap(c->UnpHalf_prev, c->UnpHalf);
+   std::swap(c->Unp1_prev, c->Unp1);
+   std::swap(c->Acc_prev, c->Acc);
+   std::swap(c->Pnp1_prev, c->Pnp1);
+}
+static void end_time_step_by_swap(cfd_ctx* c) {
+   std::swap(c->Un, c->Unp1);   // Un <- Unp1: the old Un buffer becomes the next Unp1, fully rewritten by step 3
+   std::swap(c->Pn, c->Pnp1);
+   c->timeN++;
 }
 
 int bch_calculate_KtimesAcc_prevGPU(cfd_ctx* c) {
@@ -4137,12 +4243,15 @@ int cfd_timeLoop(cfd_ctx* c, int nsteps, int stop_on_steady, cfd_step_report* re
             rep.cg_converged &= c->last_cg_conv;
             rep.cg_residual = std::max(rep.cg_residual, c->last_cg_res);
             if (conv) break;
-            if ((rc = bch_rotateIterates(c))) return rc;
+            // BCH.cpp:2929-2932.  Buffer exchange instead of four copies -- except after the LAST allowed iteration, where the loop
+            // ends right here and the newest iterate has to stay in Unp1 / Pnp1 (and in the *_prev arrays, as the reference leaves them)
+            if (iter < c->P.maxIter) rotate_iterates_by_swap(c);
+            else if ((rc = bch_rotateIterates(c))) return rc;
             if ((rc = bch_calculate_KtimesAcc_prevGPU(c))) return rc;
          }
          rep.iter = iter;
          if ((rc = bch_checkConvergenceInTimeGPU(c, &rep.steady, &rep.maxAcc))) return rc;
-         if ((rc = bch_endTimeStep(c))) return rc;
+         end_time_step_by_swap(c);   // BCH.cpp:3070-3071
       } else {
          if ((rc = gq_step1GPU(c))) return rc;
          if ((rc = gq_step2GPU(c))) return rc;

@@ -94,10 +94,9 @@ void assemble_step0(const Mesh& m, int scheme, Assembled& A, bool patternsOnly) 
    FeTables T;
    build_fe_tables(nv, T);
    const std::vector<int>* pidx = m.presIndex.empty() ? nullptr : &m.presIndex;
-   // patternsOnly (cfd_options.step0_device = 1): the device evaluates the element integrals and finds the entries by bisection, so
-   // only the patterns are built here -- plus the element -> entry map of the K / M / A pattern where the implicit scheme needs it
-   // for its per-step assembly
-   build_pattern(m, nv, nv, NN, NN, A.Mp, (patternsOnly && scheme == CFD_EXPLICIT) ? nullptr : &A.mapM);
+   // patternsOnly (cfd_options.step0_device = 1): the device evaluates the element integrals and finds the entries by bisection (the
+   // element -> entry map of the implicit scheme's per-step assembly included), so only the patterns are built here
+   build_pattern(m, nv, nv, NN, NN, A.Mp, patternsOnly ? nullptr : &A.mapM);
    const bool samePattern = (nv == 8 && !pidx);   // Q1/Q1 on a whole mesh: M, G and the FE-Laplacian Z share one pattern
    A.sharedG = samePattern;
    if (!samePattern) build_pattern(m, nv, 8, NN, NNp, A.GpOwn, patternsOnly ? nullptr : &A.mapGOwn, nullptr, pidx);

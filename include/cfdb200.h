@@ -172,15 +172,18 @@ int cfd_p2p_detach(cfd_ctx* ctx);
 
 /* named device vectors: "Un","Unp1","Unp1_prev","UnpHalf","UnpHalf_prev","Acc","Acc_prev",
  * "KtimesAcc_prev","R1","R2","R3","Pn","Pnp1","Pnp1_prev","Pdot" (explicit);
- * "Uk","Uk_prev","Pk","Pk_prev","Pk_prevprev","Pdiff","R1","R2","sparseAvalue" (implicit). */
+ * "Uk","Uk_prev","Pk","Pk_prev","Pk_prevprev","Pdiff","R1","R2" (implicit; plus "Adinv", download only: the Jacobi diagonal of the
+ * momentum matrix -- A itself is kept in the device layout, not in CSR order, and is not downloadable). */
 int cfd_download(cfd_ctx* ctx, const char* name, double* host, long long count);
 int cfd_upload(cfd_ctx* ctx, const char* name, const double* host, long long count);
 /* Raw device address of a named vector (names as above; NULL if unknown).  For host programs that -- like the reference's
  * own timeLoop under USECUDA (BCH.cpp:2866-2869, 2929-2932, 3070-3071, 3099-3100; GQ.cpp:3366-3368) -- move data between
  * iterates with their own cudaMemcpy calls on the `*_d` globals: integration/cfdb200_shim_*.cpp points those globals here.
- * Buffers are never re-allocated.  The seam functions the reference calls leave the addresses alone; gq_endTimeStep and
- * cfd_timeLoop (implicit) rotate Uk/Uk_prev and Pk/Pk_prev/Pk_prevprev by swapping buffers -- a caller that uses those
- * must fetch the pointers again afterwards.  Launch on the same stream (cfd_options.cuda_stream) or synchronise the device
+ * Buffers are never re-allocated.  The seam functions the reference calls leave the addresses alone (bch_rotateIterates and
+ * bch_endTimeStep copy, like BCH.cpp:2929-2932 / 3070-3071); gq_endTimeStep and cfd_timeLoop rotate the iterates by swapping
+ * buffers instead (implicit: Uk/Uk_prev, Pk/Pk_prev/Pk_prevprev; explicit: UnpHalf/UnpHalf_prev, Unp1/Unp1_prev, Acc/Acc_prev,
+ * Pnp1/Pnp1_prev between inner iterations, Un/Unp1 and Pn/Pnp1 at the end of a step) -- a caller that uses those must fetch the
+ * pointers again afterwards; the named download / upload calls always follow the current assignment.  Launch on the same stream (cfd_options.cuda_stream) or synchronise the device
  * between such copies and the seam calls, as the reference does (cudaThreadSynchronize). */
 void* cfd_device_pointer(cfd_ctx* ctx, const char* name);
 /* current velocity [3NN] and pressure [NNp] (Un/Pn or Uk_prev/Pk_prev after a completed step) */
