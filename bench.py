@@ -232,8 +232,9 @@ def main():
     ap.add_argument("--deterministic", type=int, default=0, help="cfd_options.deterministic")
     ap.add_argument("--path", default="csr", choices=["csr", "ebe"],
                     help="operator path of the explicit scheme: csr = assembled matrices (Sell SpMV), ebe = matrix-free element kernels (cfd_options.operator_path)")
-    ap.add_argument("--step0", default="host", choices=["host", "device"],
-                    help="set-up: host = step0 (element integrals, Z) on the host cores; device = on the GPU (cfd_options.step0_device)")
+    ap.add_argument("--step0", default="device", choices=["host", "device"],
+                    help="set-up: device (default on one GPU) = step0 (element integrals, Z, layout conversion) on the GPU (cfd_options.step0_device); "
+                         "host = on the host cores, as the library itself defaults to (partitioned runs always)")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
     sz = sizes(w)

@@ -1466,7 +1466,6 @@ struct PcgResArgs {
    const double* b;
    double* x;
    double* u;                    // the one vector other CTAs read: u = M^-1 r
-   double* u2;                   // pipelined form: second buffer for it (m = M^-1 w alternates between the two)
    const double* dinv;
    double* scratch;
    double* info;
@@ -1475,12 +1474,10 @@ struct PcgResArgs {
 };
 constexpr int kResThreads = 512;   // 16 warps, 128 registers per thread: room for the cached column ids
 constexpr int kResWarps = kResThreads / 32;
-// PIPE = true: pipelined recurrences (Ghysels-Vanroose): the dot products (r,u), (w,u), (r,r) use vectors that exist BEFORE the sweep of
-// the iteration, so their partials ride on the same grid-wide barrier that publishes m = M^-1 w for the sweep n = Z m -- ONE barrier per
-// iteration instead of two.  Same iterates as classical PCG in exact arithmetic (x, r, u = M^-1 r, w = Z u, and the search directions
-// p, s = Z p, q = M^-1 s, z = Z q are all advanced by recurrences in registers); the stopping test sees |r_i| after i updates, like
-// the classical kernel, so the iteration counts agree.
-template <bool PIPE>
+// (A pipelined form -- Ghysels-Vanroose recurrences, the dot-product partials riding on the barrier that publishes the vector: ONE
+// grid-wide barrier per iteration -- was built and measured: 361 against 366 steps/s on the shipped mesh, because the wait at the
+// reduction is the wait for the slowest sweep, not the barrier itself; and at a tolerance of 1e-12 its iteration counts leave the +-5
+// window of the tight reference fixtures (recurrence drift).  Removed.)
 __global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
    cg::grid_group grid = cg::this_grid();
    extern __shared__ double zs[];   // values | staged vector entries | this CTA's rows of w = Z u
@@ -1581,37 +1578,6 @@ __global__ void __launch_bounds__(kResThreads, 1) k_pcg_res(PcgResArgs a) {
    }
    ui = di * ri;
    if (own) a.u[row] = ui;
-   if (PIPE) {
-      grid.sync();
-      sweep(a.u);
-      if (own) wi = wrow[threadIdx.x];
-      double zi = 0.0, qi = 0.0, gammaOld = 1.0, alpha = 1.0, rr = 0.0, bb = 0.0, thresh = 0.0;
-      int it = 0;
-      while (true) {
-         // (iteration 0 writes m into u2: a slower CTA may still be staging u for its first sweep; from then on the barrier of
-         //  iteration i-1 guarantees that nobody reads the buffer iteration i writes)
-         double* mb = (it & 1) ? a.u : a.u2;
-         const double mi = di * wi;
-         if (own) mb[row] = mi;
-         double v4[4] = {ri * ui, wi * ui, ri * ri, bi * bi};
-         grid_sum<4>(grid, v4, (it & 1) ? buf0 + 4 * (size_t)gridDim.x : buf0, sh);   // the one barrier: publishes m as well
-         const double gamma = v4[0], delta = v4[1];
-         rr = v4[2];
-         if (it == 0) { bb = v4[3]; thresh = a.tol * sqrt(bb); }
-         if (sqrt(rr) <= thresh || it >= a.maxit) break;
-         sweep(mb);
-         const double ni = own ? wrow[threadIdx.x] : 0.0;
-         double beta = 0.0;
-         if (it > 0) { beta = gamma / gammaOld; alpha = gamma / (delta - beta * gamma / alpha); } else alpha = gamma / delta;
-         zi = ni + beta * zi; qi = mi + beta * qi; si = wi + beta * si; pi = ui + beta * pi;
-         xi += alpha * pi; ri -= alpha * si; ui -= alpha * qi; wi -= alpha * zi;
-         gammaOld = gamma;
-         it++;
-      }
-      if (own) a.x[row] = xi;
-      if (blockIdx.x == 0 && threadIdx.x == 0) { a.info[0] = (double)it; a.info[1] = rr; a.info[2] = bb; }
-      return;
-   }
    double v4[4] = {ri * ui, 0.0, ri * ri, bi * bi};
    grid.sync();
    sweep(a.u);
@@ -2764,13 +2730,12 @@ int run_pcg(cfd_ctx* c, const double* b, double* x, bool x0zero) {
    if (c->resBytes > 0) {   // small system: row blocks resident per CTA (values in shared memory, vectors in registers)
       PcgResArgs ra;
       ra.cta = (const ResCta*)c->resCta; ra.vals = c->resVals; ra.idx = c->resIdx; ra.cols = c->resCols; ra.grp = c->resGrp; ra.T = c->resT;
-      ra.n = c->P.NNp; ra.b = b; ra.x = x; ra.u = c->cg_p; ra.u2 = c->cg_q; ra.dinv = c->Zdinv; ra.scratch = c->partials; ra.info = c->kinfo;
+      ra.n = c->P.NNp; ra.b = b; ra.x = x; ra.u = c->cg_p; ra.dinv = c->Zdinv; ra.scratch = c->partials; ra.info = c->kinfo;
       ra.tol = c->opt.cg_tol; ra.maxit = c->opt.cg_maxit; ra.x0zero = x0zero ? 1 : 0;
       void* rargs[] = {&ra};
       ProfScope ps(c, "pcg", spmv_bytes(c->Z, 1, 1, false) + (x0zero ? Bytes(0.0) : spmv_bytes(c->Z, 1, 1, false)));
       c->lastPcgRec = ps.idx;
-      CFD_CK(cudaLaunchCooperativeKernel(c->resPipe ? (void*)k_pcg_res<true> : (void*)k_pcg_res<false>, dim3(c->numSMs), dim3(kResThreads), rargs,
-                                         c->resBytes, c->stream));
+      CFD_CK(cudaLaunchCooperativeKernel((void*)k_pcg_res, dim3(c->numSMs), dim3(kResThreads), rargs, c->resBytes, c->stream));
       c->launches++;
       return CFD_OK;
    }
@@ -3589,9 +3554,7 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                         }
                      }
                   }
-                  // recurrences: pipelined (one grid-wide barrier per iteration) unless CFD_PCG_RES_PIPE=0 asks for the single-reduction form (two)
-                  c->resPipe = !(getenv("CFD_PCG_RES_PIPE") && atoi(getenv("CFD_PCG_RES_PIPE")) == 0);
-                  const void* kres = c->resPipe ? (const void*)k_pcg_res<true> : (const void*)k_pcg_res<false>;
+                  const void* kres = (const void*)k_pcg_res;
                   CFD_CK(cudaFuncSetAttribute(kres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxBytes));
                   int occR = 0;
                   CFD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, kres, kResThreads, (size_t)maxBytes));
@@ -3608,8 +3571,8 @@ int cfd_initializeAndAllocateGPU(const cfd_problem* P, const cfd_options* opt, c
                      c->resBytes = (size_t)maxBytes;
                      c->cg_variant = 2;   // (byte model of the iteration)
                      if (verb)
-                        fprintf(stderr, "[cfdb200 init] k_pcg_res<%s>: %d rows in %d row blocks, T = %d lanes per row, %.1f MB of values, at most %.1f KB of shared memory per CTA\n",
-                                c->resPipe ? "pipelined" : "single reduction", n, nC, T, 8e-6 * (double)totalEntries, maxBytes / 1024.0);
+                        fprintf(stderr, "[cfdb200 init] k_pcg_res: %d rows in %d row blocks, T = %d lanes per row, %.1f MB of values, at most %.1f KB of shared memory per CTA\n",
+                                n, nC, T, 8e-6 * (double)totalEntries, maxBytes / 1024.0);
                   }
                }
             }

@@ -143,7 +143,6 @@ struct cfd_ctx {
    unsigned short* resIdx = nullptr;
    int *resCols = nullptr, *resGrp = nullptr;
    int resT = 0;
-   bool resPipe = true;         // pipelined recurrences (one barrier per iteration)
    size_t resBytes = 0;
    std::vector<long long> hostOffZ, hostOffK;     // host copies of the slice offsets (partitioning)
    // bookkeeping
