@@ -27,8 +27,9 @@ WORKLOADS = {
     "cavity128_q1_implicit": dict(n=128, NENv=8, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity128_q1_explicit": dict(n=128, NENv=8, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity64_q2_explicit": dict(n=64, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
-    "cavity96_q2_explicit": dict(n=96, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
-    "cavity128_q2_explicit": dict(n=128, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=1e-3),
+    # (explicit viscous term: dt below h^2 / (6 nu) with h = the Q2 node spacing -- 1e-3 blows up on these two meshes)
+    "cavity96_q2_explicit": dict(n=96, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=2.5e-4),
+    "cavity128_q2_explicit": dict(n=128, NENv=27, scheme="explicit", cluster=0.0, viscosity=0.01, dt=2e-4),
     "cavity128_q2_implicit": dict(n=128, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     "cavity64_q2_implicit": dict(n=64, NENv=27, scheme="implicit", cluster=0.0, viscosity=0.01, dt=1e-3),
     # configs[0] / configs[1]: the shipped lidDrivenCavity_NE27000.inp (30^3 Q2/Q1, sinh clustering 2.0)
