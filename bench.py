@@ -435,6 +435,9 @@ def main():
                                    "dram__bytes per launch from the committed capture (profiles/traffic.json)"),
                 cg_gdof_iter_per_s=(sz["NNp"] * cg_its / (cg_ms * 1e-3) / 1e9) if cg_ms > 0 else None,
                 kernels=kernels)
+    if dom == "pcg" and world == 1 and 0 < mb["Z"] <= 33.0:
+        line["roofline"]["resident"] = ("pressure matrix (%.0f MB) resident in the SMs' shared memory for the whole solve (k_pcg_res): DRAM traffic per solve = one read "
+                                        "of the matrix (`traffic`), so `achieved` is what a streaming kernel would have had to sustain, not HBM traffic" % mb["Z"])
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(w, 3, 1)
     print(json.dumps(line))

@@ -510,6 +510,8 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    }
    if (world > s->mesh.NE) { set_error("%d ranks for %d elements: an element block per rank needs world <= NE", world, s->mesh.NE); return CFD_ERR_ARG; }
    if (opt) s->opt = *opt; else cfd_default_options(&s->opt);
+   // the thread count chosen below is for this set-up only: the caller's OpenMP setting is put back on every way out
+   struct ThreadsBack { int n; ~ThreadsBack() { omp_set_num_threads(n); } } threadsBack{omp_get_max_threads()};
    {
       // one process per GPU: launchers such as torchrun pin OMP_NUM_THREADS=1; give each rank its share of the cores
       int want = 0;
