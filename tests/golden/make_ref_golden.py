@@ -66,6 +66,12 @@ CASES = {
     # mass matrix, 8 Gauss points, GQ.cpp:3490-3500) lets BiCGStab stagnate -- two correct implementations that both report
     # 1e-10 differ by 4e-4 in the free velocities -- so forcing the tolerance down pins nothing.
     "ref_gq_ne27000": ("implicit", "cube", dict(n=30, cluster=2.0, viscosity=0.001, converge=NEVER_STEADY), 2, {}, 61),
+    # the duct stand-in with a prescribed outflow (meshgen.duct): inlet AND outlet faces carry the plug profile -- the configs[2]
+    # stand-in on which the reference's implicit scheme settles (the free-outlet channel above blows up from the third step on:
+    # its three-step fixture ends just before).  Five steps: the fields have settled by then.
+    "ref_bch_duct644": ("explicit", "duct", dict(nx=6, ny=4, nz=4), 4, {}, 1),
+    "ref_gq_duct644_tight": ("implicit", "duct", dict(nx=6, ny=4, nz=4, converge=NEVER_STEADY), 5, TIGHT, 1),
+    "ref_gq_duct1288_tight": ("implicit", "duct", dict(nx=12, ny=8, nz=8, converge=NEVER_STEADY), 4, TIGHT, 1),
 }
 
 

@@ -26,7 +26,11 @@ SMALL = ["ref_bch_cav4", "ref_bch_cav6c", "ref_bch_chan644", "ref_gq_cav4", "ref
          "ref_gq_chan644_tight", "ref_bch_box345_nopin", "ref_bch_cav4_pin1_it1", "ref_gq_box345_nopin_tight"]
 FULL = ["ref_bch_ne27000", "ref_gq_ne27000"]
 # added after the round's GPU budget was spent: checked against the oracle here, against the CUDA path from round 2 on
-CPU_ONLY = ["ref_bch_cav8c_20steps", "ref_bch_chan483232"]
+CPU_ONLY = ["ref_bch_cav8c_20steps", "ref_bch_chan483232",
+            # duct stand-in with a prescribed outflow (meshgen.duct): written by the reference programs at the end of round 2, after the
+            # GPU budget was spent -- the oracle is pinned against them here; the CUDA path meets the oracle on the same case in
+            # tests/test_gpu_parity.py::test_duct_standin_implicit
+            "ref_bch_duct644", "ref_gq_duct644_tight", "ref_gq_duct1288_tight"]
 
 
 def load(name):
