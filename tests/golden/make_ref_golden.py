@@ -72,6 +72,9 @@ CASES = {
     "ref_bch_duct644": ("explicit", "duct", dict(nx=6, ny=4, nz=4), 4, {}, 1),
     "ref_gq_duct644_tight": ("implicit", "duct", dict(nx=6, ny=4, nz=4, converge=NEVER_STEADY), 5, TIGHT, 1),
     "ref_gq_duct1288_tight": ("implicit", "duct", dict(nx=12, ny=8, nz=8, converge=NEVER_STEADY), 4, TIGHT, 1),
+    # (no full-size 48 x 32 x 32 implicit twin: at the reference's own 1e-6 the oracle reproduces that run to 9.4e-4 / 8.1e-7 only -- the
+    #  floor of the comparison on this matrix, DESIGN.md section 2 -- and forced to 1e-12 the reference's BiCGStab runs into its hard-coded
+    #  cap of 1000 iterations in the second step, so neither setting pins anything at that size)
 }
 
 
