@@ -530,12 +530,28 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    s->globalNN = s->mesh.NN; s->globalNNp = s->mesh.NNp; s->globalNE = s->mesh.NE;
    if (world > 1) {
       if (world > 64 || rank < 0 || rank >= world) { set_error("bad partition %d/%d", rank, world); return CFD_ERR_ARG; }
-      if (s->mesh.isRestart == 1) { set_error("restart files are not supported on partitioned runs"); return CFD_ERR_ARG; }
+      // restart (readRestartFile, BCH.cpp:4214-4242) on a partition: every rank reads the one restart file of the WHOLE mesh before
+      // the mesh is cut, and keeps the rows of its own nodes (owned and ghost) below
+      std::vector<double> Ug, Pg;
+      const bool restart = s->mesh.isRestart == 1 && !restartPath.empty();
+      if (restart) {
+         Ug.assign((size_t)3 * s->mesh.NN, 0.0); Pg.assign((size_t)s->mesh.NNp, 0.0);
+         if (!read_restart(s->mesh, restartPath, Ug.data(), Pg.data())) return CFD_ERR_IO;
+      }
+      const size_t NNg = (size_t)s->mesh.NN;
       Mesh local;
       // explicit: rows of Z = G^T Md^-1 G reach two element layers; implicit: one
       partition_mesh(s->mesh, world, rank, scheme == CFD_EXPLICIT ? 2 : 1, local, s->part);
       s->mesh = std::move(local);
       s->partitioned = true;
+      if (restart) {
+         const size_t NNl = s->part.nodeGlobal.size(), NPl = s->part.presGlobal.size();
+         s->U0.assign(3 * NNl, 0.0); s->P0.assign(NPl, 0.0);
+         for (size_t i = 0; i < NNl; i++)
+            for (int d = 0; d < 3; d++) s->U0[(size_t)d * NNl + i] = Ug[(size_t)d * NNg + (size_t)s->part.nodeGlobal[i]];
+         for (size_t i = 0; i < NPl; i++) s->P0[i] = Pg[(size_t)s->part.presGlobal[i]];
+         s->mesh.isRestart = 0;   // (already applied: the block further down reads the file of a whole mesh)
+      }
    }
    Mesh& m = s->mesh;
    const bool dev0 = s->opt.step0_device == 1;
@@ -583,8 +599,8 @@ int finish_create(cfd_solver* s, int scheme, const cfd_options* opt, const std::
    if (m.isRestart == 1 && !restartPath.empty()) {
       s->U0.assign((size_t)3 * m.NN, 0.0); s->P0.assign((size_t)m.NNp, 0.0);
       if (!read_restart(m, restartPath, s->U0.data(), s->P0.data())) return CFD_ERR_IO;
-      P.U0 = s->U0.data(); P.P0 = s->P0.data();
    }
+   if (!s->U0.empty()) { P.U0 = s->U0.data(); P.P0 = s->P0.data(); }
    s->timeT = m.t_ini;
    if (!init_gpu) return CFD_OK;
    return cfd_initializeAndAllocateGPU(&P, &s->opt, &s->ctx);
@@ -629,7 +645,10 @@ int cfd_solver_create_from_inp_part(const char* inp_path, int scheme, const cfd_
    *out = nullptr;
    cfd_solver* s = new cfd_solver();
    if (!read_inp(inp_path, s->mesh)) { delete s; return CFD_ERR_IO; }
-   int rc = finish_create(s, scheme, opt, "", init_gpu, world, rank);
+   std::string base(inp_path);
+   const size_t dot = base.rfind(".inp");
+   if (dot != std::string::npos) base = base.substr(0, dot);
+   int rc = finish_create(s, scheme, opt, base + "_restart.dat", init_gpu, world, rank);
    if (rc) { delete s; return rc; }
    *out = s;
    return CFD_OK;
@@ -688,6 +707,7 @@ const void* cfd_solver_array(cfd_solver* s, const char* name, long long* count, 
    IV("part_nodeGlobal", s->part.nodeGlobal) IV("part_presGlobal", s->part.presGlobal) IV("part_elemGlobal", s->part.elemGlobal)
    IV("peerRank", s->peerRank) IV("sendVptr", s->sendVptr) IV("sendVidx", s->sendVidx) IV("recvVoff", s->recvVoff) IV("recvVcnt", s->recvVcnt)
    IV("remoteVoff", s->remoteVoff) IV("remotePoff", s->remotePoff) IV("sendPptr", s->sendPptr) IV("sendPidx", s->sendPidx) IV("recvPoff", s->recvPoff) IV("recvPcnt", s->recvPcnt)
+   DV("U0", s->U0) DV("P0", s->P0)
    DV("coord", m.coord) IV("LtoGnode", m.LtoGnode) IV("BCvelNodes", m.BCvelNodes) DV("BCstr", m.BCstr)
    IV("sparseMrowStarts", A.Mp.rowStarts) IV("sparseMcol", A.Mp.col) IV("sparseGrowStarts", A.Gp().rowStarts) IV("sparseGcol", A.Gp().col)
    IV("sparseZrowStarts", A.Zp().rowStarts) IV("sparseZcol", A.Zp().col) IV("sparseMapM_1d", A.mapM) IV("sparseMapG_1d", A.mapG())

@@ -146,3 +146,39 @@ def test_halo_exchange_gloo(world, scheme, cav):
     for p in procs:
         p.join(60)
     assert all(m == "ok" for _, m in res), res
+
+
+@pytest.mark.parametrize("scheme", ["explicit", "implicit"])
+def test_restart_file_on_a_partition(mesh, tmp_path, scheme):
+    """isRestart 1 on a partitioned run (readRestartFile, BCH.cpp:4214-4242): every rank reads the restart file of the whole mesh and
+    keeps the rows of its own nodes -- owned and ghost -- in its local numbering; pressure from the corner-node rows."""
+    import shutil
+    import fracstep
+    import meshgen
+    base = str(tmp_path / "case")
+    meshgen.cube(base + ".inp", 4, cluster=2.0, is_restart=1)
+    plain = str(tmp_path / "plain.inp")
+    meshgen.cube(plain, 4, cluster=2.0)
+    g = fracstep.Solver(plain, scheme, init_gpu=False)
+    NN, NNp = g.i("NN"), g.i("NNp")
+    rng = np.random.default_rng(3)
+    U, P = rng.standard_normal(3 * NN), rng.standard_normal(NNp)
+    g.write_tecplot_fields(base + "_restart.dat", "restart", U, P)
+    Ur, Pr = g.read_restart_fields(base + "_restart.dat")          # what the file holds (11 significant digits)
+    g.close()
+    for world in (2, 3):
+        seen = np.zeros(NN, dtype=bool)
+        for rank in range(world):
+            s = fracstep.Solver(base + ".inp", scheme, world=world, rank=rank, init_gpu=False)
+            ng, pg = s.arr("part_nodeGlobal"), s.arr("part_presGlobal")
+            U0, P0 = s.arr("U0"), s.arr("P0")
+            assert len(U0) == 3 * len(ng) and len(P0) == len(pg)
+            assert np.array_equal(U0.reshape(3, -1), Ur.reshape(3, NN)[:, ng])
+            assert np.array_equal(P0, Pr[pg])
+            seen[ng] = True
+            s.close()
+        assert seen.all()
+    # and a whole-mesh solver still reads it the old way
+    w = fracstep.Solver(base + ".inp", scheme, init_gpu=False)
+    assert np.array_equal(w.arr("U0"), Ur) and np.array_equal(w.arr("P0"), Pr)
+    w.close()
